@@ -1,0 +1,622 @@
+// ctrb_api.cu -- the C ABI of libctrb200.so (include/ctrb200.h): handles, staging of host
+// buffers, kernel launch sequencing.  There is deliberately no CPU fallback anywhere: without
+// a CUDA device every compute entry point fails with CTRB_ERR_NO_DEVICE / CTRB_ERR_CUDA.
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#include "ctrb_internal.cuh"
+
+namespace ctrb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int ctx_scratch(ctrb_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            // stream-ordered: earlier kernels on ctx->stream may still read the old buffer
+            CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
+            CTRB_CUDA(cudaStreamSynchronize(ctx->stream2));
+            CTRB_CUDA(cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        size_t cap = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], cap);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+            return CTRB_ERR_ALLOC;
+        }
+        ctx->scratch_bytes[slot] = cap;
+    }
+    *out = ctx->scratch[slot];
+    return CTRB_OK;
+}
+
+// launchers implemented in ctrb_model.cu / ctrb_collide.cu
+int launch_table(ctrb_ctx* ctx, const ctrb_model* m);
+int launch_gcurve(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_t* idx, const double* theta, int full,
+                  int precision, const long long* offsets, void* out);
+int launch_calc_indices(ctrb_ctx* ctx, const ctrb_model* m, long long B, const double* prev_ins, const double* next_ins,
+                        int32_t* prev_idx, int32_t* new_idx);
+int launch_offsets(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_t* idx, int full, long long* offsets);
+int launch_eta_ftl(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_t* prev_idx, const int32_t* new_idx,
+                   const double* velocity, const double* delta_theta, const double* prev_g, const long long* prev_off, double* eta_out,
+                   double* ftl_out, double* ftl_mag, int* err_flag);
+int launch_eval_fused(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, const ctrb_cost_desc* cd, long long B,
+                      const int32_t* idx, const double* theta, const double* rad, double* obstacle_min,
+                      double* goal_dist, double* cost, uint8_t* collide);
+int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube_num, const double* g,
+                       const long long* offsets, int max_nodes, const double* rad, double* obstacle_min,
+                       double* goal_dist);
+int launch_argmin(ctrb_ctx* ctx, long long B, const double* cost, unsigned long long* key_out);
+
+}  // namespace ctrb
+
+using namespace ctrb;
+
+// ------------------------------------------------------------------ staging helpers for CTRB_MEM_HOST
+namespace {
+struct Stage {
+    ctrb_ctx* ctx;
+    int slot;
+    int rc;
+    explicit Stage(ctrb_ctx* c) : ctx(c), slot(1), rc(CTRB_OK) {}
+    // device buffer holding a copy of host data
+    template <typename T>
+    const T* in(const T* host, size_t count, int mem) {
+        if (mem == CTRB_MEM_DEVICE || rc) return host;
+        void* d = nullptr;
+        rc = ctx_scratch(ctx, slot++, count * sizeof(T), &d);
+        if (rc) return nullptr;
+        if (cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = CTRB_ERR_CUDA;
+        }
+        return (const T*)d;
+    }
+    template <typename T>
+    T* out(T* host, size_t count, int mem) {
+        if (mem == CTRB_MEM_DEVICE || rc || host == nullptr) return host;
+        void* d = nullptr;
+        rc = ctx_scratch(ctx, slot++, count * sizeof(T), &d);
+        return (T*)d;
+    }
+    template <typename T>
+    void back(T* host, const T* dev, size_t count, int mem) {
+        if (mem == CTRB_MEM_DEVICE || rc || host == nullptr) return;
+        if (cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) {
+            set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = CTRB_ERR_CUDA;
+        }
+    }
+    int finish(int mem) {
+        if (rc) return rc;
+        if (mem == CTRB_MEM_HOST) {
+            CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        return CTRB_OK;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+const char* ctrb_last_error(void) { return g_err; }
+const char* ctrb_version(void) { return "ctrb200 0.1 (sm_100a)"; }
+
+int ctrb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ ctx
+int ctrb_ctx_create(int device, ctrb_ctx** out) {
+    CTRB_REQUIRE(out != nullptr, "ctrb_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = ctrb_device_count();
+    if (n <= 0) {
+        set_error("no CUDA device: libctrb200 has no CPU fallback");
+        return CTRB_ERR_NO_DEVICE;
+    }
+    CTRB_REQUIRE(device >= 0 && device < n, "device %d out of range (0..%d)", device, n - 1);
+    CTRB_CUDA(cudaSetDevice(device));
+    ctrb_ctx* c = new ctrb_ctx();
+    std::memset(c, 0, sizeof *c);
+    c->device = device;
+    CTRB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CTRB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CTRB_CUDA(cudaEventCreate(&c->ev[i]));
+        CTRB_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+    }
+    CTRB_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+    CTRB_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
+    cudaDeviceProp prop;
+    CTRB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; libctrb200 is built for sm_100a only", device, prop.major, prop.minor);
+        delete c;
+        return CTRB_ERR_NO_DEVICE;
+    }
+    *out = c;
+    return CTRB_OK;
+}
+
+void ctrb_ctx_destroy(ctrb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream2);
+    for (int i = 0; i < 12; ++i)
+        if (c->scratch[i]) cudaFree(c->scratch[i]);
+    cudaFree(c->d_counters);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(c->ev[i]);
+        cudaEventDestroy(c->ev_chunk[i]);
+    }
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->stream2);
+    delete c;
+}
+
+int ctrb_ctx_synchronize(ctrb_ctx* c) {
+    CTRB_REQUIRE(c, "ctx is NULL");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaStreamSynchronize(c->stream));
+    CTRB_CUDA(cudaStreamSynchronize(c->stream2));
+    return CTRB_OK;
+}
+
+int64_t ctrb_ctx_launch_count(const ctrb_ctx* c) { return c ? c->launches : 0; }
+
+int ctrb_ctx_mark(ctrb_ctx* c, int which) {
+    CTRB_REQUIRE(c && (which == 0 || which == 1), "ctrb_ctx_mark: bad argument");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaEventRecord(c->ev[which], c->stream));
+    return CTRB_OK;
+}
+
+int ctrb_ctx_elapsed_ms(ctrb_ctx* c, float* ms) {
+    CTRB_REQUIRE(c && ms, "ctrb_ctx_elapsed_ms: bad argument");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaEventSynchronize(c->ev[1]));
+    CTRB_CUDA(cudaEventElapsedTime(ms, c->ev[0], c->ev[1]));
+    return CTRB_OK;
+}
+
+int ctrb_ctx_work_counters(ctrb_ctx* c, uint64_t out[4]) {
+    CTRB_REQUIRE(c && out, "ctrb_ctx_work_counters: bad argument");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long h[8];
+    CTRB_CUDA(cudaMemcpy(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out[i] = h[i];
+    return CTRB_OK;
+}
+
+// ------------------------------------------------------------------ model
+static int check_dof(int kind, int dof) {  // strain_bases.py:316-351
+    switch (kind) {
+        case CTRB_BASE_CONSTANT: return dof == 1;
+        case CTRB_BASE_LINEAR:
+        case CTRB_BASE_QUADRATIC: return dof >= 2 && dof <= 3;
+        case CTRB_BASE_PURE_HELIX:
+        case CTRB_BASE_LINEAR_HELIX: return dof == 2;
+        case CTRB_BASE_TORSION_HELIX:
+        case CTRB_BASE_TORSION_LINEAR_HELIX: return dof == 3;
+        case CTRB_BASE_FULL: return dof >= 5 && dof <= 8;
+        default: return 0;
+    }
+}
+
+int ctrb_model_create(ctrb_ctx* ctx, const ctrb_model_desc* d, ctrb_model** out) {
+    CTRB_REQUIRE(ctx && d && out, "ctrb_model_create: NULL argument");
+    *out = nullptr;
+    CTRB_REQUIRE(d->tube_num >= 1 && d->tube_num <= CTRB_MAX_TUBES, "tube_num %d not in 1..%d", d->tube_num, CTRB_MAX_TUBES);
+    CTRB_REQUIRE(d->delta_x > 0.0, "delta_x must be positive");
+    if (d->model_type == CTRB_MODEL_STATIC) {
+        set_error("the static model is not built yet in this library version");
+        return CTRB_ERR_UNSUPPORTED;
+    }
+    CTRB_REQUIRE(d->model_type == CTRB_MODEL_KINEMATIC, "unknown model_type %d", d->model_type);
+    ctrb_model* m = new ctrb_model();
+    std::memset(m, 0, sizeof *m);
+    m->desc = *d;
+    m->device = ctx->device;
+    ModelConst& mc = m->mc;
+    mc.T = d->tube_num;
+    mc.dx = d->delta_x;
+    int tot = 0;
+    for (int n = 0; n < mc.T; ++n) {
+        if (!check_dof(d->base_kind[n], d->q_dof[n])) {
+            set_error("strain base %d should not have %d degrees of freedom", d->base_kind[n], d->q_dof[n]);
+            delete m;
+            return CTRB_ERR_INVALID;
+        }
+        mc.kind[n] = d->base_kind[n];
+        mc.dof[n] = d->q_dof[n];
+        for (int k = 0; k < CTRB_MAX_DOF; ++k) mc.q[n][k] = k < d->q_dof[n] ? d->q[n][k] : 0.0;
+        mc.L[n] = d->tube_length[n];
+        mc.npts[n] = (int)std::nearbyint(d->tube_length[n] / d->delta_x) + 1;  // model.py:37-38 (round half even)
+        if (mc.npts[n] < 1) {
+            set_error("tube %d has no discrete points", n);
+            delete m;
+            return CTRB_ERR_INVALID;
+        }
+        mc.node_base[n] = tot;
+        tot += mc.npts[n];
+    }
+    mc.total_nodes = tot;
+    CTRB_CUDA(cudaSetDevice(ctx->device));
+    CTRB_CUDA(cudaMalloc(&m->d_tab, (size_t)12 * tot * sizeof(double)));
+    CTRB_CUDA(cudaMalloc(&m->d_tab_inv, (size_t)12 * tot * sizeof(double)));
+    CTRB_CUDA(cudaMalloc(&m->d_tabR32, (size_t)9 * tot * sizeof(float)));
+    int rc = launch_table(ctx, m);
+    if (rc) {
+        ctrb_model_destroy(m);
+        return rc;
+    }
+    CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = m;
+    return CTRB_OK;
+}
+
+void ctrb_model_destroy(ctrb_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_tab);
+    cudaFree(m->d_tab_inv);
+    cudaFree(m->d_tabR32);
+    delete m;
+}
+
+int ctrb_model_num_points(const ctrb_model* m, int32_t* npts) {
+    CTRB_REQUIRE(m && npts, "ctrb_model_num_points: NULL argument");
+    for (int n = 0; n < m->mc.T; ++n) npts[n] = m->mc.npts[n];
+    return CTRB_OK;
+}
+
+// ------------------------------------------------------------------ env
+static int upload_bvh(const HostBvh& hb, DevBvh* db, void** d_nodes, void** d_tri32, void** d_tri64) {
+    std::memset(db, 0, sizeof *db);
+    *d_nodes = *d_tri32 = *d_tri64 = nullptr;
+    if (hb.ntri <= 0) return CTRB_OK;
+    CTRB_CUDA(cudaMalloc(d_nodes, hb.nodes.size() * sizeof(BvhNode)));
+    CTRB_CUDA(cudaMalloc(d_tri32, hb.tri32.size() * sizeof(float)));
+    CTRB_CUDA(cudaMalloc(d_tri64, hb.tri64.size() * sizeof(double)));
+    CTRB_CUDA(cudaMemcpy(*d_nodes, hb.nodes.data(), hb.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+    CTRB_CUDA(cudaMemcpy(*d_tri32, hb.tri32.data(), hb.tri32.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CTRB_CUDA(cudaMemcpy(*d_tri64, hb.tri64.data(), hb.tri64.size() * sizeof(double), cudaMemcpyHostToDevice));
+    db->nodes = (const BvhNode*)*d_nodes;
+    db->tri32 = (const float4*)*d_tri32;
+    db->tri64 = (const double*)*d_tri64;
+    db->nnodes = (int)hb.nodes.size();
+    db->ntri = hb.ntri;
+    db->slack = hb.slack;
+    return CTRB_OK;
+}
+
+static void copy_prim(const ctrb_prim& s, DevPrim* d) {
+    d->shape = s.shape;
+    for (int k = 0; k < 3; ++k) {
+        d->center[k] = s.center[k];
+        d->dims[k] = s.dims[k];
+    }
+    for (int k = 0; k < 9; ++k) d->rot[k] = s.rot[k];
+}
+
+int ctrb_env_create(ctrb_ctx* ctx, const double* obstacle_tris, int32_t n_obs, const ctrb_prim* prims, int32_t n_prims,
+                    const ctrb_prim* goal, const double* goal_tris, int32_t n_goal, ctrb_env** out) {
+    CTRB_REQUIRE(ctx && out, "ctrb_env_create: NULL argument");
+    *out = nullptr;
+    CTRB_REQUIRE(n_obs >= 0 && n_goal >= 0 && n_prims >= 0, "negative count");
+    CTRB_REQUIRE(n_obs == 0 || obstacle_tris, "obstacle_tris is NULL");
+    CTRB_REQUIRE(n_prims == 0 || prims, "prims is NULL");
+    CTRB_REQUIRE(n_prims <= kMaxPrims, "at most %d primitive obstacles are supported", kMaxPrims);
+    for (int i = 0; i < n_prims; ++i) {
+        if (prims[i].shape != CTRB_SHAPE_SPHERE && prims[i].shape != CTRB_SHAPE_BOX) {
+            // the reference accepts Cylinder obstacles (init_collision.py:131-135); the exact solid
+            // cylinder <-> solid cylinder distance is not built yet
+            set_error("obstacle shape %d not supported (Sphere and Box are)", prims[i].shape);
+            return CTRB_ERR_UNSUPPORTED;
+        }
+    }
+    if (goal && goal->shape == CTRB_SHAPE_MESH) CTRB_REQUIRE(n_goal > 0 && goal_tris, "mesh goal without triangles");
+    CTRB_CUDA(cudaSetDevice(ctx->device));
+    ctrb_env* e = new ctrb_env();
+    std::memset(e, 0, sizeof *e);
+    e->device = ctx->device;
+    HostBvh hb, hg;
+    build_bvh(obstacle_tris, n_obs, &hb);
+    build_bvh(goal_tris, goal && goal->shape == CTRB_SHAPE_MESH ? n_goal : 0, &hg);
+    if (hb.depth > 44 || hg.depth > 44) {
+        set_error("BVH too deep (%d) for the traversal stack", std::max(hb.depth, hg.depth));
+        delete e;
+        return CTRB_ERR_UNSUPPORTED;
+    }
+    int rc = upload_bvh(hb, &e->ec.obs, &e->d_nodes[0], &e->d_tri32[0], &e->d_tri64[0]);
+    if (!rc) rc = upload_bvh(hg, &e->ec.goal_mesh, &e->d_nodes[1], &e->d_tri32[1], &e->d_tri64[1]);
+    if (rc) {
+        ctrb_env_destroy(e);
+        return rc;
+    }
+    e->ec.nprim = n_prims;
+    for (int i = 0; i < n_prims; ++i) copy_prim(prims[i], &e->ec.prims[i]);
+    if (goal) copy_prim(*goal, &e->ec.goal);
+    else e->ec.goal.shape = CTRB_SHAPE_NONE;
+    CTRB_CUDA(cudaMalloc(&e->d_ec, sizeof(EnvConst)));
+    CTRB_CUDA(cudaMemcpy(e->d_ec, &e->ec, sizeof(EnvConst), cudaMemcpyHostToDevice));
+    e->stats[0] = (int32_t)hb.nodes.size();
+    e->stats[1] = hb.nleaves;
+    e->stats[2] = hb.depth;
+    e->stats[3] = hb.ntri;
+    *out = e;
+    return CTRB_OK;
+}
+
+void ctrb_env_destroy(ctrb_env* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(e->d_nodes[i]);
+        cudaFree(e->d_tri32[i]);
+        cudaFree(e->d_tri64[i]);
+    }
+    cudaFree(e->d_ec);
+    delete e;
+}
+
+int ctrb_env_stats(const ctrb_env* e, int32_t out[4]) {
+    CTRB_REQUIRE(e && out, "ctrb_env_stats: NULL argument");
+    for (int i = 0; i < 4; ++i) out[i] = e->stats[i];
+    return CTRB_OK;
+}
+
+#define CTRB_ENTER(ctx)                                 \
+    CTRB_REQUIRE((ctx) != nullptr, "ctx is NULL");      \
+    CTRB_CUDA(cudaSetDevice((ctx)->device))
+
+int ctrb_calculate_indices_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const double* prev_ins,
+                                 const double* next_ins, int32_t* prev_idx, int32_t* new_idx, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && B >= 0, "bad argument");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(prev_ins && next_ins && prev_idx && new_idx, "NULL buffer");
+    const size_t n = (size_t)B * m->mc.T;
+    Stage st(ctx);
+    const double* dp = st.in(prev_ins, n, mem);
+    const double* dn = st.in(next_ins, n, mem);
+    int32_t* op = st.out(prev_idx, n, mem);
+    int32_t* on = st.out(new_idx, n, mem);
+    if (st.rc) return st.rc;
+    int rc = launch_calc_indices(ctx, m, B, dp, dn, op, on);
+    if (rc) return rc;
+    st.back(prev_idx, op, n, mem);
+    st.back(new_idx, on, n, mem);
+    return st.finish(mem);
+}
+
+int ctrb_g_node_offsets(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx, int full,
+                        int64_t* node_offsets, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && B >= 0 && node_offsets, "bad argument");
+    CTRB_REQUIRE(B == 0 || idx, "idx is NULL");
+    const size_t n = (size_t)B * m->mc.T;
+    if (mem == CTRB_MEM_HOST) {
+        // validate on the host: indices outside [0, npts-1] are an error (the reference would index out of range)
+        for (size_t i = 0; i < n; ++i) {
+            int t = (int)(i % m->mc.T);
+            CTRB_REQUIRE(idx[i] >= 0 && idx[i] < m->mc.npts[t], "idx[%zu]=%d outside [0,%d)", i, idx[i], m->mc.npts[t]);
+        }
+    }
+    Stage st(ctx);
+    const int32_t* di = st.in(idx, n, mem);
+    long long* off = (long long*)st.out(node_offsets, n + 1, mem);
+    if (st.rc) return st.rc;
+    int rc = launch_offsets(ctx, m, B, di, full, off);
+    if (rc) return rc;
+    st.back(node_offsets, (int64_t*)off, n + 1, mem);
+    return st.finish(mem);
+}
+
+int ctrb_solve_g_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx, const double* theta, int full,
+                       int precision, const int64_t* node_offsets, void* g_out, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && B >= 0, "bad argument");
+    CTRB_REQUIRE(precision == CTRB_F64 || precision == CTRB_F32, "precision must be 64 or 32");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(idx && theta && node_offsets && g_out, "NULL buffer");
+    const size_t n = (size_t)B * m->mc.T;
+    const size_t esz = precision == CTRB_F64 ? 8 : 4;
+    if (mem == CTRB_MEM_DEVICE) {
+        return launch_gcurve(ctx, m, B, idx, theta, full, precision, (const long long*)node_offsets, g_out);
+    }
+    for (size_t i = 0; i < n; ++i) {
+        int t = (int)(i % m->mc.T);
+        CTRB_REQUIRE(idx[i] >= 0 && idx[i] < m->mc.npts[t], "idx[%zu]=%d outside [0,%d)", i, idx[i], m->mc.npts[t]);
+    }
+    const size_t total_nodes = (size_t)node_offsets[n];
+    Stage st(ctx);
+    const int32_t* di = st.in(idx, n, mem);
+    const double* dt = st.in(theta, n, mem);
+    const int64_t* doff = st.in(node_offsets, n + 1, mem);
+    if (st.rc) return st.rc;
+    void* dg = nullptr;
+    int rc = ctx_scratch(ctx, 10, total_nodes * 16 * esz, &dg);
+    if (rc) return rc;
+    rc = launch_gcurve(ctx, m, B, di, dt, full, precision, (const long long*)doff, dg);
+    if (rc) return rc;
+    CTRB_CUDA(cudaMemcpyAsync(g_out, dg, total_nodes * 16 * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    return st.finish(mem);
+}
+
+int ctrb_eta_ftl_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* prev_idx, const int32_t* new_idx,
+                       const double* velocity, const double* delta_theta, const double* prev_g, const int64_t* prev_offsets, double* eta_out,
+                       double* ftl_out, double* ftl_mag, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && B >= 0, "bad argument");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(prev_idx && delta_theta && prev_g && prev_offsets && eta_out, "NULL buffer");
+    CTRB_REQUIRE((new_idx != nullptr) != (velocity != nullptr), "pass exactly one of new_idx and velocity");
+    const size_t n = (size_t)B * m->mc.T;
+    void* dflag = nullptr;
+    int rc = ctx_scratch(ctx, 0, sizeof(int), &dflag);
+    if (rc) return rc;
+    CTRB_CUDA(cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
+    if (mem == CTRB_MEM_DEVICE) {
+        return launch_eta_ftl(ctx, m, B, prev_idx, new_idx, velocity, delta_theta, prev_g, (const long long*)prev_offsets, eta_out,
+                              ftl_out, ftl_mag, (int*)dflag);
+    }
+    const size_t total_nodes = (size_t)prev_offsets[n];
+    Stage st(ctx);
+    const int32_t* dpi = st.in(prev_idx, n, mem);
+    const int32_t* dni = new_idx ? st.in(new_idx, n, mem) : nullptr;
+    const double* dve = velocity ? st.in(velocity, n, mem) : nullptr;
+    const double* ddt = st.in(delta_theta, n, mem);
+    const int64_t* doff = st.in(prev_offsets, n + 1, mem);
+    double* deta = st.out(eta_out, n * 6, mem);
+    double* dmag = st.out(ftl_mag, (size_t)B * 4, mem);
+    if (st.rc) return st.rc;
+    void* dg = nullptr;
+    rc = ctx_scratch(ctx, 10, total_nodes * 16 * sizeof(double), &dg);
+    if (rc) return rc;
+    CTRB_CUDA(cudaMemcpyAsync(dg, prev_g, total_nodes * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    double* dftl = nullptr;
+    if (ftl_out) {
+        void* p = nullptr;
+        rc = ctx_scratch(ctx, 11, total_nodes * 6 * sizeof(double), &p);
+        if (rc) return rc;
+        dftl = (double*)p;
+    }
+    rc = launch_eta_ftl(ctx, m, B, dpi, dni, dve, ddt, (const double*)dg, (const long long*)doff, deta, dftl, dmag, (int*)dflag);
+    if (rc) return rc;
+    st.back(eta_out, deta, n * 6, mem);
+    st.back(ftl_mag, dmag, (size_t)B * 4, mem);
+    if (ftl_out) CTRB_CUDA(cudaMemcpyAsync(ftl_out, dftl, total_nodes * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    int hflag = 0;
+    CTRB_CUDA(cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    rc = st.finish(mem);
+    if (rc) return rc;
+    CTRB_REQUIRE(hflag == 0, "prev_g holds fewer nodes than npts - prev_idx for some tube (IndexError in the reference)");
+    return CTRB_OK;
+}
+
+int ctrb_check_collision_batch(ctrb_ctx* ctx, const ctrb_env* env, int64_t B, int32_t tube_num, const double* g,
+                               const int64_t* node_offsets, const double* rad, double* obstacle_min, double* goal_dist,
+                               int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(env && B >= 0, "bad argument");
+    CTRB_REQUIRE(tube_num >= 1 && tube_num <= CTRB_MAX_TUBES, "tube_num out of range");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(g && node_offsets && rad && obstacle_min && goal_dist, "NULL buffer");
+    const size_t n = (size_t)B * tube_num;
+    if (mem == CTRB_MEM_DEVICE) {
+        // max nodes per configuration is needed for the shared-memory carve-up: read the offsets back
+        std::vector<int64_t> h(n + 1);
+        CTRB_CUDA(cudaMemcpyAsync(h.data(), node_offsets, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
+        int64_t mx = 1;
+        for (int64_t b = 0; b < B; ++b) mx = std::max(mx, h[(b + 1) * tube_num] - h[b * tube_num]);
+        return launch_eval_curves(ctx, env, B, tube_num, g, (const long long*)node_offsets, (int)mx, rad, obstacle_min, goal_dist);
+    }
+    int64_t mx = 1;
+    for (int64_t b = 0; b < B; ++b) mx = std::max(mx, node_offsets[(b + 1) * tube_num] - node_offsets[b * tube_num]);
+    const size_t total_nodes = (size_t)node_offsets[n];
+    Stage st(ctx);
+    const int64_t* doff = st.in(node_offsets, n + 1, mem);
+    double* dob = st.out(obstacle_min, (size_t)B, mem);
+    double* dgo = st.out(goal_dist, (size_t)B, mem);
+    if (st.rc) return st.rc;
+    void* dg = nullptr;
+    int rc = ctx_scratch(ctx, 10, total_nodes * 16 * sizeof(double), &dg);
+    if (rc) return rc;
+    CTRB_CUDA(cudaMemcpyAsync(dg, g, total_nodes * 16 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_eval_curves(ctx, env, B, tube_num, (const double*)dg, (const long long*)doff, (int)mx, rad, dob, dgo);
+    if (rc) return rc;
+    st.back(obstacle_min, dob, (size_t)B, mem);
+    st.back(goal_dist, dgo, (size_t)B, mem);
+    return st.finish(mem);
+}
+
+int ctrb_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, const ctrb_cost_desc* cd, int64_t B,
+                    const int32_t* idx, const double* theta, const double* rad, double* obstacle_min, double* goal_dist,
+                    double* cost, uint8_t* collide, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && env && cd && B >= 0, "bad argument");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(idx && theta && rad && obstacle_min && goal_dist, "NULL buffer");
+    const int T = m->mc.T;
+    if (mem == CTRB_MEM_DEVICE) {
+        return launch_eval_fused(ctx, m, env, cd, B, idx, theta, rad, obstacle_min, goal_dist, cost, collide);
+    }
+    const size_t n = (size_t)B * T;
+    for (size_t i = 0; i < n; ++i) {
+        int t = (int)(i % T);
+        CTRB_REQUIRE(idx[i] >= 0 && idx[i] < m->mc.npts[t], "idx[%zu]=%d outside [0,%d)", i, idx[i], m->mc.npts[t]);
+    }
+    Stage st(ctx);
+    const int32_t* di = st.in(idx, n, mem);
+    const double* dt = st.in(theta, n, mem);
+    double* dob = st.out(obstacle_min, (size_t)B, mem);
+    double* dgo = st.out(goal_dist, (size_t)B, mem);
+    double* dco = st.out(cost, (size_t)B, mem);
+    uint8_t* dcl = st.out(collide, (size_t)B, mem);
+    if (st.rc) return st.rc;
+    int rc = launch_eval_fused(ctx, m, env, cd, B, di, dt, rad, dob, dgo, dco, dcl);
+    if (rc) return rc;
+    st.back(obstacle_min, dob, (size_t)B, mem);
+    st.back(goal_dist, dgo, (size_t)B, mem);
+    st.back(cost, dco, (size_t)B, mem);
+    st.back(collide, dcl, (size_t)B, mem);
+    return st.finish(mem);
+}
+
+int ctrb_argmin_cost(ctrb_ctx* ctx, int64_t B, const double* cost, int64_t index_base, double* best_cost,
+                     int64_t* best_index, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(B >= 0 && best_cost && best_index, "bad argument");
+    *best_cost = INFINITY;
+    *best_index = -1;
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(cost, "cost is NULL");
+    CTRB_REQUIRE(B < (1LL << 31), "at most 2^31-1 costs per call");
+    Stage st(ctx);
+    const double* dc = st.in(cost, (size_t)B, mem);
+    if (st.rc) return st.rc;
+    void* dkey = nullptr;
+    int rc = ctx_scratch(ctx, 0, 2 * sizeof(unsigned long long), &dkey);
+    if (rc) return rc;
+    rc = launch_argmin(ctx, B, dc, (unsigned long long*)dkey);
+    if (rc) return rc;
+    unsigned long long h[2];
+    CTRB_CUDA(cudaMemcpyAsync(h, dkey, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h[1] != ~0ULL) {
+        double c;
+        unsigned long long bits = h[0];
+        bits = (bits & 0x8000000000000000ULL) ? (bits & 0x7fffffffffffffffULL) : ~bits;  // undo the monotone map
+        std::memcpy(&c, &bits, sizeof c);
+        *best_cost = c;
+        *best_index = index_base + (int64_t)h[1];
+    }
+    return CTRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,520 @@
+// ctrb_collide.cu -- tube-vs-environment distance / collision and the fused
+// g-curve + collision + cost kernel (sm_100a).
+//
+// Replaces CollisionChecker.check_collision (collision_checker.py:35-95) and, in the fused
+// variant, the solve_g -> check_collision -> heuristic chain of rrt.py:110-129.
+//
+// One warp per configuration.  The warp first lays the configuration's node positions into
+// shared memory (fused: p_j = A_n C_n[j].p straight from the model table -- the g-curve
+// never touches HBM).  Every pair of consecutive nodes is a solid flat-capped cylinder
+// (collision_checker.py:121-147); lanes pull cylinders from a warp-local ticket and walk
+// a BVH over the triangle soup with a private stack.  All lanes of the warp share one
+// upper bound on the configuration's minimum distance (shared-memory atomicMin on the
+// float bits), so a cylinder far from the wall prunes against the distance another lane
+// already found, and one contact flag that ends the whole query (python-fcl's
+// defaultDistanceCallback stops at the first contact).
+//
+// Culling is fp32 (boxes rounded outward, `slack` absorbs every fp32 rounding), the
+// decisive cylinder<->triangle distance is fp64 and exact (ctrb_geom.cuh).  No tensor
+// cores: there is no dense contraction anywhere on this path.
+#include <float.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "ctrb_geom.cuh"
+#include "ctrb_se3.cuh"
+
+namespace ctrb {
+
+constexpr int kCWarps = 8;        // warps (= configurations in flight) per block
+constexpr int kTopNodes = 256;    // BVH nodes staged in shared memory (BFS prefix = top ~8 levels)
+constexpr int kStack = 48;
+
+struct WarpCtl {
+    int bound_bits;   // float bits of an upper bound on the config's min distance (>= 0 => int-ordered)
+    int collided;
+    int ticket;
+    int pad;
+};
+
+struct EvalParams {
+    ModelConst mc;
+    ModelTables tb;
+    const EnvConst* env;
+    long long B;
+    const int32_t* idx;
+    const double* theta;
+    // non-fused input
+    const double* g;
+    const long long* offsets;
+    int tube_num;
+    double rad[CTRB_MAX_TUBES];
+    // outputs
+    double* obstacle_min;
+    double* goal_dist;
+    double* cost;
+    uint8_t* collide;
+    ctrb_cost_desc cd;
+    unsigned long long* counters;  // [0..3] work counters, [4] config ticket
+    int max_nodes;                 // shared-memory rows per warp
+};
+
+__device__ __forceinline__ BvhNode load_node(const DevBvh& bvh, const BvhNode* s_top, int ntop, int ni) {
+    if (ni < ntop) return s_top[ni];
+    BvhNode n;
+    const float4* p = reinterpret_cast<const float4*>(bvh.nodes + ni);
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    n.lo0[0] = a.x; n.lo0[1] = a.y; n.lo0[2] = a.z; n.hi0[0] = a.w;
+    n.hi0[1] = b.x; n.hi0[2] = b.y; n.lo1[0] = b.z; n.lo1[1] = b.w;
+    n.lo1[2] = c.x; n.hi1[0] = c.y; n.hi1[1] = c.z; n.hi1[2] = c.w;
+    n.c0 = __float_as_int(d.x);
+    n.c1 = __float_as_int(d.y);
+    return n;
+}
+
+struct Work {
+    unsigned int nodes, pre, exact;
+};
+
+// exact min distance of one solid cylinder against the mesh, sharing bounds through `ctl`
+__device__ void cylinder_vs_mesh(const DevBvh& bvh, const BvhNode* s_top, int ntop, d3 c, d3 a, double h, double r,
+                                 WarpCtl* ctl, double& best_exact, Work& wk) {
+    const f3 cf = {(float)c.x, (float)c.y, (float)c.z};
+    const float slack = bvh.slack;
+    const float rb = __fsqrt_ru(__fmaf_ru((float)h, (float)h, (float)r * (float)r)) * 1.000001f;
+    const float rin = fminf((float)h, (float)r);
+    int stack[kStack];
+    int sp = 0;
+    stack[sp++] = 0;
+    volatile int* vbound = &ctl->bound_bits;
+    volatile int* vcoll = &ctl->collided;
+    while (sp > 0) {
+        if (*vcoll) return;
+        const int ni = stack[--sp];
+        const BvhNode nd = load_node(bvh, s_top, ntop, ni);
+        wk.nodes++;
+        float bound = __int_as_float(*vbound);
+        float reach = bound + rb + slack;
+        float reach2 = reach * reach * 1.000001f;
+        float d0 = aabb_dist2(nd.lo0, nd.hi0, cf);
+        float d1 = aabb_dist2(nd.lo1, nd.hi1, cf);
+        int l0 = nd.c0, l1 = nd.c1;
+        if (d1 < d0) {  // near child first
+            float t = d0; d0 = d1; d1 = t;
+            int ti = l0; l0 = l1; l1 = ti;
+        }
+        // inner children: push far first so that near is popped first
+        if (l1 >= 0 && d1 <= reach2 && sp < kStack) stack[sp++] = l1;
+        if (l0 >= 0 && d0 <= reach2 && sp < kStack) stack[sp++] = l0;
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            const int link = side == 0 ? l0 : l1;
+            const float dd = side == 0 ? d0 : d1;
+            if (link >= 0 || dd > reach2) continue;
+            const int code = ~link;
+            const int first = code >> 3, cnt = (code & 7) + 1;
+#pragma unroll 1
+            for (int t = first; t < first + cnt; ++t) {
+                const float4* tp = bvh.tri32 + (size_t)t * 3;
+                float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                float dpt = sqrtf(point_tri_dist2<f3, float>(cf, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z},
+                                                              f3{v2.x, v2.y, v2.z}));
+                wk.pre++;
+                if (dpt + slack < rin) {  // a ball of radius min(h, r) about the centre lies inside the solid cylinder
+                    *vcoll = 1;
+                    return;
+                }
+                // the centre belongs to the cylinder: d(cyl, tri) <= dpt
+                atomicMin(&ctl->bound_bits, __float_as_int(dpt + slack));
+                bound = __int_as_float(*vbound);
+                if (dpt - rb - slack > bound) continue;  // d(cyl, tri) >= dpt - rb
+                const double* tq = bvh.tri64 + (size_t)t * 9;
+                d3 t0 = {__ldg(tq + 0), __ldg(tq + 1), __ldg(tq + 2)};
+                d3 t1 = {__ldg(tq + 3), __ldg(tq + 4), __ldg(tq + 5)};
+                d3 t2 = {__ldg(tq + 6), __ldg(tq + 7), __ldg(tq + 8)};
+                double d = cyl_tri_dist(c, a, h, r, t0, t1, t2, (double)bound);
+                wk.exact++;
+                if (d <= 0.0) {
+                    *vcoll = 1;
+                    return;
+                }
+                if (d < best_exact) {
+                    best_exact = d;
+                    atomicMin(&ctl->bound_bits, __float_as_int(__double2float_ru(d)));
+                }
+            }
+        }
+    }
+}
+
+// exact nearest distance from a point to a mesh (goal mesh): fp32 culling, fp64 leaves
+__device__ double point_vs_mesh(const DevBvh& bvh, d3 x, Work& wk) {
+    const f3 xf = {(float)x.x, (float)x.y, (float)x.z};
+    const float slack = bvh.slack;
+    double best = DBL_MAX;
+    float bound = FLT_MAX;
+    int stack[kStack];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const int ni = stack[--sp];
+        const BvhNode nd = load_node(bvh, nullptr, 0, ni);
+        wk.nodes++;
+        float reach = bound + slack;
+        float reach2 = reach < 1e18f ? reach * reach * 1.000001f : FLT_MAX;
+        float d0 = aabb_dist2(nd.lo0, nd.hi0, xf);
+        float d1 = aabb_dist2(nd.lo1, nd.hi1, xf);
+        int l0 = nd.c0, l1 = nd.c1;
+        if (d1 < d0) {
+            float t = d0; d0 = d1; d1 = t;
+            int ti = l0; l0 = l1; l1 = ti;
+        }
+        if (l1 >= 0 && d1 <= reach2 && sp < kStack) stack[sp++] = l1;
+        if (l0 >= 0 && d0 <= reach2 && sp < kStack) stack[sp++] = l0;
+        for (int side = 0; side < 2; ++side) {
+            const int link = side == 0 ? l0 : l1;
+            const float dd = side == 0 ? d0 : d1;
+            if (link >= 0 || dd > reach2) continue;
+            const int code = ~link;
+            const int first = code >> 3, cnt = (code & 7) + 1;
+            for (int t = first; t < first + cnt; ++t) {
+                const double* tq = bvh.tri64 + (size_t)t * 9;
+                d3 t0 = {__ldg(tq + 0), __ldg(tq + 1), __ldg(tq + 2)};
+                d3 t1 = {__ldg(tq + 3), __ldg(tq + 4), __ldg(tq + 5)};
+                d3 t2 = {__ldg(tq + 6), __ldg(tq + 7), __ldg(tq + 8)};
+                double d = sqrt(point_tri_dist2<d3, double>(x, t0, t1, t2));
+                wk.exact++;
+                if (d < best) {
+                    best = d;
+                    bound = __double2float_ru(d);
+                }
+            }
+        }
+    }
+    return best;
+}
+
+__device__ void box_corner(const DevPrim& b, int k, d3& out) {
+    double s[3] = {(k & 1) ? 0.5 : -0.5, (k & 2) ? 0.5 : -0.5, (k & 4) ? 0.5 : -0.5};
+    double o[3];
+    for (int i = 0; i < 3; ++i) {
+        o[i] = b.center[i];
+        for (int ax = 0; ax < 3; ++ax) o[i] += b.rot[i * 3 + ax] * s[ax] * b.dims[ax];
+    }
+    out = {o[0], o[1], o[2]};
+}
+
+// solid cylinder vs primitive obstacle (fcl.Sphere / fcl.Box, init_collision.py:129-139)
+__device__ double cylinder_vs_prim(const DevPrim& o, d3 c, d3 a, double h, double r, double bound) {
+    if (o.shape == CTRB_SHAPE_SPHERE) {
+        double d = point_cyl_dist(d3{o.center[0], o.center[1], o.center[2]}, c, a, h, r) - o.dims[0];
+        return d < 0.0 ? 0.0 : d;
+    }
+    if (o.shape == CTRB_SHAPE_BOX) {
+        if (point_box_dist(c, o.center, o.rot, o.dims) == 0.0) return 0.0;
+        const int F[12][3] = {{0, 1, 3}, {0, 3, 2}, {4, 7, 5}, {4, 6, 7}, {0, 5, 1}, {0, 4, 5},
+                              {2, 3, 7}, {2, 7, 6}, {0, 2, 6}, {0, 6, 4}, {1, 5, 7}, {1, 7, 3}};
+        double best = DBL_MAX;
+        for (int f = 0; f < 12; ++f) {
+            d3 p0, p1, p2;
+            box_corner(o, F[f][0], p0);
+            box_corner(o, F[f][1], p1);
+            box_corner(o, F[f][2], p2);
+            double d = cyl_tri_dist(c, a, h, r, p0, p1, p2, fmin(best, bound));
+            if (d < best) best = d;
+            if (best == 0.0) break;
+        }
+        return best;
+    }
+    return DBL_MAX;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kCWarps * 32) chain_eval_kernel(EvalParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BvhNode* s_top = reinterpret_cast<BvhNode*>(smem_raw);
+    double* s_pos_all = reinterpret_cast<double*>(smem_raw + (size_t)kTopNodes * sizeof(BvhNode));
+    WarpCtl* s_ctl_all = reinterpret_cast<WarpCtl*>(s_pos_all + (size_t)kCWarps * P.max_nodes * 3);
+
+    const EnvConst& env = *P.env;
+    const int ntop = min(env.obs.nnodes, kTopNodes);
+    for (int i = threadIdx.x; i < ntop * 4; i += blockDim.x)
+        reinterpret_cast<float4*>(s_top)[i] = __ldg(reinterpret_cast<const float4*>(env.obs.nodes) + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* s_pos = s_pos_all + (size_t)warp * P.max_nodes * 3;
+    WarpCtl* ctl = s_ctl_all + warp;
+    const int T = FUSED ? P.mc.T : P.tube_num;
+    Work wk = {0, 0, 0};
+    unsigned int nconf = 0;
+
+    for (;;) {
+        // dynamic schedule: configurations differ wildly in cost (first-contact exit vs full distance)
+        long long b;
+        {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(P.counters + 4, 1ULL);
+            b = (long long)__shfl_sync(0xffffffffu, t, 0);
+        }
+        if (b >= P.B) break;
+        nconf++;
+
+        // ---- stage A: node positions of this configuration into shared memory
+        int cnt[CTRB_MAX_TUBES], first[CTRB_MAX_TUBES];
+        int total = 0;
+        if (FUSED) {
+            const int tot = P.mc.total_nodes;
+            SE3 g;
+            se3_identity(g);
+            for (int n = 0; n < T; ++n) {
+                const int id = P.idx[b * T + n];
+                se3_rot_x(g, P.theta[b * T + n]);
+                SE3 a = se3_mul(g, load_tab(P.tb.tab_inv, tot, P.mc.node_base[n] + id));
+                cnt[n] = P.mc.npts[n] - id;  // kinematic.py:100-103 (full=False)
+                first[n] = total;
+                const int colbase = P.mc.node_base[n] + id;
+                for (int k = lane; k < cnt[n]; k += 32) {
+                    const int col = colbase + k;
+                    double cx = __ldg(P.tb.tab + 9 * tot + col), cy = __ldg(P.tb.tab + 10 * tot + col),
+                           cz = __ldg(P.tb.tab + 11 * tot + col);
+                    double* dst = s_pos + (size_t)(total + k) * 3;
+                    dst[0] = fma(a.r[0], cx, fma(a.r[1], cy, fma(a.r[2], cz, a.p[0])));
+                    dst[1] = fma(a.r[3], cx, fma(a.r[4], cy, fma(a.r[5], cz, a.p[1])));
+                    dst[2] = fma(a.r[6], cx, fma(a.r[7], cy, fma(a.r[8], cz, a.p[2])));
+                }
+                total += cnt[n];
+                // tube tip frame = A * C[N-1]
+                g = se3_mul(a, load_tab(P.tb.tab, tot, P.mc.node_base[n] + P.mc.npts[n] - 1));
+            }
+        } else {
+            for (int n = 0; n < T; ++n) {
+                const long long o0 = P.offsets[b * T + n], o1 = P.offsets[b * T + n + 1];
+                cnt[n] = (int)(o1 - o0);
+                if (total + cnt[n] > P.max_nodes) cnt[n] = max(0, P.max_nodes - total);  // guarded on the host
+                first[n] = total;
+                for (int k = lane; k < cnt[n]; k += 32) {
+                    const double* gg = P.g + (o0 + k) * 16;
+                    double* dst = s_pos + (size_t)(total + k) * 3;
+                    dst[0] = __ldg(gg + 3);
+                    dst[1] = __ldg(gg + 7);
+                    dst[2] = __ldg(gg + 11);
+                }
+                total += cnt[n];
+            }
+        }
+        if (lane == 0) {
+            ctl->bound_bits = __float_as_int(FLT_MAX);
+            ctl->collided = 0;
+            ctl->ticket = 0;
+        }
+        __syncwarp();
+
+        // ---- stage B: cylinders.  item k of tube n joins nodes first[n]+k and first[n]+k+1
+        int ncyl = 0;
+        int cyl_first[CTRB_MAX_TUBES];
+        for (int n = 0; n < T; ++n) {
+            cyl_first[n] = ncyl;
+            ncyl += max(cnt[n] - 1, 0);
+        }
+        double best = DBL_MAX;
+        const bool have_obstacles = env.obs.ntri > 0 || env.nprim > 0;
+        if (have_obstacles) {
+            for (;;) {
+                const int item = atomicAdd(&ctl->ticket, 1);
+                if (item >= ncyl || *(volatile int*)&ctl->collided) break;
+                int n = 0;
+#pragma unroll
+                for (int q = 1; q < CTRB_MAX_TUBES; ++q)
+                    if (q < T && item >= cyl_first[q]) n = q;
+                const int node = first[n] + (item - cyl_first[n]);
+                const double* pf = s_pos + (size_t)node * 3;
+                d3 f = {pf[0], pf[1], pf[2]}, t = {pf[3], pf[4], pf[5]};
+                d3 vec = t - f;
+                double len = sqrt(dot(vec, vec));           // collision_checker.py:130-131
+                d3 c = f + 0.5 * vec;                        // mid_point
+                d3 a = (1.0 / len) * vec;                    // unit_vec -> cylinder axis
+                const double h = 0.5 * len, r = P.rad[n];
+                if (env.obs.ntri > 0) cylinder_vs_mesh(env.obs, s_top, ntop, c, a, h, r, ctl, best, wk);
+                for (int k = 0; k < env.nprim && !*(volatile int*)&ctl->collided; ++k) {
+                    double d = cylinder_vs_prim(env.prims[k], c, a, h, r, best);
+                    if (d <= 0.0) *(volatile int*)&ctl->collided = 1;
+                    else if (d < best) {
+                        best = d;
+                        atomicMin(&ctl->bound_bits, __float_as_int(__double2float_ru(d)));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, off));
+        const bool collided = *(volatile int*)&ctl->collided != 0;
+
+        // ---- goal: Sphere(rad[-1]) at the last node of the last tube (collision_checker.py:62-68)
+        if (lane == 0) {
+            double gd = DBL_MAX;
+            if (total > 0 && env.goal.shape != CTRB_SHAPE_NONE) {
+                // curve[-1][-1]: last node of the last tube that has nodes
+                const double* pt = s_pos + (size_t)(total - 1) * 3;
+                d3 tip = {pt[0], pt[1], pt[2]};
+                const double tr = P.rad[T - 1];
+                const DevPrim& gl = env.goal;
+                if (gl.shape == CTRB_SHAPE_SPHERE) {
+                    d3 dd = tip - d3{gl.center[0], gl.center[1], gl.center[2]};
+                    gd = sqrt(dot(dd, dd)) - gl.dims[0] - tr;
+                } else if (gl.shape == CTRB_SHAPE_BOX) {
+                    gd = point_box_dist(tip, gl.center, gl.rot, gl.dims) - tr;
+                } else if (gl.shape == CTRB_SHAPE_CYLINDER) {
+                    d3 ax = {gl.rot[2], gl.rot[5], gl.rot[8]};
+                    gd = point_cyl_dist(tip, d3{gl.center[0], gl.center[1], gl.center[2]}, ax, 0.5 * gl.dims[1], gl.dims[0]) - tr;
+                } else if (gl.shape == CTRB_SHAPE_MESH && env.goal_mesh.ntri > 0) {
+                    gd = point_vs_mesh(env.goal_mesh, tip, wk) - tr;
+                }
+                if (gd <= 0.0) gd = -1.0;
+            }
+            const double om = collided ? -1.0 : (have_obstacles ? best : DBL_MAX);
+            P.obstacle_min[b] = om;
+            P.goal_dist[b] = gd;
+            if (P.collide) P.collide[b] = collided ? 1 : 0;
+            if (P.cost) {
+                // rrt.py:116-129: a colliding configuration is discarded; at the goal the distance clamps to 0
+                double cst = CUDART_NAN;
+                if (!collided) {
+                    const double g0 = gd < 0.0 ? 0.0 : gd;
+                    if (P.cd.cost_type == CTRB_COST_SOAPWG) {
+                        const double inv = 1.0 / om;  // obstacles_and_goal.py:39-45,87-88
+                        cst = g0 * P.cd.goal_weight + inv * inv;
+                    } else if (P.cd.cost_type == CTRB_COST_ONLY_GOAL) {
+                        cst = g0;                      // only_goal_distance.py:20-24
+                    } else {
+                        cst = 0.0;                     // FTL family: the twist term comes from ctrb_eta_ftl_batch
+                    }
+                }
+                P.cost[b] = cst;
+            }
+        }
+        __syncwarp();
+    }
+    // work counters
+    for (int off = 16; off > 0; off >>= 1) {
+        wk.nodes += __shfl_xor_sync(0xffffffffu, wk.nodes, off);
+        wk.pre += __shfl_xor_sync(0xffffffffu, wk.pre, off);
+        wk.exact += __shfl_xor_sync(0xffffffffu, wk.exact, off);
+    }
+    if (lane == 0) {
+        atomicAdd(P.counters + 0, (unsigned long long)wk.nodes);
+        atomicAdd(P.counters + 1, (unsigned long long)wk.pre);
+        atomicAdd(P.counters + 2, (unsigned long long)wk.exact);
+        atomicAdd(P.counters + 3, (unsigned long long)nconf);
+    }
+}
+
+size_t eval_smem_bytes(int max_nodes) {
+    return (size_t)kTopNodes * sizeof(BvhNode) + (size_t)kCWarps * max_nodes * 3 * sizeof(double) +
+           (size_t)kCWarps * sizeof(WarpCtl);
+}
+
+int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
+    if (P.B <= 0) return CTRB_OK;
+    size_t smem = eval_smem_bytes(P.max_nodes);
+    if (smem > 200 * 1024) {
+        set_error("configuration has too many nodes (%d) for the shared-memory staging", P.max_nodes);
+        return CTRB_ERR_UNSUPPORTED;
+    }
+    CTRB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    long long blocks_needed = (P.B + kCWarps - 1) / kCWarps;
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem));
+    int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * per_sm);
+    if (fused) {
+        CTRB_CUDA(cudaFuncSetAttribute(chain_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chain_eval_kernel<true><<<grid, kCWarps * 32, smem, ctx->stream>>>(P);
+    } else {
+        CTRB_CUDA(cudaFuncSetAttribute(chain_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chain_eval_kernel<false><<<grid, kCWarps * 32, smem, ctx->stream>>>(P);
+    }
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
+    return CTRB_OK;
+}
+
+
+int launch_eval_fused(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, const ctrb_cost_desc* cd, long long B,
+                      const int32_t* idx, const double* theta, const double* rad, double* obstacle_min,
+                      double* goal_dist, double* cost, uint8_t* collide) {
+    EvalParams P;
+    memset(&P, 0, sizeof P);
+    P.mc = m->mc;
+    P.tb = m->tables();
+    P.env = env->d_ec;
+    P.B = B;
+    P.idx = idx;
+    P.theta = theta;
+    P.tube_num = m->mc.T;
+    for (int n = 0; n < m->mc.T; ++n) P.rad[n] = rad[n];
+    P.obstacle_min = obstacle_min;
+    P.goal_dist = goal_dist;
+    P.cost = cost;
+    P.collide = collide;
+    P.cd = *cd;
+    P.counters = ctx->d_counters;
+    P.max_nodes = m->mc.total_nodes;
+    return launch_eval(ctx, P, true);
+}
+
+int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube_num, const double* g,
+                       const long long* offsets, int max_nodes, const double* rad, double* obstacle_min,
+                       double* goal_dist) {
+    EvalParams P;
+    memset(&P, 0, sizeof P);
+    P.env = env->d_ec;
+    P.B = B;
+    P.g = g;
+    P.offsets = offsets;
+    P.tube_num = tube_num;
+    for (int n = 0; n < tube_num; ++n) P.rad[n] = rad[n];
+    P.obstacle_min = obstacle_min;
+    P.goal_dist = goal_dist;
+    P.counters = ctx->d_counters;
+    P.max_nodes = max_nodes;
+    return launch_eval(ctx, P, false);
+}
+
+// ------------------------------------------------------------------ best node: min finite cost, then lowest index
+__device__ __forceinline__ unsigned long long cost_key(double c) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(c);
+    return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+__global__ void argmin_key_kernel(long long B, const double* __restrict__ cost, unsigned long long* __restrict__ key) {
+    unsigned long long best = ~0ULL;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+        double c = cost[i];
+        if (c == c) best = min(best, cost_key(c));
+    }
+    for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if ((threadIdx.x & 31) == 0 && best != ~0ULL) atomicMin(key, best);
+}
+
+__global__ void argmin_index_kernel(long long B, const double* __restrict__ cost, unsigned long long* __restrict__ key) {
+    const unsigned long long k = key[0];
+    if (k == ~0ULL) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+        double c = cost[i];
+        if (c == c && cost_key(c) == k) atomicMin(key + 1, (unsigned long long)i);
+    }
+}
+
+int launch_argmin(ctrb_ctx* ctx, long long B, const double* cost, unsigned long long* key_out) {
+    CTRB_CUDA(cudaMemsetAsync(key_out, 0xff, 2 * sizeof(unsigned long long), ctx->stream));
+    int grid = (int)std::min<long long>((B + 255) / 256, (long long)ctx->sm_count * 8);
+    argmin_key_kernel<<<grid, 256, 0, ctx->stream>>>(B, cost, key_out);
+    argmin_index_kernel<<<grid, 256, 0, ctx->stream>>>(B, cost, key_out);
+    ctx->launches += 2;
+    CTRB_CUDA(cudaGetLastError());
+    return CTRB_OK;
+}
+
+}  // namespace ctrb

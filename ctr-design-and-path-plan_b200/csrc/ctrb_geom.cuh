@@ -1,0 +1,225 @@
+// ctrb_geom.cuh -- device geometry for the tube-vs-environment distance query.
+// Semantics follow what python-fcl gives CollisionChecker.check_collision
+// (collision_checker.py:35-95,121-147): each tube segment is a SOLID flat-capped
+// cylinder (fcl.Cylinder), a mesh obstacle is a triangle soup (surface), the result
+// is the exact Euclidean distance, 0 meaning contact.
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace ctrb {
+
+struct d3 {
+    double x, y, z;
+};
+__device__ __forceinline__ d3 operator+(d3 a, d3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ d3 operator*(double s, d3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ double dot(d3 a, d3 b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ d3 cross(d3 a, d3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+struct f3 {
+    float x, y, z;
+};
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+
+// squared distance from a point to an fp32 AABB
+__device__ __forceinline__ float aabb_dist2(const float lo[3], const float hi[3], f3 p) {
+    float dx = fmaxf(fmaxf(lo[0] - p.x, p.x - hi[0]), 0.f);
+    float dy = fmaxf(fmaxf(lo[1] - p.y, p.y - hi[1]), 0.f);
+    float dz = fmaxf(fmaxf(lo[2] - p.z, p.z - hi[2]), 0.f);
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+// squared point-triangle distance, closest-feature region walk; T = float or double
+template <typename V, typename S>
+__device__ __forceinline__ S point_tri_dist2(V p, V a, V b, V c) {
+    V ab = b - a, ac = c - a, ap = p - a;
+    S d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0 && d2 <= 0) return dot(ap, ap);
+    V bp = p - b;
+    S d3_ = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3_ >= 0 && d4 <= d3_) return dot(bp, bp);
+    S vc = d1 * d4 - d3_ * d2;
+    if (vc <= 0 && d1 >= 0 && d3_ <= 0) {
+        S v = d1 / (d1 - d3_);
+        S q = dot(ap, ap) - v * d1;  // |ap - v ab|^2 = ap.ap - 2 v d1 + v^2 ab.ab, with v = d1/(ab.ab) on the line
+        // use the direct form for robustness
+        V r = {ap.x - v * ab.x, ap.y - v * ab.y, ap.z - v * ab.z};
+        (void)q;
+        return dot(r, r);
+    }
+    V cp = p - c;
+    S d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0 && d5 <= d6) return dot(cp, cp);
+    S vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+        S w = d2 / (d2 - d6);
+        V r = {ap.x - w * ac.x, ap.y - w * ac.y, ap.z - w * ac.z};
+        return dot(r, r);
+    }
+    S va = d3_ * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3_) >= 0 && (d5 - d6) >= 0) {
+        S w = (d4 - d3_) / ((d4 - d3_) + (d5 - d6));
+        V bc = c - b;
+        V r = {bp.x - w * bc.x, bp.y - w * bc.y, bp.z - w * bc.z};
+        return dot(r, r);
+    }
+    // interior: distance to the plane
+    V n = {ab.y * ac.z - ab.z * ac.y, ab.z * ac.x - ab.x * ac.z, ab.x * ac.y - ab.y * ac.x};
+    S nn = dot(n, n);
+    if (nn == 0) return dot(ap, ap);
+    S t = dot(ap, n);
+    return t * t / nn;
+}
+
+// distance from a point to the solid cylinder {c + t a + u : |t| <= h, u _|_ a, |u| <= r}
+__device__ __forceinline__ double point_cyl_dist(d3 x, d3 c, d3 a, double h, double r) {
+    d3 y = x - c;
+    double t = dot(y, a);
+    d3 w = y - t * a;
+    double rho = sqrt(dot(w, w));
+    double dt = fmax(fabs(t) - h, 0.0), dr = fmax(rho - r, 0.0);
+    return sqrt(fma(dt, dt, dr * dr));
+}
+
+// Segment vs solid cylinder.  In cylinder coordinates the segment is
+//   t(s) = t0 + s tp,  rho(s)^2 = A s^2 + 2 Bq s + Cq,  s in [0,1];
+// F(s) = max(|t|-h,0)^2 + max(rho-r,0)^2 is convex and C^1, so F' is monotone and
+// its root is bracketed (Illinois regula falsi with a bisection safeguard).
+struct SegCyl {
+    double t0, tp, A, Bq, Cq, h, r;
+    __device__ __forceinline__ double eval(double s, double* g) const {
+        double t = fma(s, tp, t0);
+        double rho2 = fma(s, fma(s, A, 2.0 * Bq), Cq);
+        double rho = sqrt(fmax(rho2, 0.0));
+        double dt = fabs(t) - h, dr = rho - r;
+        double F = 0.0, gg = 0.0;
+        if (dt > 0.0) {
+            F = dt * dt;
+            gg = 2.0 * dt * (t > 0.0 ? tp : -tp);
+        }
+        if (dr > 0.0) {
+            F = fma(dr, dr, F);
+            gg = fma(2.0 * dr, fma(A, s, Bq) / rho, gg);
+        }
+        *g = gg;
+        return F;
+    }
+};
+
+// returns min over the segment p0->p1 of the SQUARED distance to the cylinder (0 = contact)
+__device__ __noinline__ double seg_cyl_dist2(d3 p0, d3 p1, d3 c, d3 a, double h, double r) {
+    d3 y0 = p0 - c, e = p1 - p0;
+    SegCyl sc;
+    sc.t0 = dot(y0, a);
+    sc.tp = dot(e, a);
+    d3 w0 = y0 - sc.t0 * a, wp = e - sc.tp * a;
+    sc.A = dot(wp, wp);
+    sc.Bq = dot(w0, wp);
+    sc.Cq = dot(w0, w0);
+    sc.h = h;
+    sc.r = r;
+    double g0, g1;
+    double F0 = sc.eval(0.0, &g0);
+    double F1 = sc.eval(1.0, &g1);
+    if (F0 == 0.0 || F1 == 0.0) return 0.0;
+    if (g0 >= 0.0) return F0;
+    if (g1 <= 0.0) return F1;
+    double lo = 0.0, hi = 1.0, glo = g0, ghi = g1, best = fmin(F0, F1);
+    int side = 0;
+#pragma unroll 1
+    for (int it = 0; it < 96; ++it) {
+        double s = (it & 3) == 3 ? 0.5 * (lo + hi) : (lo * ghi - hi * glo) / (ghi - glo);
+        if (!(s > lo && s < hi)) s = 0.5 * (lo + hi);
+        if (!(s > lo && s < hi)) break;
+        double g, F = sc.eval(s, &g);
+        best = fmin(best, F);
+        if (F == 0.0 || g == 0.0) return F;
+        if (g > 0.0) {
+            hi = s;
+            ghi = g;
+            if (side == 1) glo *= 0.5;
+            side = 1;
+        } else {
+            lo = s;
+            glo = g;
+            if (side == -1) ghi *= 0.5;
+            side = -1;
+        }
+        if (hi - lo < 1e-14) break;
+    }
+    return best;
+}
+
+__device__ __forceinline__ bool in_tri_plane(d3 z, d3 t0, d3 t1, d3 t2, d3 n) {
+    if (dot(cross(t1 - t0, z - t0), n) < 0.0) return false;
+    if (dot(cross(t2 - t1, z - t1), n) < 0.0) return false;
+    if (dot(cross(t0 - t2, z - t2), n) < 0.0) return false;
+    return true;
+}
+
+// Exact distance between the solid cylinder and a triangle; 0 = touching/intersecting.
+// The minimum of the convex point-to-cylinder distance over the triangle is on an edge,
+// or at the interior point facing the cylinder's support point toward the plane.
+// `bound`: callers only need the value if it is below bound; edges are skipped early
+// once the plane distance alone exceeds it.
+__device__ __noinline__ double cyl_tri_dist(d3 c, d3 a, double h, double r, d3 t0, d3 t1, d3 t2, double bound) {
+    d3 n = cross(t1 - t0, t2 - t0);
+    double nn = sqrt(dot(n, n));
+    double sc = 0.0, E = 0.0;
+    d3 so = {0, 0, 0};
+    bool has_plane = nn > 0.0;
+    if (has_plane) {
+        n = (1.0 / nn) * n;
+        sc = dot(c - t0, n);
+        double an = dot(a, n);
+        d3 m = n - an * a;
+        double mm = sqrt(dot(m, m));
+        if (mm > 0.0) m = (1.0 / mm) * m;
+        double sg = (an > 0.0) - (an < 0.0);
+        so = (sg * h) * a + r * m;
+        E = dot(so, n);
+        // the plane distance is a lower bound for the whole triangle
+        if (fabs(sc) - E >= bound) return fabs(sc) - E;
+    }
+    double e2 = seg_cyl_dist2(t0, t1, c, a, h, r);
+    if (e2 == 0.0) return 0.0;
+    double f2 = seg_cyl_dist2(t1, t2, c, a, h, r);
+    if (f2 == 0.0) return 0.0;
+    e2 = fmin(e2, f2);
+    f2 = seg_cyl_dist2(t2, t0, c, a, h, r);
+    if (f2 == 0.0) return 0.0;
+    e2 = fmin(e2, f2);
+    double e = sqrt(e2);
+    if (!has_plane) return e;
+    if (fabs(sc) <= E) {
+        double lam = (E > 0.0) ? -sc / E : 0.0;
+        d3 z = c + lam * so;
+        return in_tri_plane(z, t0, t1, t2, n) ? 0.0 : e;
+    }
+    double sgc = sc > 0.0 ? 1.0 : -1.0;
+    d3 y = c - sgc * so;
+    double dpl = dot(y - t0, n);
+    d3 yp = y - dpl * n;
+    if (in_tri_plane(yp, t0, t1, t2, n)) return fmin(fabs(sc) - E, e);
+    return e;
+}
+
+// distance from a point to a solid box
+__device__ __forceinline__ double point_box_dist(d3 x, const double* center, const double* rot, const double* dims) {
+    d3 y = {x.x - center[0], x.y - center[1], x.z - center[2]};
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double l = y.x * rot[0 * 3 + k] + y.y * rot[1 * 3 + k] + y.z * rot[2 * 3 + k];
+        double d = fabs(l) - 0.5 * dims[k];
+        if (d > 0.0) s = fma(d, d, s);
+    }
+    return sqrt(s);
+}
+
+}  // namespace ctrb

@@ -1,0 +1,146 @@
+// ctrb_internal.cuh -- shared declarations of libctrb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "ctrb200.h"
+
+namespace ctrb {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+#define CTRB_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            ctrb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                            cudaGetErrorString(e__));                                        \
+            return CTRB_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+#define CTRB_REQUIRE(cond, ...)             \
+    do {                                    \
+        if (!(cond)) {                      \
+            ctrb::set_error(__VA_ARGS__);   \
+            return CTRB_ERR_INVALID;        \
+        }                                   \
+    } while (0)
+
+// ---------------------------------------------------------------- model constants (kernel parameter, by value)
+struct ModelConst {
+    int T;
+    int kind[CTRB_MAX_TUBES];
+    int dof[CTRB_MAX_TUBES];
+    int npts[CTRB_MAX_TUBES];       // num_discrete_points, model.py:37-38
+    int node_base[CTRB_MAX_TUBES];  // first table column of tube n
+    int total_nodes;
+    double q[CTRB_MAX_TUBES][CTRB_MAX_DOF];
+    double L[CTRB_MAX_TUBES];
+    double dx;
+};
+
+// Table of cumulative transforms C_n[j] = E_n[1] ... E_n[j] (C_n[0] = I), where
+// E_n[i] = exp(dx * hat(B_n((i-1/2)dx) q_n + bias)) is the configuration-independent
+// per-node step of kinematic.py:106-118.  SoA: tab[k * total_nodes + node_base[n] + j],
+// k = 0..8 rotation row-major, 9..11 position.  tab_inv holds C_n[j]^-1.
+struct ModelTables {
+    const double* tab;
+    const double* tab_inv;
+    const float* tabR32;  // rotation part of tab in fp32 (9 rows)
+};
+
+}  // namespace ctrb
+
+struct ctrb_ctx {
+    int device;
+    cudaStream_t stream;
+    cudaStream_t stream2;  // second stream for host-memory chunk pipelining
+    cudaEvent_t ev[2];
+    cudaEvent_t ev_chunk[2];
+    int64_t launches;
+    // grow-only device scratch
+    void* scratch[12];
+    size_t scratch_bytes[12];
+    unsigned long long* d_counters;  // [8] work counters + scheduler tickets
+    int sm_count;
+};
+
+struct ctrb_model {
+    ctrb_model_desc desc;
+    ctrb::ModelConst mc;
+    int device;
+    double* d_tab;
+    double* d_tab_inv;
+    float* d_tabR32;
+    ctrb::ModelTables tables() const { return ctrb::ModelTables{d_tab, d_tab_inv, d_tabR32}; }
+};
+
+namespace ctrb {
+
+// ---------------------------------------------------------------- BVH (host build, device traversal)
+// 64-byte node: both children's fp32 AABBs (rounded outward) + two child links.
+// link >= 0: inner node index;  link < 0: leaf, ~link = (first_tri << 3) | (count - 1), count <= 8.
+struct alignas(16) BvhNode {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    int32_t c0, c1;
+    int32_t pad[2];
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+struct HostBvh {
+    std::vector<BvhNode> nodes;     // BFS order, root = 0 (empty when ntri == 0)
+    std::vector<double> tri64;      // [ntri][9] in leaf order
+    std::vector<float> tri32;       // [ntri][12]: v0.xyz,0, v1.xyz,0, v2.xyz,0 (rounded to nearest)
+    int ntri = 0, nleaves = 0, depth = 0;
+    int root_leaf_link = 0;         // used when the whole mesh is one leaf (nodes has a single dummy)
+    float slack = 0.f;              // absolute fp32 error budget for every fp32 distance bound
+};
+void build_bvh(const double* tris, int ntri, HostBvh* out);
+
+struct DevBvh {
+    const BvhNode* nodes;
+    const float4* tri32;
+    const double* tri64;
+    int nnodes;
+    int ntri;
+    float slack;
+};
+
+struct DevPrim {
+    int shape;
+    double center[3];
+    double rot[9];
+    double dims[3];
+};
+
+constexpr int kMaxPrims = 16;
+
+struct EnvConst {
+    DevBvh obs;
+    DevBvh goal_mesh;
+    int nprim;
+    DevPrim prims[kMaxPrims];
+    DevPrim goal;  // shape NONE when absent
+};
+
+}  // namespace ctrb
+
+struct ctrb_env {
+    int device;
+    ctrb::EnvConst ec;
+    ctrb::EnvConst* d_ec;  // device copy (too big for comfortable by-value passing with 16 prims)
+    void* d_nodes[2];
+    void* d_tri32[2];
+    void* d_tri64[2];
+    int32_t stats[4];
+};
+
+namespace ctrb {
+// scratch helper: returns device pointer of at least `bytes` in slot `slot`
+int ctx_scratch(ctrb_ctx* ctx, int slot, size_t bytes, void** out);
+}  // namespace ctrb

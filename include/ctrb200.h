@@ -1,0 +1,217 @@
+/*
+ * ctrb200.h -- C ABI of libctrb200.so, the B200-native (sm_100a) hot path of
+ * CTR DaPP (ConorMesser/ctr-design-and-path-plan): batched strain-based
+ * concentric-tube model + tube-vs-environment collision/distance + cost.
+ *
+ * Each entry point names the reference interface it replaces (file:line in the
+ * upstream repository).  The reference is pure Python over python-fcl/SciPy,
+ * so "the reference's FFI for this path" is a ctypes binding; INTEGRATION.md
+ * shows the stub a maintainer would add to ctrdapp/model and ctrdapp/collision.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; nothing throws.
+ *   - every function returns CTRB_OK (0) or a negative ctrb_status;
+ *     ctrb_last_error() gives a thread-local message for the last failure.
+ *   - `mem` says where ALL data pointers of a batch call live:
+ *     CTRB_MEM_HOST (the library stages through pinned buffers and copies
+ *     H2D/D2H itself, synchronous on return) or CTRB_MEM_DEVICE (pointers are
+ *     device pointers on the ctx's device; the call is stream-ordered on the
+ *     ctx's stream and returns without synchronising).
+ *   - handles (model, env) are immutable after create: concurrent batch calls
+ *     with different ctx objects are legal.  A ctx owns one CUDA stream and
+ *     its scratch buffers and must not be used from two threads at once.
+ *   - SE(3) matrices are 4x4 row-major, position in [0:3,3] (kinematic.py,
+ *     collision_checker.py:124-126); twists are [omega; v].
+ *   - collision sentinel: obstacle_min / goal_dist == -1.0 exactly on contact
+ *     (collision_checker.py:70; callers test `< 0`, rrt.py:116,120); DBL_MAX
+ *     when there is no obstacle / no goal.
+ */
+#ifndef CTRB200_H
+#define CTRB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTRB_MAX_TUBES 4
+#define CTRB_MAX_DOF 8
+
+typedef enum {
+    CTRB_OK = 0,
+    CTRB_ERR_INVALID = -1,      /* bad argument (ValueError in the reference) */
+    CTRB_ERR_CUDA = -2,         /* CUDA runtime failure; no CPU fallback exists */
+    CTRB_ERR_UNSUPPORTED = -3,  /* NotImplementedError in the reference */
+    CTRB_ERR_NO_DEVICE = -4,
+    CTRB_ERR_ALLOC = -5
+} ctrb_status;
+
+typedef enum { CTRB_MEM_HOST = 0, CTRB_MEM_DEVICE = 1 } ctrb_mem;
+typedef enum { CTRB_F64 = 64, CTRB_F32 = 32 } ctrb_precision;
+
+/* strain_bases.py:227-268 get_strains() names */
+typedef enum {
+    CTRB_BASE_CONSTANT = 0,
+    CTRB_BASE_LINEAR = 1,
+    CTRB_BASE_QUADRATIC = 2,
+    CTRB_BASE_PURE_HELIX = 3,
+    CTRB_BASE_LINEAR_HELIX = 4,
+    CTRB_BASE_TORSION_HELIX = 5,
+    CTRB_BASE_TORSION_LINEAR_HELIX = 6,
+    CTRB_BASE_FULL = 7
+} ctrb_base_kind;
+
+typedef enum { CTRB_MODEL_KINEMATIC = 0, CTRB_MODEL_STATIC = 1 } ctrb_model_type;
+
+/* What create_model(configuration, q) reads (model_factory.py:12-78). */
+typedef struct {
+    int32_t model_type;                 /* ctrb_model_type */
+    int32_t tube_num;                   /* 'tube_number' */
+    int32_t base_kind[CTRB_MAX_TUBES];  /* 'strain_bases' */
+    int32_t q_dof[CTRB_MAX_TUBES];      /* 'q_dof' */
+    double q[CTRB_MAX_TUBES][CTRB_MAX_DOF];
+    double tube_length[CTRB_MAX_TUBES]; /* 'tube_lengths' */
+    double delta_x;                     /* 'delta_x' */
+    double radius_outer[CTRB_MAX_TUBES];/* 'tube_radius'.outer (static stiffness, static.py:561-585) */
+    double radius_inner[CTRB_MAX_TUBES];
+    int32_t static_degree;              /* 'degree' (static_bases.py) */
+    int32_t static_basis_type;          /* 0 = last_strain_base (the only one that runs) */
+} ctrb_model_desc;
+
+typedef enum {
+    CTRB_SHAPE_NONE = 0,
+    CTRB_SHAPE_SPHERE = 1,
+    CTRB_SHAPE_BOX = 2,
+    CTRB_SHAPE_CYLINDER = 3,
+    CTRB_SHAPE_MESH = 4
+} ctrb_shape;
+
+/* One primitive obstacle or the goal (init_collision.py:128-142). */
+typedef struct {
+    int32_t shape;
+    double center[3];   /* 'transform' */
+    double rot[9];      /* row-major; rotate_align('direction') for Cylinder, identity otherwise */
+    double dims[3];     /* Sphere: radius ; Box: x,y,z lengths ; Cylinder: radius, length */
+} ctrb_prim;
+
+/* cost selector (heuristic_factory.py:173-203) */
+typedef enum {
+    CTRB_COST_SOAPWG = 0,           /* square_obstacle_avg_plus_weighted_goal */
+    CTRB_COST_ONLY_GOAL = 1,        /* only_goal_distance */
+    CTRB_COST_FTL = 2,              /* follow_the_leader */
+    CTRB_COST_FTL_W_INSERTION = 3,  /* follow_the_leader_w_insertion */
+    CTRB_COST_FTL_TRANSLATION = 4   /* follow_the_leader_translation */
+} ctrb_cost_type;
+
+typedef struct {
+    int32_t cost_type;
+    double goal_weight;       /* SOAPWG */
+    int32_t only_tip;         /* FTL family */
+    double insertion_weight;  /* FTL_W_INSERTION */
+} ctrb_cost_desc;
+
+typedef struct ctrb_model ctrb_model;
+typedef struct ctrb_env ctrb_env;
+typedef struct ctrb_ctx ctrb_ctx;
+
+/* ---- library ---- */
+const char* ctrb_last_error(void);
+const char* ctrb_version(void);
+int ctrb_device_count(void);
+
+/* ---- execution context: device, stream, scratch ---- */
+int ctrb_ctx_create(int device, ctrb_ctx** out);
+void ctrb_ctx_destroy(ctrb_ctx* ctx);
+int ctrb_ctx_synchronize(ctrb_ctx* ctx);
+/* kernels launched by this ctx so far (bench.py's gpu_launches). */
+int64_t ctrb_ctx_launch_count(const ctrb_ctx* ctx);
+/* milliseconds the ctx's stream spent between the two most recent
+ * ctrb_ctx_mark() calls (CUDA events on the launching stream). */
+int ctrb_ctx_mark(ctrb_ctx* ctx, int which /*0 = start, 1 = stop*/);
+int ctrb_ctx_elapsed_ms(ctrb_ctx* ctx, float* ms);
+
+/* ---- model: replaces create_model() / Model.__init__ (model_factory.py:12-78, model.py:33-38) ---- */
+int ctrb_model_create(ctrb_ctx* ctx, const ctrb_model_desc* desc, ctrb_model** out);
+void ctrb_model_destroy(ctrb_model* m);
+/* num_discrete_points (model.py:37-38) */
+int ctrb_model_num_points(const ctrb_model* m, int32_t* npts /*[tube_num]*/);
+
+/* ---- environment: replaces CollisionChecker.__init__ / add_obstacles / add_goal
+ *      (collision_checker.py:31-33, init_collision.py:14-146).  Triangles are
+ *      [n][3][3] doubles, already translated (float32 STL vertex promoted to
+ *      double + 'transform', init_collision.py:82-86,125). ---- */
+int ctrb_env_create(ctrb_ctx* ctx, const double* obstacle_tris, int32_t n_obstacle_tris, const ctrb_prim* prims,
+                    int32_t n_prims, const ctrb_prim* goal /* may be NULL */, const double* goal_tris,
+                    int32_t n_goal_tris, ctrb_env** out);
+void ctrb_env_destroy(ctrb_env* e);
+/* BVH statistics for reporting: nodes, leaves, max depth, triangles */
+int ctrb_env_stats(const ctrb_env* e, int32_t out[4]);
+
+/* ---- index rounding: replaces calculate_indices() (kinematic.py:201-274), batched.
+ *      prev/next insertions are in the model's inverted coordinate (s = L - insertion). ---- */
+int ctrb_calculate_indices_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const double* prev_ins /*[B][T]*/,
+                                 const double* next_ins /*[B][T]*/, int32_t* prev_idx /*[B][T]*/,
+                                 int32_t* new_idx /*[B][T]*/, int mem);
+
+/* ---- g-curves: replaces Kinematic.solve_g (kinematic.py:82-130) for B configurations.
+ *      Output is ragged and packed: tube n of config b owns nodes
+ *      [node_offsets[b*T+n], node_offsets[b*T+n+1]) of g_out, each node a 4x4
+ *      row-major matrix of `precision`.  With full == 0 tube n has
+ *      npts[n]-idx[b][n] nodes (kinematic.py:100-103), with full != 0 npts[n]. ---- */
+int ctrb_g_node_offsets(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx /*[B][T]*/, int full,
+                        int64_t* node_offsets /*[B*T+1]*/, int mem);
+int ctrb_solve_g_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx /*[B][T]*/,
+                       const double* theta /*[B][T]*/, int full, int precision,
+                       const int64_t* node_offsets /*[B*T+1]*/, void* g_out, int mem);
+
+/* ---- eta + follow-the-leader: replaces Kinematic.solve_eta (kinematic.py:132-198).
+ *      prev_g is packed like ctrb_solve_g_batch output (fp64) with prev_offsets;
+ *      tube n of config b must hold npts[n]-prev_idx[b][n] nodes.
+ *      ftl_out (may be NULL) is packed with the same offsets, 6 doubles per node;
+ *      ftl_mag[b][0] = magnitude at the tip node of the last tube,
+ *      ftl_mag[b][1] = mean magnitude over all nodes (follow_the_leader.py:29-38,89-116),
+ *      [2],[3] = the same with the translation-only magnitude (:173-189).
+ *      Exactly one of new_idx / velocity is given: solve_integrate derives the velocity
+ *      from the rounded indices, (prev_idx - new_idx) * delta_x (kinematic.py:71); solve_eta's
+ *      own signature takes it as a float list (kinematic.py:132). ---- */
+int ctrb_eta_ftl_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* prev_idx /*[B][T]*/,
+                       const int32_t* new_idx /*[B][T] or NULL*/, const double* velocity /*[B][T] or NULL*/,
+                       const double* delta_theta /*[B][T]*/,
+                       const double* prev_g, const int64_t* prev_offsets /*[B*T+1]*/,
+                       double* eta_out /*[B][T][6]*/, double* ftl_out /* nullable */, double* ftl_mag /*[B][4]*/,
+                       int mem);
+
+/* ---- collision on given curves: replaces CollisionChecker.check_collision
+ *      (collision_checker.py:35-70) for B curves.  g is packed fp64 4x4 nodes with
+ *      node_offsets as above; rad[T] are the tube radii. ---- */
+int ctrb_check_collision_batch(ctrb_ctx* ctx, const ctrb_env* env, int64_t B, int32_t tube_num, const double* g,
+                               const int64_t* node_offsets /*[B*T+1]*/, const double* rad /*[T]*/,
+                               double* obstacle_min /*[B]*/, double* goal_dist /*[B]*/, int mem);
+
+/* ---- fused hot path: g-curve (never leaves the SM) + collision/distance + own cost:
+ *      replaces the solve_g -> check_collision -> heuristic_factory.create chain of
+ *      RRT._single_iteration (rrt.py:110-129) for B independent configurations.
+ *      cost follows rrt.py:116-129: NaN for colliding configs (the planner discards
+ *      them), goal_dist clamped at 0 when the tip is at the goal.
+ *      collide[b] = 1 iff obstacle_min[b] < 0. ---- */
+int ctrb_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, const ctrb_cost_desc* cost_desc,
+                    int64_t B, const int32_t* idx /*[B][T]*/, const double* theta /*[B][T]*/,
+                    const double* rad /*[T], host pointer always*/, double* obstacle_min /*[B]*/,
+                    double* goal_dist /*[B]*/, double* cost /*[B]*/, uint8_t* collide /*[B], nullable*/, int mem);
+
+/* work counters of the most recent ctrb_eval_batch / ctrb_check_collision_batch on this ctx
+ * (bench publishes them): [0] BVH nodes visited, [1] fp32 point-triangle
+ * prefilter tests, [2] exact fp64 cylinder-triangle tests, [3] configurations. Synchronises. */
+int ctrb_ctx_work_counters(ctrb_ctx* ctx, uint64_t out[4]);
+
+/* best (lowest finite cost) configuration of a cost vector: packed key reduction on the
+ * device; the multi-GPU driver all-reduces (min) the returned key over NCCL.
+ * key = monotone fp64 bits of the cost (upper 64 - 24 bits) ... see DESIGN.md. */
+int ctrb_argmin_cost(ctrb_ctx* ctx, int64_t B, const double* cost, int64_t index_base, double* best_cost,
+                     int64_t* best_index, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTRB200_H */
