@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- configs/sec of the fused hot path (g-curve + collision/distance + cost).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libctrb200, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on all host threads
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 3-tube model,
+tube_lengths [33,66,99] at delta_x = 1 (100 arc-length nodes on the longest tube), against
+colon_straight.STL (11 492 triangles) posed mid-lumen, 10^7 configurations per step and GPU.
+A "step" is one pass of the hot path over one batch: g-curve positions (never leave the SM),
+chain-vs-mesh distance, goal distance, own cost, and the best-node reduction.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "ctr-design-and-path-plan_b200", ROOT / "tests"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+BASES, DOF = ["linear"] * 3, [2, 3, 3]
+Q = [0.02, 0.001, 0.05, 0.0001, 0.002, 0.03, 0.0002, 0.0005]
+LENGTHS, DX, RAD = [33, 66, 99], 1, [1.2, 0.9, 0.6]
+NPTS = [34, 67, 100]
+GOAL_WEIGHT = 3.0
+ENV_FILE = ROOT / "tests" / "fixtures" / "env_c3_colon_straight.json"
+WORKLOADS = {  # exposure range per tube ("shallow" and "uniform")
+    "c3_kinematic_colon_straight_shallow": (1, 8),
+    "c3_kinematic_colon_straight_uniform": (1, 33),
+}
+BYTES_PER_CONFIG = 3 * (4 + 8) + (8 + 8 + 8 + 1)  # idx + theta in, obstacle_min + goal_dist + cost + bit out
+
+
+def make_inputs(B, seed, lo, hi):
+    rng = np.random.default_rng(seed)
+    e = np.stack([rng.integers(lo, min(hi, NPTS[t] - 1) + 1, B) for t in range(3)], 1)
+    idx = (np.asarray(NPTS)[None, :] - 1 - e).astype(np.int32)
+    theta = rng.uniform(0, 2 * np.pi, (B, 3))
+    return idx, theta
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def oracle_objects():
+    from oracle import oracle as orc
+    om = orc.make_model(BASES, DOF, Q, LENGTHS, DX)
+    oenv = orc.Env.from_json(ENV_FILE)
+    return orc, om, oenv
+
+
+def time_oracle(om, oenv, idx, theta, threads):
+    t0 = time.perf_counter()
+    obs, goal, cost = oenv.eval_batch(om, idx, theta, RAD, GOAL_WEIGHT, nthreads=threads)
+    return time.perf_counter() - t0, obs
+
+
+def run_reference(args, rank):
+    """CPU arm: the reference's own path is pure Python over python-fcl (not installable offline), so the
+    timed implementation is the C oracle port of it, on every host thread this process may use."""
+    if rank != 0:
+        return
+    lo, hi = WORKLOADS[args.workload]
+    threads = len(os.sched_getaffinity(0))
+    _, om, oenv = oracle_objects()
+    idx, theta = make_inputs(args.ref_sample, 1003, lo, hi)
+    for _ in range(args.warmup):
+        time_oracle(om, oenv, idx, theta, threads)
+    times = []
+    for _ in range(args.steps):
+        dt, obs = time_oracle(om, oenv, idx, theta, threads)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = args.ref_sample / (ms * 1e-3)
+    sample = f"{args.ref_sample} configs/step of {args.workload} (seed 1003), collide fraction {(obs < 0).mean():.3f}"
+    line = {"impl": "reference", "metric": "configs/sec (g-curve + collision + cost)", "value": value,
+            "unit": "configs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": args.workload, "configs_per_step": args.ref_sample,
+                                            "model": "3-tube kinematic, 100 arc-length nodes",
+                                            "environment": "colon_straight.STL (11492 triangles), mid-lumen pose"},
+            "cpu_baseline": {"value": value, "unit": "configs/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "configs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=10_000_000, help="configurations per step and per GPU")
+    ap.add_argument("--workload", default="c3_kinematic_colon_straight_shallow", choices=list(WORKLOADS))
+    ap.add_argument("--ref-sample", type=int, default=65536, help="configs per step of the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / kernels report")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from ctrdapp_b200 import _lib as L
+    from ctrdapp_b200.collision import CollisionChecker
+    from ctrdapp_b200.model.kinematic import Kinematic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libctrb200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = L.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    m = Kinematic(3, [np.array(Q[0:2]), np.array(Q[2:5]), np.array(Q[5:8])], DOF, LENGTHS, DX, BASES, ctx=ctx)
+    cc = CollisionChecker(ENV_FILE, ctx=ctx)
+    lo, hi = WORKLOADS[args.workload]
+    B = args.batch
+    idx_h, theta_h = make_inputs(B, 1003 + rank, lo, hi)
+
+    # ---- device-resident arm: inputs already in HBM
+    idx_d = torch.from_numpy(idx_h).to(dev)
+    theta_d = torch.from_numpy(theta_h).to(dev)
+    obs_d = torch.empty(B, dtype=torch.float64, device=dev)
+    goal_d = torch.empty(B, dtype=torch.float64, device=dev)
+    cost_d = torch.empty(B, dtype=torch.float64, device=dev)
+    coll_d = torch.empty(B, dtype=torch.uint8, device=dev)
+    rad = np.ascontiguousarray(RAD, np.float64)
+    cd = L.CostDesc(L.COST_TYPES["square_obstacle_avg_plus_weighted_goal"], GOAL_WEIGHT, 1, 0.0)
+    gathered = torch.empty(world * 2, dtype=torch.float64, device=dev) if world > 1 else None
+    lib = L.lib()
+
+    def eval_dev():
+        L.check(lib.ctrb_eval_batch(ctx.handle, m.handle, cc.handle, C.byref(cd), B, L.ptr(idx_d), L.ptr(theta_d),
+                                    L.ptr(rad), L.ptr(obs_d), L.ptr(goal_d), L.ptr(cost_d), L.ptr(coll_d), L.MEM_DEVICE))
+
+    def step():
+        eval_dev()
+        best_cost, best_index = C.c_double(), C.c_int64()
+        L.check(lib.ctrb_argmin_cost(ctx.handle, B, L.ptr(cost_d), rank * B, C.byref(best_cost), C.byref(best_index),
+                                     L.MEM_DEVICE))
+        if world > 1:  # gather every rank's best node; the payload is 16 B per rank
+            mine = torch.tensor([best_cost.value, float(best_index.value)], dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, mine)
+            g = gathered.view(world, 2).cpu().numpy()
+            k = int(np.argmin(g[:, 0]))
+            return float(g[k, 0]), int(g[k, 1])
+        return best_cost.value, best_index.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        best = step()
+    barrier()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        ctx.mark(0)
+        eval_dev()
+        ctx.mark(1)
+        best_cost, best_index = C.c_double(), C.c_int64()
+        L.check(lib.ctrb_argmin_cost(ctx.handle, B, L.ptr(cost_d), rank * B, C.byref(best_cost), C.byref(best_index),
+                                     L.MEM_DEVICE))
+        if world > 1:
+            mine = torch.tensor([best_cost.value, float(best_index.value)], dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, mine)
+        kern_ms.append(ctx.elapsed_ms())
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    work = ctx.work_counters()
+    collide_frac = float((obs_d < 0).double().mean().item())
+
+    # ---- e2e arm: HOST (pinned) buffers through the C ABI, copies inside the timed region
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
+    idx_p, theta_p = pin(idx_h), pin(theta_h)
+    obs_p, goal_p, cost_p = (pin(np.empty(B)) for _ in range(3))
+    coll_p = pin(np.empty(B, np.uint8))
+
+    def step_host():
+        L.check(lib.ctrb_eval_batch(ctx.handle, m.handle, cc.handle, C.byref(cd), B, L.ptr(idx_p), L.ptr(theta_p),
+                                    L.ptr(rad), L.ptr(obs_p), L.ptr(goal_p), L.ptr(cost_p), L.ptr(coll_p), L.MEM_HOST))
+        return float(np.nanmin(cost_p)) if np.isfinite(cost_p).any() else float("inf")
+
+    step_host()
+    barrier()
+    n_e2e = max(2, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / float(te.item())
+    assert np.array_equal(obs_p < 0, (obs_d < 0).cpu().numpy())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (chain_eval_kernel<fused>), timed live with CUDA events on its stream
+    peak, peak_src = measured_peaks()
+    k_ms = float(np.mean(kern_ms))
+    achieved = BYTES_PER_CONFIG * B / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "chain_eval_kernel<true>", "kernel_ms": k_ms,
+                "algorithmic_bytes_per_config": BYTES_PER_CONFIG, "peak_source": peak_src,
+                "note": "latency/compute-bound tree traversal: HBM traffic is ~61 B/config by construction; "
+                        "see compute_roofline for the binding resource"}
+    f32_peak, f64_peak = ctx.measure_fma_peak(32), ctx.measure_fma_peak(64)
+    per = 1.0 / max(work["configs"], 1)
+    flop32 = (work["bvh_nodes"] * 30.0 + work["prefilter_tests"] * 60.0) * per
+    flop64 = work["exact_tests"] * 350.0 * per
+    compute = {"bvh_nodes_per_config": work["bvh_nodes"] * per, "prefilter_tests_per_config": work["prefilter_tests"] * per,
+               "exact_tests_per_config": work["exact_tests"] * per, "fp32_flop_per_config": flop32,
+               "fp64_flop_per_config": flop64, "fp32_tflops_achieved": flop32 * B / (k_ms * 1e-3) / 1e12,
+               "fp64_tflops_achieved": flop64 * B / (k_ms * 1e-3) / 1e12, "fp32_fma_peak_tflops_measured": f32_peak,
+               "fp64_fma_peak_tflops_measured": f64_peak,
+               "flop_model": "30/BVH node + 60/point-triangle prefilter (fp32), 350/exact cylinder-triangle (fp64), SURVEY 8d"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        _, om, oenv = oracle_objects()
+        dt, _ = time_oracle(om, oenv, idx_h[:8192], theta_h[:8192], threads)
+        n = int(min(B, max(8192, 15.0 / max(dt / 8192, 1e-9))))
+        dt, o_obs = time_oracle(om, oenv, idx_h[:n], theta_h[:n], threads)
+        agree = bool(np.array_equal(o_obs < 0, obs_p[:n] < 0))
+        cpu = {"value": n / dt, "unit": "configs/s", "cores": threads, "kind": "port",
+               "sample": f"first {n} configs of the timed batch ({dt:.1f} s, oracle C port of the reference path, "
+                         f"pthreads; collision bits equal to the GPU's: {agree})"}
+
+    extra = {}
+    if not args.no_extra:
+        # secondary figures (not bench lines): the other exposure distribution, and the C2 g-curve kernel
+        for name, (l2, h2) in WORKLOADS.items():
+            if name == args.workload:
+                continue
+            Bx = min(B, 2_000_000)
+            ih, th = make_inputs(Bx, 1003, l2, h2)
+            idd, thd = torch.from_numpy(ih).to(dev), torch.from_numpy(th).to(dev)
+            for rep in range(2):
+                ctx.mark(0)
+                L.check(lib.ctrb_eval_batch(ctx.handle, m.handle, cc.handle, C.byref(cd), Bx, L.ptr(idd), L.ptr(thd),
+                                            L.ptr(rad), L.ptr(obs_d), L.ptr(goal_d), L.ptr(cost_d), L.ptr(coll_d), L.MEM_DEVICE))
+                ctx.mark(1)
+                ms = ctx.elapsed_ms()
+            extra[name] = {"configs_per_s": Bx / (ms * 1e-3), "collide_fraction": float((obs_d[:Bx] < 0).double().mean().item())}
+        m2 = Kinematic(2, [np.array([0.02, 0.001]), np.array([0.05, 0.0001, 0.002])], [2, 3], [120, 120], 1,
+                       ["linear", "linear"], ctx=ctx)
+        rng = np.random.default_rng(1002)
+        B2 = 1_000_000
+        i2 = torch.from_numpy(rng.integers(0, 121, (B2, 2)).astype(np.int32)).to(dev)
+        t2 = torch.from_numpy(rng.uniform(0, 2 * np.pi, (B2, 2))).to(dev)
+        off = torch.empty(B2 * 2 + 1, dtype=torch.int64, device=dev)
+        L.check(lib.ctrb_g_node_offsets(ctx.handle, m2.handle, B2, L.ptr(i2), 0, L.ptr(off), L.MEM_DEVICE))
+        total = int(off[-1].item())
+        for prec, dt_ in ((64, torch.float64), (32, torch.float32)):
+            g = torch.empty((total, 4, 4), dtype=dt_, device=dev)
+            for rep in range(3):
+                ctx.mark(0)
+                L.check(lib.ctrb_solve_g_batch(ctx.handle, m2.handle, B2, L.ptr(i2), L.ptr(t2), 0, prec, L.ptr(off),
+                                               L.ptr(g), L.MEM_DEVICE))
+                ctx.mark(1)
+                ms = ctx.elapsed_ms()
+            gbs = g.numel() * g.element_size() / (ms * 1e-3) / 1e9
+            extra[f"c2_gcurve_fp{prec}"] = {"configs_per_s": B2 / (ms * 1e-3), "ms": ms, "nodes": total,
+                                            "hbm_write_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+            del g
+
+    line = {"metric": "configs/sec (g-curve + collision + cost)", "value": value, "unit": "configs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "configs_per_step_per_gpu": B,
+                       "model": "3-tube kinematic (linear bases, q_dof [2,3,3]), tube_lengths [33,66,99], delta_x 1",
+                       "environment": "colon_straight.STL (11492 triangles) translated to a mid-lumen pose + Sphere(5) goal",
+                       "exposure_per_tube": [lo, hi], "collide_fraction": collide_frac,
+                       "l2": "inputs+outputs are 610 MB per step (> 126 MB L2); no explicit flush",
+                       "parallelism": f"dp{world} (configs sharded, best node gathered over NCCL)" if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": B * 3 * 12, "d2h_bytes_per_step": B * 25,
+                    "steps": n_e2e, "path": "ctrb_eval_batch(CTRB_MEM_HOST) on pinned numpy buffers"},
+            "gpu_launches": int(launches), "roofline": roofline, "compute_roofline": compute,
+            "best_node": {"cost": best[0], "index": best[1]}, "bvh": cc.stats()}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    if extra:
+        line["extra"] = extra
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

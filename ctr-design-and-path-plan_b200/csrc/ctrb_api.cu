@@ -61,6 +61,7 @@ int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube
                        const long long* offsets, int max_nodes, const double* rad, double* obstacle_min,
                        double* goal_dist);
 int launch_argmin(ctrb_ctx* ctx, long long B, const double* cost, unsigned long long* key_out);
+int launch_fma_peak(ctrb_ctx* ctx, int precision, double* tflops);
 
 }  // namespace ctrb
 
@@ -140,6 +141,7 @@ int ctrb_ctx_create(int device, ctrb_ctx** out) {
     std::memset(c, 0, sizeof *c);
     c->device = device;
     CTRB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = c->stream;
     CTRB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CTRB_CUDA(cudaEventCreate(&c->ev[i]));
@@ -171,7 +173,7 @@ void ctrb_ctx_destroy(ctrb_ctx* c) {
         cudaEventDestroy(c->ev[i]);
         cudaEventDestroy(c->ev_chunk[i]);
     }
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->stream2);
     delete c;
 }
@@ -182,6 +184,21 @@ int ctrb_ctx_synchronize(ctrb_ctx* c) {
     CTRB_CUDA(cudaStreamSynchronize(c->stream));
     CTRB_CUDA(cudaStreamSynchronize(c->stream2));
     return CTRB_OK;
+}
+
+int ctrb_ctx_set_stream(ctrb_ctx* c, void* cuda_stream) {
+    CTRB_REQUIRE(c, "ctx is NULL");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return CTRB_OK;
+}
+
+int ctrb_measure_fma_peak(ctrb_ctx* c, int precision, double* tflops) {
+    CTRB_REQUIRE(c && tflops, "bad argument");
+    CTRB_REQUIRE(precision == CTRB_F64 || precision == CTRB_F32, "precision must be 64 or 32");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    return launch_fma_peak(c, precision, tflops);
 }
 
 int64_t ctrb_ctx_launch_count(const ctrb_ctx* c) { return c ? c->launches : 0; }

@@ -58,6 +58,7 @@ struct ModelTables {
 struct ctrb_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t own_stream;
     cudaStream_t stream2;  // second stream for host-memory chunk pipelining
     cudaEvent_t ev[2];
     cudaEvent_t ev_chunk[2];

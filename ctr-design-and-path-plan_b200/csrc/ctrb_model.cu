@@ -377,6 +377,52 @@ __global__ void __launch_bounds__(kEWarps * 32)
     }
 }
 
+// ------------------------------------------------------------------ FMA peak probe (compute-roofline denominator)
+template <typename F>
+__global__ void __launch_bounds__(256) fma_peak_kernel(F* out, int iters, F seed) {
+    F a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + (F)(threadIdx.x + k);
+    const F m = (F)0.999999, c = (F)1e-3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = a[k] * m + c;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = a[k] * m + c;
+    }
+    F s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == (F)-1) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true: keeps the chain live
+}
+
+int launch_fma_peak(ctrb_ctx* ctx, int precision, double* tflops) {
+    void* d = nullptr;
+    int rc = ctx_scratch(ctx, 0, 1 << 20, &d);
+    if (rc) return rc;
+    const int grid = ctx->sm_count * 8, iters = precision == CTRB_F64 ? 4096 : 16384;
+    cudaEvent_t e0, e1;
+    CTRB_CUDA(cudaEventCreate(&e0));
+    CTRB_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CTRB_CUDA(cudaEventRecord(e0, ctx->stream));
+        if (precision == CTRB_F64) fma_peak_kernel<double><<<grid, 256, 0, ctx->stream>>>((double*)d, iters, 1.0);
+        else fma_peak_kernel<float><<<grid, 256, 0, ctx->stream>>>((float*)d, iters, 1.0f);
+        CTRB_CUDA(cudaEventRecord(e1, ctx->stream));
+        CTRB_CUDA(cudaEventSynchronize(e1));
+        float ms;
+        CTRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+        ctx->launches++;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double flops = 2.0 * 16.0 * (double)iters * 256.0 * (double)grid;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return CTRB_OK;
+}
+
 // ------------------------------------------------------------------ host launchers (called from ctrb_api.cu)
 int launch_table(ctrb_ctx* ctx, const ctrb_model* m) {
     kin_table_kernel<<<1, 32, 0, ctx->stream>>>(m->mc, m->d_tab, m->d_tab_inv, m->d_tabR32);

@@ -53,6 +53,8 @@ SYMBOLS = {
     "ctrb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "ctrb_ctx_destroy": (None, [_vp]),
     "ctrb_ctx_synchronize": (C.c_int, [_vp]),
+    "ctrb_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "ctrb_measure_fma_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "ctrb_ctx_launch_count": (_i64, [_vp]),
     "ctrb_ctx_mark": (C.c_int, [_vp, C.c_int]),
     "ctrb_ctx_elapsed_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
@@ -149,6 +151,15 @@ class Context:
 
     def synchronize(self):
         check(lib().ctrb_ctx_synchronize(self._h))
+
+    def set_stream(self, cuda_stream):
+        """Launch on a caller-owned cudaStream_t (int handle); None restores the ctx's own stream."""
+        check(lib().ctrb_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def measure_fma_peak(self, precision=64):
+        out = C.c_double()
+        check(lib().ctrb_measure_fma_peak(self._h, precision, C.byref(out)))
+        return out.value
 
     def launch_count(self):
         return int(lib().ctrb_ctx_launch_count(self._h))

@@ -124,12 +124,19 @@ int ctrb_device_count(void);
 int ctrb_ctx_create(int device, ctrb_ctx** out);
 void ctrb_ctx_destroy(ctrb_ctx* ctx);
 int ctrb_ctx_synchronize(ctrb_ctx* ctx);
+/* Launch on a caller-owned stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
+ * so that the caller's events and collectives order with the kernels; NULL restores the ctx's own. */
+int ctrb_ctx_set_stream(ctrb_ctx* ctx, void* cuda_stream);
 /* kernels launched by this ctx so far (bench.py's gpu_launches). */
 int64_t ctrb_ctx_launch_count(const ctrb_ctx* ctx);
 /* milliseconds the ctx's stream spent between the two most recent
  * ctrb_ctx_mark() calls (CUDA events on the launching stream). */
 int ctrb_ctx_mark(ctrb_ctx* ctx, int which /*0 = start, 1 = stop*/);
 int ctrb_ctx_elapsed_ms(ctrb_ctx* ctx, float* ms);
+
+/* Measured CUDA-core FMA peak of this device (dependent-free FMA chains on every SM), the
+ * denominator of the compute roofline of the collision kernel: precision CTRB_F32 / CTRB_F64. */
+int ctrb_measure_fma_peak(ctrb_ctx* ctx, int precision, double* tflops);
 
 /* ---- model: replaces create_model() / Model.__init__ (model_factory.py:12-78, model.py:33-38) ---- */
 int ctrb_model_create(ctrb_ctx* ctx, const ctrb_model_desc* desc, ctrb_model** out);

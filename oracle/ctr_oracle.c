@@ -889,9 +889,13 @@ int orc_env_check_collision(const orc_env* env, const double* pos, const int* co
             }
         }
         p += 3 * counts[n];
-        if (counts[n] > 0) tip = p - 3;
     }
     out[0] = (best <= 0.0) ? -1.0 : best;
+    { /* curve[-1][-1]: last node of the last tube, whether or not the obstacle loop ended early */
+        int total = 0;
+        for (int n = 0; n < ntubes; ++n) total += counts[n];
+        if (total > 0 && counts[ntubes - 1] > 0) tip = pos + 3 * (size_t)(total - 1);
+    }
 
     /* collision_checker.py:62-68 */
     double gd = DBL_MAX;

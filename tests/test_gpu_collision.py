@@ -48,7 +48,8 @@ def test_reference_literals():
 
 
 @pytest.mark.parametrize("env_name,lo,hi", [("env_colon_straight_new.json", 1, 8), ("env_colon_straight_new.json", 1, 33),
-                                            ("env_c3_colon_straight.json", 1, 8), ("env_colon_angled.json", 1, 12)])
+                                            ("env_c3_colon_straight.json", 1, 8), ("env_c3_colon_straight.json", 1, 20),
+                                            ("env_colon_angled.json", 1, 12)])
 def test_fused_eval_vs_oracle(env_name, lo, hi):
     from oracle import oracle as orc
     from ctrdapp_b200.collision import CollisionChecker
@@ -76,8 +77,8 @@ def test_check_collision_batch_given_curves():
     from oracle import oracle as orc
     from ctrdapp_b200.collision import CollisionChecker
     m, om = gpu_model("config_yaml"), orc_model("config_yaml")
-    cc = CollisionChecker(FIXTURES / "env_c1b_in_simple.json")
-    oenv = orc.Env.from_json(FIXTURES / "env_c1b_in_simple.json")
+    cc = CollisionChecker(FIXTURES / "env_boxes_multi.json")
+    oenv = orc.Env.from_json(FIXTURES / "env_boxes_multi.json")
     rng = np.random.default_rng(1001)
     B = 256
     idx, theta = random_configs(m.num_discrete_points, B, rng)
@@ -90,6 +91,18 @@ def test_check_collision_batch_given_curves():
         o_obs[b], o_goal[b] = oenv.check_collision(curve, [0.9, 0.6])
     _compare(obs, goal, o_obs, o_goal)
     assert (obs > 0).sum() > 10 and (obs < 0).sum() > 0
+
+
+def test_c3_survey_pose_all_collide():
+    """SURVEY 8d's pose of colon_straight.STL puts a wall within 3.4 mm of the robot base:
+    every configuration with >= 1 mm exposed per tube collides (first-contact exit regime)."""
+    from ctrdapp_b200.collision import CollisionChecker
+    m = gpu_model("c3_three_tube")
+    cc = CollisionChecker(FIXTURES / "env_c3_survey_pose.json")
+    rng = np.random.default_rng(1003)
+    idx, theta = random_configs(m.num_discrete_points, 20000, rng, 1, 33)
+    obs, goal, cost, coll = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
+    assert (obs == -1.0).mean() > 0.999 and np.all(goal > 0)
 
 
 def test_c1_box_at_base_all_collide():
@@ -179,12 +192,12 @@ def test_large_batch_properties():
     cc = CollisionChecker(FIXTURES / "env_c3_colon_straight.json")
     rng = np.random.default_rng(1003)
     B = 1_000_000
-    idx, theta = random_configs(m.num_discrete_points, B, rng, 1, 33)
+    idx, theta = random_configs(m.num_discrete_points, B, rng, 1, 8)
     obs, goal, cost, coll = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
     assert np.array_equal(coll == 1, obs == -1.0)
     assert np.all((obs == -1.0) | (obs > 0))
     free = obs > 0
-    assert 0.001 < free.mean() < 0.5
+    assert 0.1 < free.mean() < 0.6
     np.testing.assert_allclose(cost[free], 3.0 * np.maximum(goal[free], 0) + 1.0 / obs[free] ** 2, rtol=1e-12)
     sub = rng.choice(B, 1500, replace=False)
     oenv = orc.Env.from_json(FIXTURES / "env_c3_colon_straight.json")
