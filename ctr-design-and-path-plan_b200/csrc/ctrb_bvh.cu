@@ -13,7 +13,13 @@
 namespace ctrb {
 
 namespace {
-constexpr int kLeafMax = 4;
+#ifndef CTRB_LEAF_MAX
+#define CTRB_LEAF_MAX 4
+#endif
+#ifndef CTRB_LEAF_FORCE
+#define CTRB_LEAF_FORCE 0
+#endif
+constexpr int kLeafMax = CTRB_LEAF_MAX;
 constexpr int kBins = 16;
 
 struct Box {
@@ -151,7 +157,7 @@ void build_bvh(const double* tris, int ntri, HostBvh* out) {
             }
         }
         double leaf_cost = nd.box.area() * nd.count;
-        bool make_leaf = (nd.count <= kLeafMax) && (best_axis < 0 || best_cost >= leaf_cost);
+        bool make_leaf = (nd.count <= kLeafMax) && (CTRB_LEAF_FORCE || best_axis < 0 || best_cost >= leaf_cost);
         if (make_leaf) continue;
         int mid;
         if (best_axis < 0) {  // all centroids coincide: split evenly

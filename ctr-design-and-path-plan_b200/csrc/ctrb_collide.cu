@@ -28,8 +28,17 @@
 
 namespace ctrb {
 
-constexpr int kCWarps = 8;        // warps (= configurations in flight) per block
-constexpr int kTopNodes = 256;    // BVH nodes staged in shared memory (BFS prefix = top ~8 levels)
+#ifndef CTRB_EVAL_WARPS
+#define CTRB_EVAL_WARPS 8
+#endif
+#ifndef CTRB_EVAL_MINBLOCKS
+#define CTRB_EVAL_MINBLOCKS 2
+#endif
+#ifndef CTRB_TOP_NODES
+#define CTRB_TOP_NODES 256
+#endif
+constexpr int kCWarps = CTRB_EVAL_WARPS;      // warps (= configurations in flight) per block
+constexpr int kTopNodes = CTRB_TOP_NODES;     // BVH nodes staged in shared memory (BFS prefix = top levels)
 constexpr int kStack = 48;
 
 struct WarpCtl {
@@ -79,7 +88,7 @@ struct Work {
 };
 
 // exact min distance of one solid cylinder against the mesh, sharing bounds through `ctl`
-__device__ void cylinder_vs_mesh(const DevBvh& bvh, const BvhNode* s_top, int ntop, d3 c, d3 a, double h, double r,
+__device__ __noinline__ void cylinder_vs_mesh(const DevBvh& bvh, const BvhNode* s_top, int ntop, d3 c, d3 a, double h, double r,
                                  WarpCtl* ctl, double& best_exact, Work& wk) {
     const f3 cf = {(float)c.x, (float)c.y, (float)c.z};
     const float slack = bvh.slack;
@@ -150,7 +159,7 @@ __device__ void cylinder_vs_mesh(const DevBvh& bvh, const BvhNode* s_top, int nt
 }
 
 // exact nearest distance from a point to a mesh (goal mesh): fp32 culling, fp64 leaves
-__device__ double point_vs_mesh(const DevBvh& bvh, d3 x, Work& wk) {
+__device__ __noinline__ double point_vs_mesh(const DevBvh& bvh, d3 x, Work& wk) {
     const f3 xf = {(float)x.x, (float)x.y, (float)x.z};
     const float slack = bvh.slack;
     double best = DBL_MAX;
@@ -207,7 +216,7 @@ __device__ void box_corner(const DevPrim& b, int k, d3& out) {
 }
 
 // solid cylinder vs primitive obstacle (fcl.Sphere / fcl.Box, init_collision.py:129-139)
-__device__ double cylinder_vs_prim(const DevPrim& o, d3 c, d3 a, double h, double r, double bound) {
+__device__ __noinline__ double cylinder_vs_prim(const DevPrim& o, d3 c, d3 a, double h, double r, double bound) {
     if (o.shape == CTRB_SHAPE_SPHERE) {
         double d = point_cyl_dist(d3{o.center[0], o.center[1], o.center[2]}, c, a, h, r) - o.dims[0];
         return d < 0.0 ? 0.0 : d;
@@ -232,7 +241,7 @@ __device__ double cylinder_vs_prim(const DevPrim& o, d3 c, d3 a, double h, doubl
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kCWarps * 32) chain_eval_kernel(EvalParams P) {
+__global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_kernel(EvalParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BvhNode* s_top = reinterpret_cast<BvhNode*>(smem_raw);
     double* s_pos_all = reinterpret_cast<double*>(smem_raw + (size_t)kTopNodes * sizeof(BvhNode));
@@ -426,7 +435,7 @@ int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
     }
     CTRB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     long long blocks_needed = (P.B + kCWarps - 1) / kCWarps;
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
     int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * per_sm);
     if (fused) {
         CTRB_CUDA(cudaFuncSetAttribute(chain_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -81,6 +81,10 @@ _lock = threading.Lock()
 
 
 def lib_path():
+    """In-tree library; CTRB200_LIB overrides it (used by tools/ to compare build variants)."""
+    import os
+    if os.environ.get("CTRB200_LIB"):
+        return pathlib.Path(os.environ["CTRB200_LIB"])
     return pathlib.Path(__file__).resolve().parent.parent / "libctrb200.so"
 
 
