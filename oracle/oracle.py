@@ -37,6 +37,11 @@ class OrcPrim(C.Structure):
                 ("dims", C.c_double * 3)]
 
 
+class OrcStatic(C.Structure):
+    _fields_ = [("m", OrcModel), ("r_out", C.c_double * MAX_TUBES), ("r_in", C.c_double * MAX_TUBES),
+                ("degree", C.c_int)]
+
+
 def build(force=False):
     so = _HERE / "libctr_oracle.so"
     srcs = [_HERE / "ctr_oracle.c", _HERE / "ctr_oracle.h", _HERE / "static_oracle.c"]
@@ -361,3 +366,53 @@ def build_tube(curve, rad):
                 quat = quat / np.linalg.norm(quat)
             out.append((rad[n], length, mid, quat))
     return out
+
+
+# ---------------------------------------------------------------- static model
+def make_static(strain_bases, q_dof, q, tube_lengths, delta_x, r_out, r_in, degree=2):
+    s = OrcStatic()
+    s.m = make_model(strain_bases, q_dof, q, tube_lengths, delta_x)
+    for n in range(len(tube_lengths)):
+        s.r_out[n] = float(r_out[n])
+        s.r_in[n] = float(r_in[n])
+    s.degree = degree
+    return s
+
+
+def static_init_guess(s):
+    x0 = np.zeros(64)
+    n = lib().orc_static_init_guess(C.byref(s), _dp(x0))
+    return x0[:n].copy()
+
+
+def static_residual(s, indices, thetas, q):
+    F = np.zeros(64)
+    n = lib().orc_static_residual(C.byref(s), _ip(np.ascontiguousarray(indices, np.int32)), _dp(_f64(thetas)),
+                                  _dp(_f64(q)), _dp(F))
+    return F[:n].copy()
+
+
+def static_curves(s, indices, thetas, sol):
+    T = s.m.tube_num
+    tot = sum(s.m.npts[n] for n in range(T))
+    g = np.zeros((tot, 4, 4))
+    counts = np.zeros(T, np.int32)
+    lib().orc_static_curves(C.byref(s), _ip(np.ascontiguousarray(indices, np.int32)), _dp(_f64(thetas)),
+                            _dp(_f64(sol)), _dp(g), _ip(counts))
+    return _split(g, counts.tolist(), (4, 4))
+
+
+def static_solve_g(s, indices, thetas, initial_guess=None, xtol=0.0):
+    """Static.solve_g (static.py:71-135) -> (g list, solution x, nfev, info)."""
+    T = s.m.tube_num
+    tot = sum(s.m.npts[n] for n in range(T))
+    g = np.zeros((tot, 4, 4))
+    counts = np.zeros(T, np.int32)
+    sol = np.zeros(64)
+    nfev, info = C.c_int(), C.c_int()
+    x0 = None if initial_guess is None else _dp(_f64(initial_guess))
+    lib().orc_static_solve_g.argtypes = None
+    lib().orc_static_solve_g(C.byref(s), _ip(np.ascontiguousarray(indices, np.int32)), _dp(_f64(thetas)), x0,
+                             C.c_double(xtol), _dp(g), _ip(counts), _dp(sol), C.byref(nfev), C.byref(info))
+    n = lib().orc_static_ndof(C.byref(s), _ip(np.ascontiguousarray(indices, np.int32)), _dp(_f64(thetas)))
+    return _split(g, counts.tolist(), (4, 4)), sol[:n].copy(), nfev.value, info.value
