@@ -61,7 +61,16 @@ int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube
                        const long long* offsets, int max_nodes, const double* rad, double* obstacle_min,
                        double* goal_dist);
 int launch_argmin(ctrb_ctx* ctx, long long B, const double* cost, unsigned long long* key_out);
+int launch_eval_curves_cost(ctrb_ctx* ctx, const ctrb_env* env, const ctrb_cost_desc* cd, long long B, int tube_num,
+                            const double* g, const long long* offsets, int max_nodes, const double* rad,
+                            double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide);
 int launch_fma_peak(ctrb_ctx* ctx, int precision, double* tflops);
+int static_model_init(const ctrb_model_desc* d, const ModelConst& mc, StModel* out);
+int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
+                        const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
+                        double* sol_out, int32_t* nfev_out, int32_t* info_out);
+int launch_static_residual(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
+                           const double* q, double* F);
 
 }  // namespace ctrb
 
@@ -248,11 +257,8 @@ int ctrb_model_create(ctrb_ctx* ctx, const ctrb_model_desc* d, ctrb_model** out)
     *out = nullptr;
     CTRB_REQUIRE(d->tube_num >= 1 && d->tube_num <= CTRB_MAX_TUBES, "tube_num %d not in 1..%d", d->tube_num, CTRB_MAX_TUBES);
     CTRB_REQUIRE(d->delta_x > 0.0, "delta_x must be positive");
-    if (d->model_type == CTRB_MODEL_STATIC) {
-        set_error("the static model is not built yet in this library version");
-        return CTRB_ERR_UNSUPPORTED;
-    }
-    CTRB_REQUIRE(d->model_type == CTRB_MODEL_KINEMATIC, "unknown model_type %d", d->model_type);
+    CTRB_REQUIRE(d->model_type == CTRB_MODEL_KINEMATIC || d->model_type == CTRB_MODEL_STATIC, "unknown model_type %d",
+                 d->model_type);
     ctrb_model* m = new ctrb_model();
     std::memset(m, 0, sizeof *m);
     m->desc = *d;
@@ -281,6 +287,14 @@ int ctrb_model_create(ctrb_ctx* ctx, const ctrb_model_desc* d, ctrb_model** out)
         tot += mc.npts[n];
     }
     mc.total_nodes = tot;
+    if (d->model_type == CTRB_MODEL_STATIC) {
+        int rcs = static_model_init(d, mc, &m->sm);
+        if (rcs) {
+            delete m;
+            return rcs;
+        }
+        m->is_static = 1;
+    }
     CTRB_CUDA(cudaSetDevice(ctx->device));
     CTRB_CUDA(cudaMalloc(&m->d_tab, (size_t)12 * tot * sizeof(double)));
     CTRB_CUDA(cudaMalloc(&m->d_tab_inv, (size_t)12 * tot * sizeof(double)));
@@ -602,6 +616,146 @@ int ctrb_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, con
     st.back(goal_dist, dgo, (size_t)B, mem);
     st.back(cost, dco, (size_t)B, mem);
     st.back(collide, dcl, (size_t)B, mem);
+    return st.finish(mem);
+}
+
+// ------------------------------------------------------------------ static model
+int ctrb_static_num_unknowns(const ctrb_model* m, int32_t* nq) {
+    CTRB_REQUIRE(m && nq, "NULL argument");
+    CTRB_REQUIRE(m->is_static, "not a static model handle");
+    *nq = m->sm.nq;
+    return CTRB_OK;
+}
+
+int ctrb_static_initial_guess(const ctrb_model* m, double* x0) {
+    CTRB_REQUIRE(m && x0, "NULL argument");
+    CTRB_REQUIRE(m->is_static, "not a static model handle");
+    for (int k = 0; k < m->sm.nq; ++k) x0[k] = m->sm.x0[k];
+    return CTRB_OK;
+}
+
+static int check_idx_host(const ctrb_model* m, int64_t B, const int32_t* idx) {
+    const size_t n = (size_t)B * m->mc.T;
+    for (size_t i = 0; i < n; ++i) {
+        int t = (int)(i % m->mc.T);
+        CTRB_REQUIRE(idx[i] >= 0 && idx[i] < m->mc.npts[t], "idx[%zu]=%d outside [0,%d)", i, idx[i], m->mc.npts[t]);
+    }
+    return CTRB_OK;
+}
+
+int ctrb_static_residual_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx, const double* theta,
+                               const double* q, double* F, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && B >= 0, "bad argument");
+    CTRB_REQUIRE(m->is_static, "not a static model handle");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(idx && theta && q && F, "NULL buffer");
+    const size_t n = (size_t)B * m->mc.T, nqs = (size_t)B * m->sm.nq;
+    if (mem == CTRB_MEM_HOST) {
+        int rc = check_idx_host(m, B, idx);
+        if (rc) return rc;
+    }
+    Stage st(ctx);
+    const int32_t* di = st.in(idx, n, mem);
+    const double* dt = st.in(theta, n, mem);
+    const double* dq = st.in(q, nqs, mem);
+    double* dF = st.out(F, nqs, mem);
+    if (st.rc) return st.rc;
+    int rc = launch_static_residual(ctx, m->sm, B, di, dt, dq, dF);
+    if (rc) return rc;
+    st.back(F, dF, nqs, mem);
+    return st.finish(mem);
+}
+
+int ctrb_static_solve_g_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx, const double* theta,
+                              const double* initial_guess, int x0_per_config, double xtol, const int64_t* node_offsets,
+                              double* g_out, double* solution_q, int32_t* nfev, int32_t* info, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && B >= 0, "bad argument");
+    CTRB_REQUIRE(m->is_static, "not a static model handle");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(idx && theta, "NULL buffer");
+    CTRB_REQUIRE(!g_out || node_offsets, "g_out needs node_offsets");
+    const size_t n = (size_t)B * m->mc.T, nqs = (size_t)B * m->sm.nq;
+    if (mem == CTRB_MEM_DEVICE) {
+        return launch_static_solve(ctx, m->sm, B, idx, theta, initial_guess, x0_per_config, xtol,
+                                   (const long long*)node_offsets, g_out, solution_q, nfev, info);
+    }
+    int rc = check_idx_host(m, B, idx);
+    if (rc) return rc;
+    Stage st(ctx);
+    const int32_t* di = st.in(idx, n, mem);
+    const double* dt = st.in(theta, n, mem);
+    const double* dx0 = initial_guess ? st.in(initial_guess, x0_per_config ? nqs : (size_t)m->sm.nq, mem) : nullptr;
+    const int64_t* doff = node_offsets ? st.in(node_offsets, n + 1, mem) : nullptr;
+    double* dsol = st.out(solution_q, nqs, mem);
+    int32_t* dnf = st.out(nfev, (size_t)B, mem);
+    int32_t* dinf = st.out(info, (size_t)B, mem);
+    if (st.rc) return st.rc;
+    void* dg = nullptr;
+    size_t total_nodes = 0;
+    if (g_out) {
+        total_nodes = (size_t)node_offsets[n];
+        rc = ctx_scratch(ctx, 10, total_nodes * 16 * sizeof(double), &dg);
+        if (rc) return rc;
+    }
+    rc = launch_static_solve(ctx, m->sm, B, di, dt, dx0, x0_per_config, xtol, (const long long*)doff, (double*)dg, dsol, dnf,
+                             dinf);
+    if (rc) return rc;
+    st.back(solution_q, dsol, nqs, mem);
+    st.back(nfev, dnf, (size_t)B, mem);
+    st.back(info, dinf, (size_t)B, mem);
+    if (g_out) CTRB_CUDA(cudaMemcpyAsync(g_out, dg, total_nodes * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return st.finish(mem);
+}
+
+int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, const ctrb_cost_desc* cd, int64_t B,
+                           const int32_t* idx, const double* theta, const double* rad, double* obstacle_min,
+                           double* goal_dist, double* cost, uint8_t* collide, int32_t* info, int32_t* nfev, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && env && cd && B >= 0, "bad argument");
+    CTRB_REQUIRE(m->is_static, "not a static model handle");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(idx && theta && rad && obstacle_min && goal_dist, "NULL buffer");
+    const int T = m->mc.T;
+    const size_t n = (size_t)B * T;
+    if (mem == CTRB_MEM_HOST) {
+        int rc = check_idx_host(m, B, idx);
+        if (rc) return rc;
+    }
+    Stage st(ctx);
+    const int32_t* di = st.in(idx, n, mem);
+    const double* dt = st.in(theta, n, mem);
+    double* dob = st.out(obstacle_min, (size_t)B, mem);
+    double* dgo = st.out(goal_dist, (size_t)B, mem);
+    double* dco = st.out(cost, (size_t)B, mem);
+    uint8_t* dcl = st.out(collide, (size_t)B, mem);
+    int32_t* dinf = st.out(info, (size_t)B, mem);
+    int32_t* dnf = st.out(nfev, (size_t)B, mem);
+    if (st.rc) return st.rc;
+    // ragged offsets and the g-curve scratch live on the device only
+    void* doff = nullptr;
+    int rc = ctx_scratch(ctx, 9, (n + 1) * sizeof(long long), &doff);
+    if (rc) return rc;
+    rc = launch_offsets(ctx, m, B, di, 0, (long long*)doff);
+    if (rc) return rc;
+    long long total = 0;
+    CTRB_CUDA(cudaMemcpyAsync(&total, (long long*)doff + n, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
+    void* dg = nullptr;
+    rc = ctx_scratch(ctx, 10, (size_t)total * 16 * sizeof(double), &dg);
+    if (rc) return rc;
+    rc = launch_static_solve(ctx, m->sm, B, di, dt, nullptr, 0, 0.0, (const long long*)doff, (double*)dg, nullptr, dnf, dinf);
+    if (rc) return rc;
+    rc = launch_eval_curves_cost(ctx, env, cd, B, T, (const double*)dg, (const long long*)doff, m->mc.total_nodes, rad, dob,
+                                 dgo, dco, dcl);
+    if (rc) return rc;
+    st.back(obstacle_min, dob, (size_t)B, mem);
+    st.back(goal_dist, dgo, (size_t)B, mem);
+    st.back(cost, dco, (size_t)B, mem);
+    st.back(collide, dcl, (size_t)B, mem);
+    st.back(info, dinf, (size_t)B, mem);
+    st.back(nfev, dnf, (size_t)B, mem);
     return st.finish(mem);
 }
 

@@ -491,6 +491,27 @@ int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube
     return launch_eval(ctx, P, false);
 }
 
+int launch_eval_curves_cost(ctrb_ctx* ctx, const ctrb_env* env, const ctrb_cost_desc* cd, long long B, int tube_num,
+                            const double* g, const long long* offsets, int max_nodes, const double* rad,
+                            double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide) {
+    EvalParams P;
+    memset(&P, 0, sizeof P);
+    P.env = env->d_ec;
+    P.B = B;
+    P.g = g;
+    P.offsets = offsets;
+    P.tube_num = tube_num;
+    for (int n = 0; n < tube_num; ++n) P.rad[n] = rad[n];
+    P.obstacle_min = obstacle_min;
+    P.goal_dist = goal_dist;
+    P.cost = cost;
+    P.collide = collide;
+    P.cd = *cd;
+    P.counters = ctx->d_counters;
+    P.max_nodes = max_nodes;
+    return launch_eval(ctx, P, false);
+}
+
 // ------------------------------------------------------------------ best node: min finite cost, then lowest index
 __device__ __forceinline__ unsigned long long cost_key(double c) {
     unsigned long long b = (unsigned long long)__double_as_longlong(c);

@@ -53,6 +53,17 @@ struct ModelTables {
     const float* tabR32;  // rotation part of tab in fp32 (9 rows)
 };
 
+constexpr int kStaticMaxNq = 30;
+// static model constants (kernel parameter, by value); see ctrb_static.cu
+struct StModel {
+    ModelConst mc;
+    double Kr[CTRB_MAX_TUBES][3];  // rotational stiffness diag (static.py:561-585): G*2I, E*I, E*I
+    int nq;
+    int ndof[6];                   // order (1,1),(2,1),(3,1),(2,2),(3,2),(3,3)  (static.py:63)
+    int qoff[6];
+    double x0[kStaticMaxNq];       // get_init_vals (static_bases.py:142-168)
+};
+
 }  // namespace ctrb
 
 struct ctrb_ctx {
@@ -77,6 +88,8 @@ struct ctrb_model {
     double* d_tab;
     double* d_tab_inv;
     float* d_tabR32;
+    int is_static;
+    ctrb::StModel sm;
     ctrb::ModelTables tables() const { return ctrb::ModelTables{d_tab, d_tab_inv, d_tabR32}; }
 };
 

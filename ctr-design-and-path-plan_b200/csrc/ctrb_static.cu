@@ -1,0 +1,978 @@
+// ctrb_static.cu -- the static strain-based model (ctrdapp/model/static.py, static_bases.py
+// 'last_strain_base', degree 2) as one warp per configuration on sm_100a.
+//
+// Static.solve_g (static.py:71-135) = MINPACK hybrd on a 15- (2 tubes) or 30-unknown
+// (3 tubes) equilibrium + Magnus integration of the section curves.  Here:
+//
+//  * residual (static.py:228-454).  calculate_integral (:456-491) only ever samples its
+//    integrand at the two Gauss abscissae, by linear interpolation between the bracketing
+//    nodes, and every tube!=section twist is a pure x-torsion polynomial, so the relative
+//    frames gg21/gg31/gg32 are Rx(theta0 + closed-form integral) and sg = closed-form
+//    integral of the basis (2-point Gauss per step is exact for these cubics).  The residual
+//    therefore needs 4 node evaluations per section instead of a march over every node, and
+//    all wrenches reduce to 3-vector moments (the force rows cancel exactly: v = e_x).
+//  * root finder: MINPACK hybrd itself (forward-difference Jacobian, QR, dogleg, Broyden
+//    rank-1 updates, SciPy's defaults), so that iterates, evaluation counts and the
+//    converged flag follow the reference's.  Work arrays live in shared memory; lanes own
+//    Jacobian columns (fdjac1: one perturbed residual per lane), matrix columns (qrfac, qform)
+//    and matrix rows (r1mpyq); the O(n^2) scalar recurrences (dogleg, r1updt) run on lane 0.
+//  * curves: integrate_g (:165-198) with its absolute-index quirk, as a warp-parallel
+//    inclusive scan of the per-node Magnus exponentials (SE(3) product is associative).
+#include <float.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "ctrb_se3.cuh"
+
+namespace ctrb {
+
+constexpr int kSWarps = 4;    // warps (= configurations) per block
+constexpr int kNP = 32;       // padded unknown count / leading dimension
+constexpr int kMaxNq = kStaticMaxNq;
+
+struct StCfg {
+    int i11, i21, i31, i22, i32, i33;
+    int L[3];  // nodes of sections 1..3
+    double th[3];
+    // calculate_integral's two abscissae per section: bracketing nodes and interpolation terms
+    int lo[3][2], hi[3][2];
+    double dxs[3][2], dxn[3][2], len[3];
+};
+
+// ------------------------------------------------------------------ small helpers
+struct V3 {
+    double x, y, z;
+};
+__device__ __forceinline__ V3 rotx(double s, double c, V3 v) { return {v.x, c * v.y - s * v.z, s * v.y + c * v.z}; }
+__device__ __forceinline__ V3 rotxT(double s, double c, V3 v) { return {v.x, c * v.y + s * v.z, -s * v.y + c * v.z}; }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double poly3(const double* q, double x) { return q[0] + q[1] * x + q[2] * (x * x); }
+// closed-form integral of q . (1, x, x^2) from 0 to X
+__device__ __forceinline__ double ipoly3(const double* q, double X) {
+    return q[0] * X + q[1] * (0.5 * X * X) + q[2] * (X * X * X * (1.0 / 3.0));
+}
+
+// rows 0..2 of a strain base as a 3 x dof matrix (strain_bases.py:7-224)
+__device__ void strain_base_rows(int kind, int dof, double x, double B[3][CTRB_MAX_DOF]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < CTRB_MAX_DOF; ++k) B[r][k] = 0.0;
+    switch (kind) {
+        case CTRB_BASE_CONSTANT: B[1][0] = 1.0; break;
+        case CTRB_BASE_LINEAR:
+            B[1][0] = 1.0;
+            if (dof > 2) B[1][1] = x;
+            B[2][dof - 1] = x;
+            break;
+        case CTRB_BASE_QUADRATIC:
+            B[1][0] = 1.0;
+            if (dof > 2) B[1][1] = x * x;
+            B[2][dof - 1] = x * x;
+            break;
+        case CTRB_BASE_PURE_HELIX: B[1][0] = sin(x / 10); B[2][1] = cos(x / 10); break;
+        case CTRB_BASE_LINEAR_HELIX: B[1][0] = sin(x / 10); B[2][1] = x * cos(x / 10); break;
+        case CTRB_BASE_TORSION_HELIX: B[0][0] = 1.0; B[1][1] = 1.0; B[2][2] = 1.0; break;
+        case CTRB_BASE_TORSION_LINEAR_HELIX: B[0][0] = 1.0; B[1][1] = 1.0; B[2][2] = x; break;
+        case CTRB_BASE_FULL: {
+            int bs = (dof & 1) ? 1 : 2;
+            B[0][0] = 1.0;
+            if (!(dof & 1)) B[0][1] = x;
+            B[1][bs] = 1.0;
+            B[1][bs + 1] = x;
+            if (dof <= 6) {
+                B[2][bs + 2] = 1.0;
+                B[2][bs + 3] = x;
+            } else {
+                B[1][bs + 2] = x * x;
+                B[2][bs + 3] = 1.0;
+                B[2][bs + 4] = x;
+                B[2][bs + 5] = x * x;
+            }
+            break;
+        }
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------ per-configuration setup
+// static.py:81-95 section indices; :456-491 quadrature brackets
+__device__ void st_setup(const StModel& sm, const int* idx, const double* theta, StCfg& c) {
+    const int T = sm.mc.T;
+    const int* N = sm.mc.npts;
+    int i11 = idx[0], i22 = idx[T - 2], i33 = idx[T - 1];
+    int i21 = i22 - (N[0] - i11 - 1);
+    int i32 = i33 - (N[T - 2] - i22 - 1);
+    int i31 = i32 - (N[0] - i11 - 1);
+    if (T == 2) i11 = i21 = i31 = 0;
+    c.i11 = i11; c.i21 = i21; c.i31 = i31; c.i22 = i22; c.i32 = i32; c.i33 = i33;
+    c.L[0] = T == 3 ? N[0] - i11 : 1;
+    c.L[1] = N[T - 2] - i22;
+    c.L[2] = N[T - 1] - i33;
+    for (int n = 0; n < 3; ++n) c.th[n] = n < T ? theta[n] : 0.0;
+    const double cs[2] = {(1.0 / sqrt(3.0) + 1.0) / 2.0, (-1.0 / sqrt(3.0) + 1.0) / 2.0};  // static.py:601-603
+    for (int s = 0; s < 3; ++s) {
+        const int np = c.L[s];
+        const double length = (np - 1) * sm.mc.dx;
+        c.len[s] = length;
+        for (int a = 0; a < 2; ++a) {
+            c.lo[s][a] = c.hi[s][a] = 0;
+            c.dxs[s][a] = 1.0;
+            c.dxn[s][a] = 0.0;
+            if (!(length > 0.0)) continue;
+            const double step = length / (np - 1);  // np.linspace(0, length, num_points)
+            const double xn = cs[a] * length;
+            // searchsorted(x_vals, xn, side='left') clipped to [1, np-1]
+            int hi = (int)ceil(xn / step);
+            if (hi < 0) hi = 0;
+            if (hi > np - 1) hi = np - 1;
+            while (hi < np - 1 && ((hi == np - 1) ? length : hi * step) < xn) ++hi;
+            while (hi > 0 && (((hi - 1) == np - 1) ? length : (hi - 1) * step) >= xn) --hi;
+            if (hi < 1) hi = 1;
+            const int lo = hi - 1;
+            const double xlo = lo * step, xhi = (hi == np - 1) ? length : hi * step;
+            c.lo[s][a] = lo;
+            c.hi[s][a] = hi;
+            c.dxs[s][a] = xhi - xlo;
+            c.dxn[s][a] = xn - xlo;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ integrands at one node
+// section 1 (static.py:261-345), three tubes; y = [intc1 (9), intg21 (3), intg31 (3)]
+__device__ void node_sec1(const StModel& sm, const StCfg& c, const double* q, int i, double y[15]) {
+    const double dx = sm.mc.dx, X = i * dx;
+    const double* q11 = q + sm.qoff[0];
+    const double* q21 = q + sm.qoff[1];
+    const double* q31 = q + sm.qoff[2];
+    V3 w1 = {poly3(q11, X), poly3(q11 + 3, X), poly3(q11 + 6, X)};
+    const double tg21 = poly3(q21, X), tg31 = poly3(q31, X);
+    double s21, c21, s31, c31;
+    sincos(c.th[1] + ipoly3(q21, X), &s21, &c21);  // gg21 = Rx(theta1 + int tau21)
+    sincos(c.th[2] + ipoly3(q31, X), &s31, &c31);
+    V3 w21 = rotxT(s21, c21, w1);
+    w21.x += tg21;
+    V3 w31 = rotxT(s31, c31, w21);
+    w31.x += tg31;
+    double ws[3];
+    strain_omega(sm.mc, 0, (i + c.i11) * dx, ws);
+    V3 m11 = {sm.Kr[0][0] * (w1.x - ws[0]), sm.Kr[0][1] * (w1.y - ws[1]), sm.Kr[0][2] * (w1.z - ws[2])};
+    strain_omega(sm.mc, 1, (i + c.i21) * dx, ws);
+    V3 m21 = {sm.Kr[1][0] * (w21.x - ws[0]), sm.Kr[1][1] * (w21.y - ws[1]), sm.Kr[1][2] * (w21.z - ws[2])};
+    strain_omega(sm.mc, 2, (i + c.i31) * dx, ws);
+    V3 m31 = {sm.Kr[2][0] * (w31.x - ws[0]), sm.Kr[2][1] * (w31.y - ws[1]), sm.Kr[2][2] * (w31.z - ws[2])};
+    V3 r31m = rotx(s31, c31, m31);                 // coAd(gg31) fi_31 (moment part)
+    V3 u = {m21.x + r31m.x, m21.y + r31m.y, m21.z + r31m.z};
+    V3 ru = rotx(s21, c21, u);                      // coAd21 (fi_21 + coAd31 fi_31)
+    V3 wsum = {m11.x + ru.x, m11.y + ru.y, m11.z + ru.z};
+    V3 z21 = cross3(w1, ru);                        // coad(ksi_1) (...)
+    V3 z31 = cross3(w1, rotx(s21, c21, r31m));
+    const double P[3] = {1.0, X, X * X};
+    const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};  // sg (row 0) = int of the basis
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        y[k] = P[k] * wsum.x;
+        y[3 + k] = P[k] * wsum.y;
+        y[6 + k] = P[k] * wsum.z;
+        y[9 + k] = P[k] * (m21.x + m31.x) - S[k] * z21.x;
+        y[12 + k] = P[k] * m31.x - S[k] * z31.x;
+    }
+}
+
+// section 2 (static.py:347-436); y = [intc2 (9), intg32 (3), intg312 (3)]
+__device__ void node_sec2(const StModel& sm, const StCfg& c, const double* q, int i, double s31e, double c31e,
+                          const double S31e[3], double y[15]) {
+    const int T = sm.mc.T;
+    const double dx = sm.mc.dx, X = i * dx;
+    const double* q22 = q + sm.qoff[3];
+    const double* q32 = q + sm.qoff[4];
+    V3 w2 = {poly3(q22, X), poly3(q22 + 3, X), poly3(q22 + 6, X)};
+    const double t32 = poly3(q32, X);
+    double s32, c32;
+    sincos((T == 2 ? c.th[1] : 0.0) + ipoly3(q32, X), &s32, &c32);
+    V3 w32 = rotxT(s32, c32, rotxT(s31e, c31e, w2));
+    w32.x += t32;
+    double ws[3];
+    strain_omega(sm.mc, T - 2, (i + c.i22) * dx, ws);
+    V3 m22 = {sm.Kr[T - 2][0] * (w2.x - ws[0]), sm.Kr[T - 2][1] * (w2.y - ws[1]), sm.Kr[T - 2][2] * (w2.z - ws[2])};
+    strain_omega(sm.mc, T - 1, (i + c.i32) * dx, ws);
+    V3 m32 = {sm.Kr[T - 1][0] * (w32.x - ws[0]), sm.Kr[T - 1][1] * (w32.y - ws[1]), sm.Kr[T - 1][2] * (w32.z - ws[2])};
+    V3 a = rotx(s31e, c31e, rotx(s32, c32, m32));   // coAd31 coAd32 fi_32
+    V3 wsum = {m22.x + a.x, m22.y + a.y, m22.z + a.z};
+    V3 z = cross3(w2, a);
+    const double P[3] = {1.0, X, X * X};
+    const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        y[k] = P[k] * wsum.x;
+        y[3 + k] = P[k] * wsum.y;
+        y[6 + k] = P[k] * wsum.z;
+        y[9 + k] = P[k] * m32.x - S[k] * z.x;
+        y[12 + k] = S31e[k] * z.x;
+    }
+}
+
+// section 3 (static.py:438-452); y = intc3 (dof of the last tube)
+__device__ void node_sec3(const StModel& sm, const StCfg& c, const double* q, int i, double y[CTRB_MAX_DOF]) {
+    const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
+    const double* q33 = q + sm.qoff[5];
+    double B[3][CTRB_MAX_DOF];
+    strain_base_rows(sm.mc.kind[T - 1], dof, (i + c.i33) * sm.mc.dx, B);
+    double m[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < dof; ++k) {
+            a += B[r][k] * q33[k];
+            b += B[r][k] * sm.mc.q[T - 1][k];
+        }
+        m[r] = sm.Kr[T - 1][r] * (a - b);
+    }
+    for (int k = 0; k < dof; ++k) y[k] = B[0][k] * m[0] + B[1][k] * m[1] + B[2][k] * m[2];
+}
+
+// static_equilibrium (static.py:228-259): F(q), n = sm.nq
+__device__ void st_residual(const StModel& sm, const StCfg& c, const double* q, double* F) {
+    const int T = sm.mc.T;
+    double s31e = 0.0, c31e = 1.0, S31e[3] = {0.0, 0.0, 0.0};
+    double F31[3] = {0.0, 0.0, 0.0};
+    if (T == 3) {
+        double acc[15];
+#pragma unroll
+        for (int k = 0; k < 15; ++k) acc[k] = 0.0;
+        if (c.len[0] > 0.0) {
+            for (int a = 0; a < 2; ++a) {
+                double ylo[15], yhi[15];
+                node_sec1(sm, c, q, c.lo[0][a], ylo);
+                node_sec1(sm, c, q, c.hi[0][a], yhi);
+#pragma unroll
+                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * (((yhi[k] - ylo[k]) / c.dxs[0][a]) * c.dxn[0][a] + ylo[k]);
+            }
+        }
+        const double h = c.len[0] / 2;
+        for (int k = 0; k < 9; ++k) F[sm.qoff[0] + k] = h * acc[k];
+        for (int k = 0; k < 3; ++k) F[sm.qoff[1] + k] = h * acc[9 + k];
+        for (int k = 0; k < 3; ++k) F31[k] = h * acc[12 + k];
+        // final relative frame / basis integral of tube 3 over section 1 (equilibrium_three's return)
+        const double Xe = (c.L[0] - 1) * sm.mc.dx;
+        sincos(c.th[2] + ipoly3(q + sm.qoff[2], Xe), &s31e, &c31e);
+        S31e[0] = Xe;
+        S31e[1] = 0.5 * Xe * Xe;
+        S31e[2] = Xe * Xe * Xe * (1.0 / 3.0);
+    }
+    {
+        double acc[15];
+#pragma unroll
+        for (int k = 0; k < 15; ++k) acc[k] = 0.0;
+        if (c.len[1] > 0.0) {
+            for (int a = 0; a < 2; ++a) {
+                double ylo[15], yhi[15];
+                node_sec2(sm, c, q, c.lo[1][a], s31e, c31e, S31e, ylo);
+                node_sec2(sm, c, q, c.hi[1][a], s31e, c31e, S31e, yhi);
+#pragma unroll
+                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * (((yhi[k] - ylo[k]) / c.dxs[1][a]) * c.dxn[1][a] + ylo[k]);
+            }
+        }
+        const double h = c.len[1] / 2;
+        for (int k = 0; k < 9; ++k) F[sm.qoff[3] + k] = h * acc[k];
+        for (int k = 0; k < 3; ++k) F[sm.qoff[4] + k] = h * acc[9 + k];
+        if (T == 3)
+            for (int k = 0; k < 3; ++k) F[sm.qoff[2] + k] = F31[k] - h * acc[12 + k];  // intg_31 - intg_312
+    }
+    {
+        const int dof = sm.ndof[5];
+        double acc[CTRB_MAX_DOF];
+        for (int k = 0; k < CTRB_MAX_DOF; ++k) acc[k] = 0.0;
+        if (c.len[2] > 0.0) {
+            for (int a = 0; a < 2; ++a) {
+                double ylo[CTRB_MAX_DOF], yhi[CTRB_MAX_DOF];
+                node_sec3(sm, c, q, c.lo[2][a], ylo);
+                node_sec3(sm, c, q, c.hi[2][a], yhi);
+                for (int k = 0; k < dof; ++k) acc[k] += 0.5 * (((yhi[k] - ylo[k]) / c.dxs[2][a]) * c.dxn[2][a] + ylo[k]);
+            }
+        }
+        const double h = c.len[2] / 2;
+        for (int k = 0; k < dof; ++k) F[sm.qoff[5] + k] = h * acc[k];
+    }
+}
+
+// ------------------------------------------------------------------ MINPACK hybrd, warp-cooperative
+// All arrays are shared memory of this warp.  Matrices are column-major with leading dimension kNP.
+struct HybrdMem {
+    double fjac[kNP * kNP];
+    double r[kNP * (kNP + 1) / 2];
+    double x[kNP], fvec[kNP], qtf[kNP], diag[kNP], wa1[kNP], wa2[kNP], wa3[kNP], wa4[kNP];
+    double scal[8];  // lane 0 -> warp broadcast slots
+    int iscal[4];
+};
+
+__device__ double st_enorm(int n, const double* x) {
+    // MINPACK enorm: scaled accumulation (the intermediate range is the only one reached here, but
+    // keep the three accumulators so that over/underflow behaves as in the reference)
+    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+    double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
+    const double agiant = rgiant / (double)n;
+    for (int i = 0; i < n; ++i) {
+        const double xabs = fabs(x[i]);
+        if (xabs > rdwarf && xabs < agiant) {
+            s2 += xabs * xabs;
+        } else if (xabs <= rdwarf) {
+            if (xabs > x3max) {
+                const double rr = x3max / xabs;
+                s3 = 1 + s3 * rr * rr;
+                x3max = xabs;
+            } else if (xabs != 0) {
+                const double rr = xabs / x3max;
+                s3 += rr * rr;
+            }
+        } else {
+            if (xabs > x1max) {
+                const double rr = x1max / xabs;
+                s1 = 1 + s1 * rr * rr;
+                x1max = xabs;
+            } else {
+                const double rr = xabs / x1max;
+                s1 += rr * rr;
+            }
+        }
+    }
+    if (s1 != 0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0) {
+        if (s2 >= x3max) return sqrt(s2 * (1 + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    }
+    return x3max * sqrt(s3);
+}
+
+__device__ void st_dogleg(int n, const double* r, const double* diag, const double* qtb, double delta, double* x,
+                          double* wa1, double* wa2) {
+    const double epsmch = DBL_EPSILON;
+    int jj = (n * (n + 1)) / 2;
+    for (int k = 1; k <= n; ++k) {
+        const int j = n - k;
+        jj -= k;
+        int l = jj + 1;
+        double sum = 0;
+        for (int i = j + 1; i < n; ++i) {
+            sum += r[l] * x[i];
+            ++l;
+        }
+        double temp = r[jj];
+        if (temp == 0) {
+            l = j;
+            for (int i = 0; i <= j; ++i) {
+                temp = fmax(temp, fabs(r[l]));
+                l = l + n - i - 1;
+            }
+            temp = epsmch * temp;
+            if (temp == 0) temp = epsmch;
+        }
+        x[j] = (qtb[j] - sum) / temp;
+    }
+    for (int j = 0; j < n; ++j) {
+        wa1[j] = 0;
+        wa2[j] = diag[j] * x[j];
+    }
+    const double qnorm = st_enorm(n, wa2);
+    if (qnorm <= delta) return;
+    int l = 0;
+    for (int j = 0; j < n; ++j) {
+        const double temp = qtb[j];
+        for (int i = j; i < n; ++i) {
+            wa1[i] += r[l] * temp;
+            ++l;
+        }
+        wa1[j] = wa1[j] / diag[j];
+    }
+    const double gnorm = st_enorm(n, wa1);
+    double sgnorm = 0, alpha = delta / qnorm;
+    if (gnorm != 0) {
+        for (int j = 0; j < n; ++j) wa1[j] = (wa1[j] / gnorm) / diag[j];
+        l = 0;
+        for (int j = 0; j < n; ++j) {
+            double sum = 0;
+            for (int i = j; i < n; ++i) {
+                sum += r[l] * wa1[i];
+                ++l;
+            }
+            wa2[j] = sum;
+        }
+        double temp = st_enorm(n, wa2);
+        sgnorm = (gnorm / temp) / temp;
+        alpha = 0;
+        if (sgnorm < delta) {
+            const double bnorm = st_enorm(n, qtb);
+            temp = (bnorm / gnorm) * (bnorm / qnorm) * (sgnorm / delta);
+            const double dq = delta / qnorm, sd = sgnorm / delta;
+            temp = temp - dq * sd * sd + sqrt((temp - dq) * (temp - dq) + (1 - dq * dq) * (1 - sd * sd));
+            alpha = (dq * (1 - sd * sd)) / temp;
+        }
+    }
+    const double temp = (1 - alpha) * fmin(sgnorm, delta);
+    for (int j = 0; j < n; ++j) x[j] = temp * wa1[j] + alpha * x[j];
+}
+
+__device__ void st_r1updt(int n, double* s, const double* u, double* v, double* w, int* sing) {
+    const double giant = DBL_MAX;
+    const int m = n;
+    int jj = (n * (2 * m - n + 1)) / 2 - (m - n) - 1;
+    w[n - 1] = s[jj];
+    for (int j = n - 2; j >= 0; --j) {
+        jj -= (m - j);
+        w[j] = 0;
+        if (v[j] != 0) {
+            double c_, s_, tau;
+            if (fabs(v[n - 1]) < fabs(v[j])) {
+                const double cotan = v[n - 1] / v[j];
+                s_ = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
+                c_ = s_ * cotan;
+                tau = 1;
+                if (fabs(c_) * giant > 1) tau = 1 / c_;
+            } else {
+                const double tn = v[j] / v[n - 1];
+                c_ = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
+                s_ = c_ * tn;
+                tau = s_;
+            }
+            v[n - 1] = s_ * v[j] + c_ * v[n - 1];
+            v[j] = tau;
+            int l = jj;
+            for (int i = j; i < m; ++i) {
+                const double temp = c_ * s[l] - s_ * w[i];
+                w[i] = s_ * s[l] + c_ * w[i];
+                s[l] = temp;
+                ++l;
+            }
+        }
+    }
+    for (int i = 0; i < m; ++i) w[i] += v[n - 1] * u[i];
+    *sing = 0;
+    for (int j = 0; j < n - 1; ++j) {
+        if (w[j] != 0) {
+            double c_, s_, tau;
+            if (fabs(s[jj]) < fabs(w[j])) {
+                const double cotan = s[jj] / w[j];
+                s_ = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
+                c_ = s_ * cotan;
+                tau = 1;
+                if (fabs(c_) * giant > 1) tau = 1 / c_;
+            } else {
+                const double tn = w[j] / s[jj];
+                c_ = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
+                s_ = c_ * tn;
+                tau = s_;
+            }
+            int l = jj;
+            for (int i = j; i < m; ++i) {
+                const double temp = c_ * s[l] + s_ * w[i];
+                w[i] = -s_ * s[l] + c_ * w[i];
+                s[l] = temp;
+                ++l;
+            }
+            w[j] = tau;
+        }
+        if (s[jj] == 0) *sing = 1;
+        jj += (m - j);
+    }
+    s[jj] = w[n - 1];
+    if (s[jj] == 0) *sing = 1;
+}
+
+// apply the 2(n-1) Givens rotations stored in v, w to ONE row a[0..n-1] with stride lda (r1mpyq)
+__device__ void st_r1mpyq_row(int n, double* a, int lda, const double* v, const double* w) {
+    for (int j = n - 2; j >= 0; --j) {
+        double c_, s_;
+        if (fabs(v[j]) > 1) {
+            c_ = 1 / v[j];
+            s_ = sqrt(1 - c_ * c_);
+        } else {
+            s_ = v[j];
+            c_ = sqrt(1 - s_ * s_);
+        }
+        const double temp = c_ * a[j * lda] - s_ * a[(n - 1) * lda];
+        a[(n - 1) * lda] = s_ * a[j * lda] + c_ * a[(n - 1) * lda];
+        a[j * lda] = temp;
+    }
+    for (int j = 0; j < n - 1; ++j) {
+        double c_, s_;
+        if (fabs(w[j]) > 1) {
+            c_ = 1 / w[j];
+            s_ = sqrt(1 - c_ * c_);
+        } else {
+            s_ = w[j];
+            c_ = sqrt(1 - s_ * s_);
+        }
+        const double temp = c_ * a[j * lda] + s_ * a[(n - 1) * lda];
+        a[(n - 1) * lda] = -s_ * a[j * lda] + c_ * a[(n - 1) * lda];
+        a[j * lda] = temp;
+    }
+}
+
+// returns info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress); *nfev_out = evaluations
+__device__ int st_hybrd(const StModel& sm, const StCfg& c, HybrdMem& M, int lane, double xtol, int maxfev, double factor,
+                        int* nfev_out) {
+    const int n = sm.nq;
+    const double epsmch = DBL_EPSILON, p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
+    double* fjac = M.fjac;
+    int info = 0, nfev;
+    if (lane == 0) {
+        st_residual(sm, c, M.x, M.fvec);
+        M.scal[0] = st_enorm(n, M.fvec);
+    }
+    __syncwarp();
+    nfev = 1;
+    double fnorm = M.scal[0];
+    int iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
+    double delta = 0, xnorm = 0;
+    for (;;) {  // outer loop: fresh forward-difference Jacobian
+        bool jeval = true;
+        // fdjac1 (dense): lane j evaluates the residual at x + h e_j and fills column j
+        if (lane < n) {
+            double xp[kMaxNq], Fp[kMaxNq];
+            for (int k = 0; k < n; ++k) xp[k] = M.x[k];
+            const double eps = sqrt(epsmch);
+            const double temp = xp[lane];
+            double h = eps * fabs(temp);
+            if (h == 0) h = eps;
+            xp[lane] = temp + h;
+            st_residual(sm, c, xp, Fp);
+            for (int i = 0; i < n; ++i) fjac[i + lane * kNP] = (Fp[i] - M.fvec[i]) / h;
+        }
+        nfev += n;
+        __syncwarp();
+        // qrfac: Householder QR without pivoting; lane k owns column k
+        if (lane < n) {
+            const double an = st_enorm(n, fjac + lane * kNP);
+            M.wa2[lane] = an;  // acnorm
+            M.wa1[lane] = an;  // rdiag (overwritten below)
+        }
+        __syncwarp();
+        for (int j = 0; j < n; ++j) {
+            double ajnorm = st_enorm(n - j, fjac + j + j * kNP);  // every lane computes the same value
+            if (ajnorm != 0) {
+                if (fjac[j + j * kNP] < 0) ajnorm = -ajnorm;
+                __syncwarp();
+                if (lane >= j && lane < n) fjac[lane + j * kNP] /= ajnorm;  // lane = row here
+                __syncwarp();
+                if (lane == 0) fjac[j + j * kNP] += 1;
+                __syncwarp();
+                if (lane > j && lane < n) {  // lane = column k
+                    double sum = 0;
+                    for (int i = j; i < n; ++i) sum += fjac[i + j * kNP] * fjac[i + lane * kNP];
+                    const double temp = sum / fjac[j + j * kNP];
+                    for (int i = j; i < n; ++i) fjac[i + lane * kNP] -= temp * fjac[i + j * kNP];
+                }
+            }
+            if (lane == 0) M.wa1[j] = -ajnorm;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (iter == 1) {
+                for (int j = 0; j < n; ++j) {
+                    M.diag[j] = M.wa2[j];
+                    if (M.wa2[j] == 0) M.diag[j] = 1;
+                }
+                for (int j = 0; j < n; ++j) M.wa3[j] = M.diag[j] * M.x[j];
+                xnorm = st_enorm(n, M.wa3);
+                delta = factor * xnorm;
+                if (delta == 0) delta = factor;
+            }
+            for (int i = 0; i < n; ++i) M.qtf[i] = M.fvec[i];
+            for (int j = 0; j < n; ++j) {
+                if (fjac[j + j * kNP] != 0) {
+                    double sum = 0;
+                    for (int i = j; i < n; ++i) sum += fjac[i + j * kNP] * M.qtf[i];
+                    const double temp = -sum / fjac[j + j * kNP];
+                    for (int i = j; i < n; ++i) M.qtf[i] += fjac[i + j * kNP] * temp;
+                }
+            }
+            for (int j = 0; j < n; ++j) {
+                int l = j;
+                for (int i = 0; i < j; ++i) {
+                    M.r[l] = fjac[i + j * kNP];
+                    l = l + n - i - 1;
+                }
+                M.r[l] = M.wa1[j];
+            }
+            M.scal[1] = xnorm;
+            M.scal[2] = delta;
+        }
+        __syncwarp();
+        xnorm = M.scal[1];
+        delta = M.scal[2];
+        // qform: accumulate Q in fjac; lane = column j of the trailing update
+        for (int j = 1; j < n; ++j)
+            if (lane < j) fjac[lane + j * kNP] = 0;
+        __syncwarp();
+        for (int l = 0; l < n; ++l) {
+            const int k = n - l - 1;
+            if (lane >= k && lane < n) M.wa3[lane] = fjac[lane + k * kNP];  // wa(i) = q(i,k)
+            __syncwarp();
+            if (lane >= k && lane < n) fjac[lane + k * kNP] = (lane == k) ? 1.0 : 0.0;
+            __syncwarp();
+            if (M.wa3[k] != 0) {
+                if (lane >= k && lane < n) {  // lane = column j
+                    double sum = 0;
+                    for (int i = k; i < n; ++i) sum += fjac[i + lane * kNP] * M.wa3[i];
+                    const double temp = sum / M.wa3[k];
+                    for (int i = k; i < n; ++i) fjac[i + lane * kNP] -= temp * M.wa3[i];
+                }
+            }
+            __syncwarp();
+        }
+        if (lane < n) M.diag[lane] = fmax(M.diag[lane], M.wa2[lane]);
+        __syncwarp();
+        for (;;) {  // inner loop
+            double pnorm = 0, fnorm1 = 0, actred, prered, ratio;
+            if (lane == 0) {
+                st_dogleg(n, M.r, M.diag, M.qtf, delta, M.wa1, M.wa2, M.wa3);
+                for (int j = 0; j < n; ++j) {
+                    M.wa1[j] = -M.wa1[j];
+                    M.wa2[j] = M.x[j] + M.wa1[j];
+                    M.wa3[j] = M.diag[j] * M.wa1[j];
+                }
+                pnorm = st_enorm(n, M.wa3);
+                if (iter == 1) delta = fmin(delta, pnorm);
+                st_residual(sm, c, M.wa2, M.wa4);
+                fnorm1 = st_enorm(n, M.wa4);
+                actred = -1;
+                if (fnorm1 < fnorm) actred = 1 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+                int l = 0;
+                for (int i = 0; i < n; ++i) {
+                    double sum = 0;
+                    for (int j = i; j < n; ++j) {
+                        sum += M.r[l] * M.wa1[j];
+                        ++l;
+                    }
+                    M.wa3[i] = M.qtf[i] + sum;
+                }
+                const double temp = st_enorm(n, M.wa3);
+                prered = 0;
+                if (temp < fnorm) prered = 1 - (temp / fnorm) * (temp / fnorm);
+                ratio = 0;
+                if (prered > 0) ratio = actred / prered;
+                if (ratio < p1) {
+                    ncsuc = 0;
+                    ncfail++;
+                    delta = p5 * delta;
+                } else {
+                    ncfail = 0;
+                    ncsuc++;
+                    if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
+                    if (fabs(ratio - 1) <= p1) delta = pnorm / p5;
+                }
+                if (ratio >= p0001) {
+                    for (int j = 0; j < n; ++j) {
+                        M.x[j] = M.wa2[j];
+                        M.wa2[j] = M.diag[j] * M.x[j];
+                        M.fvec[j] = M.wa4[j];
+                    }
+                    xnorm = st_enorm(n, M.wa2);
+                    fnorm = fnorm1;
+                    iter++;
+                }
+                nslow1++;
+                if (actred >= p001) nslow1 = 0;
+                if (jeval) nslow2++;
+                if (actred >= p1) nslow2 = 0;
+                int inf = 0;
+                if (delta <= xtol * xnorm || fnorm == 0) inf = 1;
+                if (inf == 0) {
+                    if (nfev + 1 >= maxfev) inf = 2;
+                    if (p1 * fmax(p1 * delta, pnorm) <= epsmch * xnorm) inf = 3;
+                    if (nslow2 == 5) inf = 4;
+                    if (nslow1 == 10) inf = 5;
+                }
+                M.scal[0] = fnorm;
+                M.scal[1] = xnorm;
+                M.scal[2] = delta;
+                M.scal[3] = pnorm;
+                M.scal[4] = ratio;
+                M.iscal[0] = inf;
+                M.iscal[1] = ncfail;
+                M.iscal[2] = iter;
+            }
+            __syncwarp();
+            nfev++;
+            fnorm = M.scal[0];
+            xnorm = M.scal[1];
+            delta = M.scal[2];
+            pnorm = M.scal[3];
+            ratio = M.scal[4];
+            info = M.iscal[0];
+            ncfail = M.iscal[1];
+            iter = M.iscal[2];
+            if (info != 0) {
+                *nfev_out = nfev;
+                return info;
+            }
+            if (ncfail == 2) break;  // recompute the Jacobian
+            // rank-one (Broyden) update: lane j forms its entries, lane 0 runs r1updt, lanes apply the
+            // rotations to their row of Q and lane 0 to qtf
+            if (lane < n) {
+                double sum = 0;
+                for (int i = 0; i < n; ++i) sum += fjac[i + lane * kNP] * M.wa4[i];
+                const double w2 = (sum - M.wa3[lane]) / pnorm;
+                const double w1 = M.diag[lane] * ((M.diag[lane] * M.wa1[lane]) / pnorm);
+                M.wa2[lane] = w2;
+                M.wa1[lane] = w1;
+                if (ratio >= p0001) M.qtf[lane] = sum;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                int sing;
+                st_r1updt(n, M.r, M.wa1, M.wa2, M.wa3, &sing);
+            }
+            __syncwarp();
+            if (lane < n) st_r1mpyq_row(n, fjac + lane, kNP, M.wa2, M.wa3);
+            if (lane == 31) st_r1mpyq_row(n, M.qtf, 1, M.wa2, M.wa3);
+            __syncwarp();
+            jeval = false;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ curve integration (integrate_g)
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+// half_step_integral for a tube==section basis (with bias): the Magnus exponential of one step.
+// wA, wB = omega at the two Gauss points; v = e_x at both.
+__device__ __forceinline__ SE3 magnus_step(const double wA[3], const double wB[3], double dx) {
+    const double cf = (sqrt(3.0) * dx * dx) / 12;
+    // Gamma = dx/2 (xi1^ + xi2^) + cf [xi2^, xi1^];  [.,.] = (w2 x w1, w2 x v1 - w1 x v2), v1 = v2 = e_x
+    V3 a = {wA[0], wA[1], wA[2]}, b = {wB[0], wB[1], wB[2]};
+    V3 cw = cross3(b, a);
+    V3 d = {b.x - a.x, b.y - a.y, b.z - a.z};
+    V3 cv = cross3(d, V3{1.0, 0.0, 0.0});
+    double w[3] = {(dx / 2) * (a.x + b.x) + cf * cw.x, (dx / 2) * (a.y + b.y) + cf * cw.y, (dx / 2) * (a.z + b.z) + cf * cw.z};
+    double v[3] = {(dx / 2) * 2.0 + cf * cv.x, cf * cv.y, cf * cv.z};
+    return se3_exp(w, v, 1.0);
+}
+
+// omega of the (tube==section) basis at absolute section coordinate `sidx` (static_bases.py:61-81)
+__device__ __forceinline__ void sect_omega(const StModel& sm, const StCfg& c, const double* qs, int sect, double sidx,
+                                           double w[3]) {
+    const double dx = sm.mc.dx;
+    if (sect == 3) {
+        const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
+        double B[3][CTRB_MAX_DOF];
+        strain_base_rows(sm.mc.kind[T - 1], dof, (sidx + c.i33) * dx, B);  // _easy_last_basis adds idx33 (again)
+        for (int r = 0; r < 3; ++r) {
+            double a = 0.0;
+            for (int k = 0; k < dof; ++k) a += B[r][k] * qs[k];
+            w[r] = a;
+        }
+    } else {
+        const double x = sidx * dx;
+        w[0] = poly3(qs, x);
+        w[1] = poly3(qs + 3, x);
+        w[2] = poly3(qs + 6, x);
+    }
+}
+
+// Writes `count` nodes of one section curve: node 0 = g0, node k = g0 * E_1 ... E_k with
+// E_k the Magnus step at absolute index start + k.  Returns the last node (all lanes).
+__device__ SE3 integrate_section(const StModel& sm, const StCfg& c, const double* qs, int sect, int start, int count,
+                                 SE3 g0, double* out, int lane) {
+    const double dx = sm.mc.dx;
+    const double cg1 = 0.5 - sqrt(3.0) / 6, cg2 = 0.5 + sqrt(3.0) / 6;  // static.py:597-599
+    if (lane == 0 && out) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            out[r * 4 + 0] = g0.r[r * 3 + 0];
+            out[r * 4 + 1] = g0.r[r * 3 + 1];
+            out[r * 4 + 2] = g0.r[r * 3 + 2];
+            out[r * 4 + 3] = g0.p[r];
+        }
+        out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;
+    }
+    SE3 carry = g0;
+    for (int base = 1; base < count; base += 32) {
+        const int k = base + lane;
+        SE3 e;
+        se3_identity(e);
+        if (k < count) {
+            const double si = (double)(start + k);
+            double wA[3], wB[3];
+            sect_omega(sm, c, qs, sect, si + cg1 - 1, wA);
+            sect_omega(sm, c, qs, sect, si + cg2 - 1, wB);
+            e = magnus_step(wA, wB, dx);
+        }
+        // inclusive scan of SE(3) products across lanes (Hillis-Steele)
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            SE3 o;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) o.r[t] = shfl_up_d(e.r[t], off);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) o.p[t] = shfl_up_d(e.p[t], off);
+            if (lane >= off) e = se3_mul(o, e);
+        }
+        SE3 g = se3_mul(carry, e);
+        if (k < count && out) {
+            double* dst = out + (size_t)k * 16;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                dst[r * 4 + 0] = g.r[r * 3 + 0];
+                dst[r * 4 + 1] = g.r[r * 3 + 1];
+                dst[r * 4 + 2] = g.r[r * 3 + 2];
+                dst[r * 4 + 3] = g.p[r];
+            }
+            dst[12] = 0; dst[13] = 0; dst[14] = 0; dst[15] = 1;
+        }
+        const int last = min(31, count - 1 - base);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) carry.r[t] = shfl_d(g.r[t], last);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) carry.p[t] = shfl_d(g.p[t], last);
+    }
+    return carry;
+}
+
+__device__ __forceinline__ SE3 se3_rx(double angle) {
+    SE3 g;
+    se3_identity(g);
+    double s, c;
+    sincos(angle, &s, &c);
+    g.r[4] = c; g.r[5] = -s; g.r[7] = s; g.r[8] = c;
+    return g;
+}
+
+// integral of q.(1,x,x^2) over the ABSOLUTE interval integrate_g walks (static.py:192-195)
+__device__ __forceinline__ double ipoly3_abs(const double* q, double a, double b) { return ipoly3(q, b) - ipoly3(q, a); }
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kSWarps * 32)
+    static_solve_kernel(StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
+                        const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
+                        double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
+                        int32_t* __restrict__ info_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    HybrdMem& M = reinterpret_cast<HybrdMem*>(smem_raw)[warp];
+    const int T = sm.mc.T, n = sm.nq;
+    for (long long b = (long long)blockIdx.x * kSWarps + warp; b < B; b += (long long)gridDim.x * kSWarps) {
+        StCfg c;
+        st_setup(sm, idx + b * T, theta + b * T, c);
+        if (lane < n) M.x[lane] = x0 ? x0[(x0_per_config ? b * n : 0) + lane] : sm.x0[lane];
+        __syncwarp();
+        int nfev = 0;
+        const int info = st_hybrd(sm, c, M, lane, xtol, 200 * (n + 1), 100.0, &nfev);
+        __syncwarp();
+        if (sol_out && lane < n) sol_out[b * n + lane] = M.x[lane];
+        if (lane == 0) {
+            if (nfev_out) nfev_out[b] = nfev;
+            if (info_out) info_out[b] = info;
+        }
+        if (g_out) {
+            const double* q = M.x;
+            const double dx = sm.mc.dx;
+            SE3 g11_last, g21_last, g31_last;
+            se3_identity(g11_last);
+            if (T == 3) {
+                g11_last = integrate_section(sm, c, q + sm.qoff[0], 1, c.i11, c.L[0], se3_rx(c.th[0]),
+                                             g_out + offsets[b * T + 0] * 16, lane);
+                g21_last = se3_rx(c.th[1] + ipoly3_abs(q + sm.qoff[1], c.i21 * dx, (c.i21 + c.L[0] - 1) * dx));
+                g31_last = se3_rx(c.th[2] + ipoly3_abs(q + sm.qoff[2], c.i31 * dx, (c.i31 + c.L[0] - 1) * dx));
+            } else {
+                g21_last = se3_rx(c.th[0]);  // static.py:114-118
+                g31_last = se3_rx(c.th[1]);
+            }
+            SE3 g22_last = integrate_section(sm, c, q + sm.qoff[3], 2, c.i22, c.L[1], se3_mul(g11_last, g21_last),
+                                             g_out + offsets[b * T + (T - 2)] * 16, lane);
+            SE3 g32_last = se3_rx(ipoly3_abs(q + sm.qoff[4], c.i32 * dx, (c.i32 + c.L[1] - 1) * dx));
+            integrate_section(sm, c, q + sm.qoff[5], 3, c.i33, c.L[2], se3_mul(se3_mul(g22_last, g31_last), g32_last),
+                              g_out + offsets[b * T + (T - 1)] * 16, lane);
+        }
+        __syncwarp();
+    }
+}
+
+// residual only (parity tests): one thread per (config) evaluates F(q)
+__global__ void static_residual_kernel(StModel sm, long long B, const int32_t* __restrict__ idx,
+                                       const double* __restrict__ theta, const double* __restrict__ q,
+                                       double* __restrict__ F) {
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    StCfg c;
+    st_setup(sm, idx + b * sm.mc.T, theta + b * sm.mc.T, c);
+    double ql[kMaxNq], Fl[kMaxNq];
+    for (int k = 0; k < sm.nq; ++k) ql[k] = q[b * sm.nq + k];
+    st_residual(sm, c, ql, Fl);
+    for (int k = 0; k < sm.nq; ++k) F[b * sm.nq + k] = Fl[k];
+}
+
+// ------------------------------------------------------------------ host side
+int static_model_init(const ctrb_model_desc* d, const ModelConst& mc, StModel* out) {
+    StModel sm;
+    memset(&sm, 0, sizeof sm);
+    sm.mc = mc;
+    const int T = mc.T;
+    if (T != 2 && T != 3) {
+        set_error("%d is not supported by the static model", T);  // static.py:77-78
+        return CTRB_ERR_INVALID;
+    }
+    if (d->static_degree != 2 || d->static_basis_type != 0) {
+        set_error("static model: only basis_type 'last_strain_base' with degree 2 is supported (the reference's other "
+                  "bases do not run, SURVEY App. B#2; _simple_basis hard-codes column offsets 3 and 6)");
+        return CTRB_ERR_UNSUPPORTED;
+    }
+    const double pi = 3.141592653589793;
+    for (int n = 0; n < T; ++n) {  // static.py:561-585
+        const double o = d->radius_outer[n], i = d->radius_inner[n];
+        const double polar = pi / 4 * (o * o * o * o - i * i * i * i);
+        const double mom = polar * 2;
+        sm.Kr[n][0] = 23.1e6 * mom;
+        sm.Kr[n][1] = 60e6 * polar;
+        sm.Kr[n][2] = 60e6 * polar;
+    }
+    const int da = 3;
+    int nd[6] = {T == 3 ? 3 * da : 0, T == 3 ? da : 0, T == 3 ? da : 0, 3 * da, da, mc.dof[T - 1]};
+    int o = 0;
+    for (int k = 0; k < 6; ++k) {
+        sm.ndof[k] = nd[k];
+        sm.qoff[k] = o;
+        o += nd[k];
+    }
+    sm.nq = o;
+    if (o > kMaxNq) {
+        set_error("static model: %d unknowns exceed the supported %d", o, kMaxNq);
+        return CTRB_ERR_UNSUPPORTED;
+    }
+    const int first = o - nd[5];  // static_bases.py:142-168
+    for (int k = 0; k < first; ++k) sm.x0[k] = (k % da == 0) ? 0.01 : 0.0;
+    for (int k = 0; k < nd[5]; ++k) sm.x0[first + k] = mc.q[T - 1][k];
+    *out = sm;
+    return CTRB_OK;
+}
+
+int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
+                        const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
+                        double* sol_out, int32_t* nfev_out, int32_t* info_out) {
+    if (B <= 0) return CTRB_OK;
+    const size_t smem = sizeof(HybrdMem) * kSWarps;
+    CTRB_CUDA(cudaFuncSetAttribute(static_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks_needed = (B + kSWarps - 1) / kSWarps;
+    int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * 4);
+    static_solve_kernel<<<grid, kSWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config,
+                                                                  xtol > 0 ? xtol : 1.49012e-8, offsets, g_out, sol_out,
+                                                                  nfev_out, info_out);
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
+    return CTRB_OK;
+}
+
+int launch_static_residual(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
+                           const double* q, double* F) {
+    if (B <= 0) return CTRB_OK;
+    static_residual_kernel<<<(unsigned)((B + 63) / 64), 64, 0, ctx->stream>>>(sm, B, idx, theta, q, F);
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
+    return CTRB_OK;
+}
+
+}  // namespace ctrb

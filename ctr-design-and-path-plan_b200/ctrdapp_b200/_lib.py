@@ -70,6 +70,13 @@ SYMBOLS = {
     "ctrb_g_node_offsets": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int, _vp, C.c_int]),
     "ctrb_solve_g_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "ctrb_eta_ftl_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "ctrb_static_num_unknowns": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "ctrb_static_initial_guess": (C.c_int, [_vp, _vp]),
+    "ctrb_static_residual_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_int]),
+    "ctrb_static_solve_g_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp,
+                                            C.c_int]),
+    "ctrb_static_eval_batch": (C.c_int, [_vp, _vp, _vp, C.POINTER(CostDesc), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _vp, C.c_int]),
     "ctrb_check_collision_batch": (C.c_int, [_vp, _vp, _i64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "ctrb_eval_batch": (C.c_int, [_vp, _vp, _vp, C.POINTER(CostDesc), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   C.c_int]),

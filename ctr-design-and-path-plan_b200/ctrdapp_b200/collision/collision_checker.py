@@ -104,6 +104,14 @@ class CollisionChecker:
         goal = np.empty(B)
         cost = np.empty(B)
         coll = np.empty(B, np.uint8)
+        if getattr(model, "num_unknowns", None):  # static model: solve -> collide, plus the converged flag
+            info = np.empty(B, np.int32)
+            nfev = np.empty(B, np.int32)
+            L.check(L.lib().ctrb_static_eval_batch(self.ctx.handle, model.handle, self._h, C.byref(cd), B, L.ptr(idx),
+                                                   L.ptr(theta), L.ptr(rad), L.ptr(obs), L.ptr(goal), L.ptr(cost),
+                                                   L.ptr(coll), L.ptr(info), L.ptr(nfev), L.MEM_HOST))
+            self.last_static = {"info": info, "nfev": nfev, "converged": info == 1}
+            return obs, goal, cost, coll
         L.check(L.lib().ctrb_eval_batch(self.ctx.handle, model.handle, self._h, C.byref(cd), B, L.ptr(idx),
                                         L.ptr(theta), L.ptr(rad), L.ptr(obs), L.ptr(goal), L.ptr(cost),
                                         L.ptr(coll), L.MEM_HOST))

@@ -32,21 +32,29 @@ class Kinematic(Model):
         self.q_dof = q_dof
         self.q = q
         self.ctx = ctx or L.default_context()
-        d = L.ModelDesc()
-        d.model_type = 0
-        d.tube_num = tube_num
-        for n in range(tube_num):
-            d.base_kind[n] = L.BASE_KINDS[self.strain_base[n]]
-            d.q_dof[n] = q_dof[n]
-            for k in range(q_dof[n]):
-                d.q[n][k] = float(q[n][k])
-            d.tube_length[n] = float(max_tube_length[n])
-        d.delta_x = float(delta_x)
+        d = self._make_desc()
         self._h = C.c_void_p()
         L.check(L.lib().ctrb_model_create(self.ctx.handle, C.byref(d), C.byref(self._h)))
         npts = (C.c_int32 * L.MAX_TUBES)()
         L.check(L.lib().ctrb_model_num_points(self._h, npts))
         assert list(npts[:tube_num]) == self.num_discrete_points
+        self._after_create()
+
+    def _make_desc(self):
+        d = L.ModelDesc()
+        d.model_type = 0
+        d.tube_num = self.tube_num
+        for n in range(self.tube_num):
+            d.base_kind[n] = L.BASE_KINDS[self.strain_base[n]]
+            d.q_dof[n] = self.q_dof[n]
+            for k in range(self.q_dof[n]):
+                d.q[n][k] = float(self.q[n][k])
+            d.tube_length[n] = float(self.max_tube_length[n])
+        d.delta_x = float(self.delta_x)
+        return d
+
+    def _after_create(self):
+        pass
 
     def __del__(self):
         try:

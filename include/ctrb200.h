@@ -189,6 +189,22 @@ int ctrb_eta_ftl_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int3
                        double* eta_out /*[B][T][6]*/, double* ftl_out /* nullable */, double* ftl_mag /*[B][4]*/,
                        int mem);
 
+/* ---- static model: replaces Static.solve_g (static.py:71-135): MINPACK hybrd on the 15- / 30-unknown
+ *      equilibrium + integrate_g of the section curves, per configuration.
+ *      g_out is packed like ctrb_solve_g_batch (fp64, same node_offsets: tube n has npts[n]-idx[n] nodes).
+ *      initial_guess: NULL (Static.general_init_guess), or [nq] shared (x0_per_config = 0), or [B][nq].
+ *      xtol <= 0 selects SciPy's default 1.49012e-8.  solution_q [B][nq], nfev [B] (MINPACK's count; SciPy
+ *      reports 2 more), info [B] (MINPACK info: 1 = converged -- what solution.success means) may be NULL. ---- */
+int ctrb_static_num_unknowns(const ctrb_model* m, int32_t* nq);
+int ctrb_static_initial_guess(const ctrb_model* m, double* x0 /*[nq], host*/);
+int ctrb_static_residual_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx /*[B][T]*/,
+                               const double* theta /*[B][T]*/, const double* q /*[B][nq]*/, double* F /*[B][nq]*/,
+                               int mem);
+int ctrb_static_solve_g_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx /*[B][T]*/,
+                              const double* theta /*[B][T]*/, const double* initial_guess, int x0_per_config,
+                              double xtol, const int64_t* node_offsets /*[B*T+1]*/, double* g_out /* nullable */,
+                              double* solution_q, int32_t* nfev, int32_t* info, int mem);
+
 /* ---- collision on given curves: replaces CollisionChecker.check_collision
  *      (collision_checker.py:35-70) for B curves.  g is packed fp64 4x4 nodes with
  *      node_offsets as above; rad[T] are the tube radii. ---- */
@@ -206,6 +222,13 @@ int ctrb_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, con
                     int64_t B, const int32_t* idx /*[B][T]*/, const double* theta /*[B][T]*/,
                     const double* rad /*[T], host pointer always*/, double* obstacle_min /*[B]*/,
                     double* goal_dist /*[B]*/, double* cost /*[B]*/, uint8_t* collide /*[B], nullable*/, int mem);
+/* The same chain for a static model handle: static solve (g-curves to device scratch) -> collision ->
+ * cost, plus the per-configuration MINPACK info (1 = converged), which the reference discards
+ * (static.py:102-104) and SURVEY 7 makes part of the output contract. */
+int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, const ctrb_cost_desc* cost_desc,
+                           int64_t B, const int32_t* idx, const double* theta, const double* rad,
+                           double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide,
+                           int32_t* info /*[B], nullable*/, int32_t* nfev /*[B], nullable*/, int mem);
 
 /* work counters of the most recent ctrb_eval_batch / ctrb_check_collision_batch on this ctx
  * (bench publishes them): [0] BVH nodes visited, [1] fp32 point-triangle

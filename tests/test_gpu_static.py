@@ -1,0 +1,143 @@
+"""GPU parity: the static model kernels (closed-form residual, warp-cooperative MINPACK hybrd,
+scan-integrated curves) vs the reference's golden vectors and vs the literal CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, FIXTURES
+from models_def import STATIC_MODELS
+from util import gpu_static, orc_static, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gs():
+    return np.load(GOLDEN / "static.npz")
+
+
+def _short(m, idx):
+    return min(m.num_discrete_points[n] - idx[n] for n in range(m.tube_num)) <= 2
+
+
+@pytest.mark.parametrize("name", list(STATIC_MODELS))
+def test_residual_golden(gs, name):
+    """static_equilibrium(x): 4 bracketing nodes + closed forms vs the reference's per-node march."""
+    m = gpu_static(name)
+    np.testing.assert_array_equal(m.general_init_guess, gs[f"{name}/x0"])
+    cases = STATIC_MODELS[name][-1]
+    for c, (idx, th) in enumerate(cases):
+        xs, Fs = gs[f"{name}/c{c}/res_x"], gs[f"{name}/c{c}/res_F"]
+        got = m.static_equilibrium_batch([idx] * len(xs), [th] * len(xs), xs)
+        for F, G in zip(Fs, got):
+            assert np.max(np.abs(G - F)) <= 1e-10 * max(np.max(np.abs(F)), 1e-300), (name, c)
+
+
+@pytest.mark.parametrize("name", list(STATIC_MODELS))
+def test_curves_from_reference_solution(gs, name):
+    """integrate_g parity given the SAME q: feed the reference's solution as the initial guess with a
+    loose xtol so that hybrd accepts it after its first Jacobian (q stays within ~1e-9 of the input)."""
+    m = gpu_static(name)
+    cases = STATIC_MODELS[name][-1]
+    for c, (idx, th) in enumerate(cases):
+        if gs[f"{name}/c{c}/meta_tight"][1] == 0:
+            continue
+        ref_q = gs[f"{name}/c{c}/sol_tight"]
+        res = m.solve_g_batch([idx], [th], initial_guess=ref_q, xtol=1e-13)
+        ref_g = gs[f"{name}/c{c}/g_tight"]
+        assert res["g"].shape == ref_g.shape
+        if _short(m, idx):
+            continue  # degenerate one-step sections: compared through the oracle only
+        assert np.max(np.abs(res["solution"][0] - ref_q)) <= 1e-9 * max(1.0, np.max(np.abs(ref_q)))
+        assert rel_err(res["g"], ref_g) < 1e-8, (name, c, rel_err(res["g"], ref_g))
+
+
+@pytest.mark.parametrize("name", list(STATIC_MODELS))
+def test_solve_g_golden(gs, name):
+    """Static.solve_g from the default initial guess: same root as SciPy's hybr, same success flag, a
+    comparable evaluation count; g-curves within the reference's own loose-vs-tight deviation."""
+    m = gpu_static(name)
+    cases = STATIC_MODELS[name][-1]
+    idx = np.array([c[0] for c in cases], np.int32)
+    th = np.array([c[1] for c in cases])
+    res = m.solve_g_batch(idx, th)
+    T = m.tube_num
+    for c in range(len(cases)):
+        nfev_ref, ok_ref, _ = gs[f"{name}/c{c}/meta_default"]
+        assert bool(res["converged"][c]) == bool(ok_ref), (name, c, res["info"][c])
+        if not ok_ref or _short(m, cases[c][0]):
+            continue
+        ref_q = gs[f"{name}/c{c}/sol_tight"]
+        assert np.max(np.abs(res["solution"][c] - ref_q)) <= 5e-6 * max(1.0, np.max(np.abs(ref_q))), (name, c)
+        assert abs(int(res["nfev"][c]) + 2 - nfev_ref) <= 0.4 * nfev_ref, (name, c, res["nfev"][c], nfev_ref)
+        lo, hi = res["offsets"][c * T], res["offsets"][(c + 1) * T]
+        ref_g = gs[f"{name}/c{c}/g_default"]
+        dev_ref = rel_err(gs[f"{name}/c{c}/g_tight"], ref_g)          # the reference's own loose-tolerance deviation
+        assert rel_err(res["g"][lo:hi], ref_g) <= max(1e-8, 20 * dev_ref), (name, c)
+    # reference-shaped call
+    g = m.solve_g(list(cases[0][0]), list(cases[0][1]))
+    assert [len(t) for t in g] == gs[f"{name}/c0/counts_default"].tolist()
+    assert m.last_solution["success"]
+
+
+def test_random_batch_vs_oracle():
+    """300 random C1 configurations: converged flags and roots vs the CPU oracle's literal hybrd."""
+    from oracle import oracle as orc
+    name = "c1_two_tube"
+    m, s = gpu_static(name), orc_static(name)
+    rng = np.random.default_rng(1001)
+    B = 300
+    idx = rng.integers(0, 118, (B, 2)).astype(np.int32)   # >= 3 nodes per section
+    th = rng.uniform(0, 2 * np.pi, (B, 2))
+    res = m.solve_g_batch(idx, th)
+    agree_flag, agree_root, worst_g = 0, 0, 0.0
+    for b in range(B):
+        g, sol, nfev, info = orc.static_solve_g(s, idx[b], th[b])
+        agree_flag += (info == 1) == bool(res["converged"][b])
+        if info == 1 and res["converged"][b]:
+            same = np.max(np.abs(sol - res["solution"][b])) <= 1e-5 * max(1.0, np.max(np.abs(sol)))
+            agree_root += same
+            if same:
+                lo, hi = res["offsets"][b * 2], res["offsets"][b * 2 + 2]
+                worst_g = max(worst_g, rel_err(res["g"][lo:hi], np.concatenate(g, 0)))
+    assert agree_flag >= 0.98 * B, agree_flag
+    # The equilibrium is multi-stable and hybrd's path is chaotic in its input: perturbing the initial guess by
+    # 1e-13 (relative) moves the ORACLE itself to a different equilibrium in 13 of these 292 configurations
+    # (DESIGN.md section 8).  The closed-form residual differs from the marched one by ~1e-13, so the same
+    # fraction (measured: 15 of 292) lands on another equilibrium here; everything else must be the same root.
+    assert agree_root >= 0.90 * res["converged"].sum(), (agree_root, res["converged"].sum())
+    assert worst_g < 1e-4, worst_g  # both stopped at xtol = 1.49e-8: curves agree to the solver tolerance
+
+
+def test_static_fused_eval():
+    """BASELINE configs[0]: 2-tube static model, 1024 random configs vs in_simple.STL (C1, all collide at the
+    base) and vs the translated box (C1b, distances exercised): static solve -> collision -> cost."""
+    from oracle import oracle as orc
+    from ctrdapp_b200.collision import CollisionChecker
+    name = "c1_two_tube"
+    m, s = gpu_static(name), orc_static(name)
+    rng = np.random.default_rng(1001)
+    B = 1024
+    idx = rng.integers(0, 120, (B, 2)).astype(np.int32)
+    th = rng.uniform(0, 2 * np.pi, (B, 2))
+    cc = CollisionChecker(FIXTURES / "env_c1_in_simple.json")
+    obs, goal, cost, coll = cc.evaluate_batch(m, idx, th, [0.9, 0.6], goal_weight=3.0)
+    assert np.all(obs == -1.0) and np.all(np.isnan(cost)) and cc.last_static["converged"].mean() > 0.9
+    cc = CollisionChecker(FIXTURES / "env_boxes_multi.json")
+    oenv = orc.Env.from_json(FIXTURES / "env_boxes_multi.json")
+    obs, goal, cost, coll = cc.evaluate_batch(m, idx, th, [0.9, 0.6], goal_weight=3.0)
+    # the solve is deterministic: the fused path's curves are those of solve_g_batch, so the oracle's collision
+    # query on those curves must agree to the collision contract (1e-6 mm), whatever equilibrium was reached
+    res = m.solve_g_batch(idx, th)
+    assert np.array_equal(res["info"], cc.last_static["info"])
+    checked = 0
+    for b in range(0, B, 8):
+        curve = [res["g"][res["offsets"][b * 2 + n]:res["offsets"][b * 2 + n + 1]] for n in range(2)]
+        if not np.all(np.isfinite(res["g"][res["offsets"][b * 2]:res["offsets"][b * 2 + 2]])):
+            continue
+        o_obs, o_goal = oenv.check_collision(curve, [0.9, 0.6])
+        assert (o_obs < 0) == (obs[b] < 0)
+        if o_obs > 0:
+            assert abs(o_obs - obs[b]) < 1e-6 and abs(o_goal - goal[b]) < 1e-6
+            assert cost[b] == pytest.approx(3.0 * max(o_goal, 0.0) + 1.0 / o_obs ** 2, rel=1e-9)
+        checked += 1
+    assert checked > 100

@@ -42,3 +42,17 @@ def random_configs(npts, B, rng, lo_exposure=None, hi_exposure=None):
         idx = np.asarray(npts)[None, :] - 1 - e
     theta = rng.uniform(0, 2 * np.pi, (B, T))
     return idx.astype(np.int32), theta
+
+
+def gpu_static(name):
+    from ctrdapp_b200.model.static import Static
+    from models_def import STATIC_MODELS
+    bases, dof, q, lengths, dx, r_out, r_in, degree, cases = STATIC_MODELS[name]
+    return Static(len(lengths), split_q(q, dof), dof, lengths, dx, bases, {"outer": r_out, "inner": r_in}, degree)
+
+
+def orc_static(name):
+    from oracle import oracle as orc
+    from models_def import STATIC_MODELS
+    bases, dof, q, lengths, dx, r_out, r_in, degree, cases = STATIC_MODELS[name]
+    return orc.make_static(bases, dof, q, lengths, dx, r_out, r_in, degree)
