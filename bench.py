@@ -4,11 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (libctrb200, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on all host threads
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 3-tube model,
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 3-tube STATIC model,
 tube_lengths [33,66,99] at delta_x = 1 (100 arc-length nodes on the longest tube), against
-colon_straight.STL (11 492 triangles) posed mid-lumen, 10^7 configurations per step and GPU.
-A "step" is one pass of the hot path over one batch: g-curve positions (never leave the SM),
-chain-vs-mesh distance, goal distance, own cost, and the best-node reduction.
+colon_straight.STL (11 492 triangles) posed mid-lumen.  A "step" is one pass of the hot path over one
+batch: per-configuration equilibrium solve (MINPACK hybrd, 30 unknowns) + section curves, chain-vs-mesh
+distance, goal distance, own cost, and the best-node reduction.  The kinematic-model variant of the same
+chain (g-curve positions never leave the SM) is `--workload c3_kinematic_*` and is always reported
+under "extra" together with the configs[1] g-curve kernel.
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
@@ -34,9 +36,12 @@ LENGTHS, DX, RAD = [33, 66, 99], 1, [1.2, 0.9, 0.6]
 NPTS = [34, 67, 100]
 GOAL_WEIGHT = 3.0
 ENV_FILE = ROOT / "tests" / "fixtures" / "env_c3_colon_straight.json"
-WORKLOADS = {  # exposure range per tube ("shallow" and "uniform")
-    "c3_kinematic_colon_straight_shallow": (1, 8),
-    "c3_kinematic_colon_straight_uniform": (1, 33),
+RIN = [1.0, 0.7, 0.4]
+WORKLOADS = {  # name -> (model, exposure lo, hi, default configs per step per GPU); SURVEY 8d "shallow" / "uniform"
+    "c3_static_colon_straight_shallow": ("static", 1, 8, 1 << 20),
+    "c3_static_colon_straight_uniform": ("static", 1, 33, 1 << 18),
+    "c3_kinematic_colon_straight_shallow": ("kinematic", 1, 8, 10_000_000),
+    "c3_kinematic_colon_straight_uniform": ("kinematic", 1, 33, 10_000_000),
 }
 BYTES_PER_CONFIG = 3 * (4 + 8) + (8 + 8 + 8 + 1)  # idx + theta in, obstacle_min + goal_dist + cost + bit out
 
@@ -94,16 +99,23 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def oracle_objects():
+def oracle_objects(kind="kinematic"):
     from oracle import oracle as orc
-    om = orc.make_model(BASES, DOF, Q, LENGTHS, DX)
+    if kind == "static":
+        om = orc.make_static(BASES, DOF, Q, LENGTHS, DX, RAD, RIN, 2)
+    else:
+        om = orc.make_model(BASES, DOF, Q, LENGTHS, DX)
     oenv = orc.Env.from_json(ENV_FILE)
     return orc, om, oenv
 
 
 def time_oracle(om, oenv, idx, theta, threads):
+    from oracle import oracle as orc
     t0 = time.perf_counter()
-    obs, goal, cost = oenv.eval_batch(om, idx, theta, RAD, GOAL_WEIGHT, nthreads=threads)
+    if isinstance(om, orc.OrcStatic):
+        obs = orc.static_eval_batch(oenv, om, idx, theta, RAD, GOAL_WEIGHT, nthreads=threads)[0]
+    else:
+        obs = oenv.eval_batch(om, idx, theta, RAD, GOAL_WEIGHT, nthreads=threads)[0]
     return time.perf_counter() - t0, obs
 
 
@@ -112,9 +124,11 @@ def run_reference(args, rank):
     timed implementation is the C oracle port of it, on every host thread this process may use."""
     if rank != 0:
         return
-    lo, hi = WORKLOADS[args.workload]
+    kind, lo, hi, _ = WORKLOADS[args.workload]
     threads = len(os.sched_getaffinity(0))
-    _, om, oenv = oracle_objects()
+    _, om, oenv = oracle_objects(kind)
+    if args.ref_sample <= 0:
+        args.ref_sample = 16384 if kind == "static" else 65536
     idx, theta = make_inputs(args.ref_sample, 1003, lo, hi)
     for _ in range(args.warmup):
         time_oracle(om, oenv, idx, theta, threads)
@@ -129,7 +143,7 @@ def run_reference(args, rank):
             "unit": "configs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": args.workload, "configs_per_step": args.ref_sample,
-                                            "model": "3-tube kinematic, 100 arc-length nodes",
+                                            "model": f"3-tube {kind}, 100 arc-length nodes",
                                             "environment": "colon_straight.STL (11492 triangles), mid-lumen pose"},
             "cpu_baseline": {"value": value, "unit": "configs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "configs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -143,9 +157,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=10_000_000, help="configurations per step and per GPU")
-    ap.add_argument("--workload", default="c3_kinematic_colon_straight_shallow", choices=list(WORKLOADS))
-    ap.add_argument("--ref-sample", type=int, default=65536, help="configs per step of the CPU arm")
+    ap.add_argument("--batch", type=int, default=0, help="configurations per step and per GPU (0 = workload default)")
+    ap.add_argument("--workload", default="c3_static_colon_straight_shallow", choices=list(WORKLOADS))
+    ap.add_argument("--ref-sample", type=int, default=0, help="configs per step of the CPU arm (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / kernels report")
     args = ap.parse_args()
@@ -174,10 +188,14 @@ def main():
 
     ctx = L.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    m = Kinematic(3, [np.array(Q[0:2]), np.array(Q[2:5]), np.array(Q[5:8])], DOF, LENGTHS, DX, BASES, ctx=ctx)
+    from ctrdapp_b200.model.static import Static
+    qs = [np.array(Q[0:2]), np.array(Q[2:5]), np.array(Q[5:8])]
+    mk = Kinematic(3, qs, DOF, LENGTHS, DX, BASES, ctx=ctx)
+    ms = Static(3, qs, DOF, LENGTHS, DX, BASES, {"outer": RAD, "inner": RIN}, 2, ctx=ctx)
     cc = CollisionChecker(ENV_FILE, ctx=ctx)
-    lo, hi = WORKLOADS[args.workload]
-    B = args.batch
+    kind, lo, hi, default_B = WORKLOADS[args.workload]
+    m = ms if kind == "static" else mk
+    B = args.batch or default_B
     idx_h, theta_h = make_inputs(B, 1003 + rank, lo, hi)
 
     # ---- device-resident arm: inputs already in HBM
@@ -192,9 +210,24 @@ def main():
     gathered = torch.empty(world * 2, dtype=torch.float64, device=dev) if world > 1 else None
     lib = L.lib()
 
+    info_d = torch.empty(B, dtype=torch.int32, device=dev)
+    nfev_d = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def eval_any(model, n, idx_p, theta_p, outs, mem):
+        """one pass of the hot path over n configurations (device or host buffers)"""
+        o, g, c, cl, inf, nf = outs
+        if model is ms:
+            L.check(lib.ctrb_static_eval_batch(ctx.handle, model.handle, cc.handle, C.byref(cd), n, L.ptr(idx_p),
+                                               L.ptr(theta_p), L.ptr(rad), L.ptr(o), L.ptr(g), L.ptr(c), L.ptr(cl),
+                                               L.ptr(inf), L.ptr(nf), mem))
+        else:
+            L.check(lib.ctrb_eval_batch(ctx.handle, model.handle, cc.handle, C.byref(cd), n, L.ptr(idx_p), L.ptr(theta_p),
+                                        L.ptr(rad), L.ptr(o), L.ptr(g), L.ptr(c), L.ptr(cl), mem))
+
+    dev_outs = (obs_d, goal_d, cost_d, coll_d, info_d, nfev_d)
+
     def eval_dev():
-        L.check(lib.ctrb_eval_batch(ctx.handle, m.handle, cc.handle, C.byref(cd), B, L.ptr(idx_d), L.ptr(theta_d),
-                                    L.ptr(rad), L.ptr(obs_d), L.ptr(goal_d), L.ptr(cost_d), L.ptr(coll_d), L.MEM_DEVICE))
+        eval_any(m, B, idx_d, theta_d, dev_outs, L.MEM_DEVICE)
 
     def step():
         eval_dev()
@@ -221,20 +254,21 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
+    kern_ms, aux_ms = [], []
     barrier()
     e0.record()
+    dom = "static_solve" if kind == "static" else "chain_eval"
     for _ in range(args.steps):
-        ctx.mark(0)
         eval_dev()
-        ctx.mark(1)
         best_cost, best_index = C.c_double(), C.c_int64()
         L.check(lib.ctrb_argmin_cost(ctx.handle, B, L.ptr(cost_d), rank * B, C.byref(best_cost), C.byref(best_index),
                                      L.MEM_DEVICE))
         if world > 1:
             mine = torch.tensor([best_cost.value, float(best_index.value)], dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(gathered, mine)
-        kern_ms.append(ctx.elapsed_ms())
+        kern_ms.append(ctx.last_kernel_ms(dom))  # CUDA events around the dominant kernel, on its stream
+        if kind == "static":
+            aux_ms.append(ctx.last_kernel_ms("chain_eval"))
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -253,10 +287,10 @@ def main():
     idx_p, theta_p = pin(idx_h), pin(theta_h)
     obs_p, goal_p, cost_p = (pin(np.empty(B)) for _ in range(3))
     coll_p = pin(np.empty(B, np.uint8))
+    info_p, nfev_p = pin(np.empty(B, np.int32)), pin(np.empty(B, np.int32))
 
     def step_host():
-        L.check(lib.ctrb_eval_batch(ctx.handle, m.handle, cc.handle, C.byref(cd), B, L.ptr(idx_p), L.ptr(theta_p),
-                                    L.ptr(rad), L.ptr(obs_p), L.ptr(goal_p), L.ptr(cost_p), L.ptr(coll_p), L.MEM_HOST))
+        eval_any(m, B, idx_p, theta_p, (obs_p, goal_p, cost_p, coll_p, info_p, nfev_p), L.MEM_HOST)
         return float(np.nanmin(cost_p)) if np.isfinite(cost_p).any() else float("inf")
 
     step_host()
@@ -271,61 +305,91 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B / float(te.item())
-    assert np.array_equal(obs_p < 0, (obs_d < 0).cpu().numpy())
+    assert np.array_equal(obs_p < 0, (obs_d < 0).cpu().numpy())  # host-buffer and device-buffer paths agree
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (chain_eval_kernel<fused>), timed live with CUDA events on its stream
+    # ---- roofline of the dominant kernel, timed live with CUDA events on its stream
     peak, peak_src = measured_peaks()
     k_ms = float(np.mean(kern_ms))
-    achieved = BYTES_PER_CONFIG * B / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "chain_eval_kernel<true>", "kernel_ms": k_ms,
-                "algorithmic_bytes_per_config": BYTES_PER_CONFIG, "peak_source": peak_src,
-                "note": "latency/compute-bound tree traversal: HBM traffic is ~61 B/config by construction; "
-                        "see compute_roofline for the binding resource"}
     f32_peak, f64_peak = ctx.measure_fma_peak(32), ctx.measure_fma_peak(64)
     per = 1.0 / max(work["configs"], 1)
-    flop32 = (work["bvh_nodes"] * 30.0 + work["prefilter_tests"] * 60.0) * per
-    flop64 = work["exact_tests"] * 350.0 * per
-    compute = {"bvh_nodes_per_config": work["bvh_nodes"] * per, "prefilter_tests_per_config": work["prefilter_tests"] * per,
-               "exact_tests_per_config": work["exact_tests"] * per, "fp32_flop_per_config": flop32,
-               "fp64_flop_per_config": flop64, "fp32_tflops_achieved": flop32 * B / (k_ms * 1e-3) / 1e12,
-               "fp64_tflops_achieved": flop64 * B / (k_ms * 1e-3) / 1e12, "fp32_fma_peak_tflops_measured": f32_peak,
-               "fp64_fma_peak_tflops_measured": f64_peak,
-               "flop_model": "30/BVH node + 60/point-triangle prefilter (fp32), 350/exact cylinder-triangle (fp64), SURVEY 8d"}
+    if kind == "static":
+        nfev_mean = float(nfev_d.double().mean().item())
+        conv_frac = float((info_d == 1).double().mean().item())
+        nodes_mean = float((3 * 1 + (np.asarray(NPTS)[None, :] - 1 - idx_h).sum(1)).mean())
+        # algorithmic HBM bytes of the solve: inputs, info/nfev, and the section curves it writes (128 B/node)
+        bpc = 3 * 12 + 8 + 128.0 * nodes_mean
+        achieved = bpc * B / (k_ms * 1e-3) / 1e9
+        # FLOP model: 2.6 kFLOP per residual evaluation (12 node integrands, closed forms) +
+        # hybrd's dense algebra per Jacobian (QR + Q: 2 n^3) and per iteration (dogleg, r1updt, r1mpyq: 9 n^2), n = 30
+        n_jac = max(1.0, nfev_mean / 45.0)
+        flop64 = nfev_mean * 2600.0 + n_jac * 2 * 30 ** 3 + max(nfev_mean - 30 * n_jac, 1.0) * 9 * 30 ** 2 + nodes_mean * 260.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "static_solve_kernel", "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_config": bpc, "peak_source": peak_src,
+                    "note": "per-configuration nonlinear solve: bound by fp64 CUDA-core latency/throughput and "
+                            "shared-memory traffic of hybrd's work arrays, not HBM; see compute_roofline"}
+        compute = {"residual_evaluations_per_config": nfev_mean, "converged_fraction": conv_frac,
+                   "fp64_flop_per_config": flop64, "fp64_tflops_achieved": flop64 * B / (k_ms * 1e-3) / 1e12,
+                   "fp64_fma_peak_tflops_measured": f64_peak, "fp32_fma_peak_tflops_measured": f32_peak,
+                   "collision_kernel_ms": float(np.mean(aux_ms)), "collision_share_of_step": float(np.mean(aux_ms)) / ms_per_step,
+                   "solve_share_of_step": k_ms / ms_per_step,
+                   "bvh_nodes_per_config": work["bvh_nodes"] * per, "exact_tests_per_config": work["exact_tests"] * per,
+                   "flop_model": "2.6 kFLOP/residual evaluation + hybrd dense algebra (n = 30) + 260/output node"}
+    else:
+        achieved = BYTES_PER_CONFIG * B / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "chain_eval_kernel<true>", "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_config": BYTES_PER_CONFIG, "peak_source": peak_src,
+                    "note": "latency/compute-bound tree traversal: HBM traffic is ~61 B/config by construction; "
+                            "see compute_roofline for the binding resource"}
+        flop32 = (work["bvh_nodes"] * 30.0 + work["prefilter_tests"] * 60.0) * per
+        flop64 = work["exact_tests"] * 350.0 * per
+        compute = {"bvh_nodes_per_config": work["bvh_nodes"] * per, "prefilter_tests_per_config": work["prefilter_tests"] * per,
+                   "exact_tests_per_config": work["exact_tests"] * per, "fp32_flop_per_config": flop32,
+                   "fp64_flop_per_config": flop64, "fp32_tflops_achieved": flop32 * B / (k_ms * 1e-3) / 1e12,
+                   "fp64_tflops_achieved": flop64 * B / (k_ms * 1e-3) / 1e12, "fp32_fma_peak_tflops_measured": f32_peak,
+                   "fp64_fma_peak_tflops_measured": f64_peak,
+                   "flop_model": "30/BVH node + 60/point-triangle prefilter (fp32), 350/exact cylinder-triangle (fp64), SURVEY 8d"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
-        _, om, oenv = oracle_objects()
-        dt, _ = time_oracle(om, oenv, idx_h[:8192], theta_h[:8192], threads)
-        n = int(min(B, max(8192, 15.0 / max(dt / 8192, 1e-9))))
+        _, om, oenv = oracle_objects(kind)
+        n0 = 2048 if kind == "static" else 8192
+        dt, _ = time_oracle(om, oenv, idx_h[:n0], theta_h[:n0], threads)
+        n = int(min(B, max(n0, 15.0 / max(dt / n0, 1e-9))))
         dt, o_obs = time_oracle(om, oenv, idx_h[:n], theta_h[:n], threads)
-        agree = bool(np.array_equal(o_obs < 0, obs_p[:n] < 0))
+        agree = float(np.mean((o_obs < 0) == (obs_p[:n] < 0)))
         cpu = {"value": n / dt, "unit": "configs/s", "cores": threads, "kind": "port",
                "sample": f"first {n} configs of the timed batch ({dt:.1f} s, oracle C port of the reference path, "
-                         f"pthreads; collision bits equal to the GPU's: {agree})"}
+                         f"pthreads; collision-bit agreement with the GPU: {agree:.4f})"}
 
     extra = {}
     if not args.no_extra:
         # secondary figures (not bench lines): the other exposure distribution, and the C2 g-curve kernel
-        for name, (l2, h2) in WORKLOADS.items():
+        for name, (k2, l2, h2, _) in WORKLOADS.items():
             if name == args.workload:
                 continue
-            Bx = min(B, 2_000_000)
+            mx = ms if k2 == "static" else mk
+            Bx = min(B, 1 << 17) if k2 == "static" else 2_000_000
             ih, th = make_inputs(Bx, 1003, l2, h2)
             idd, thd = torch.from_numpy(ih).to(dev), torch.from_numpy(th).to(dev)
+            outs = tuple(torch.empty(Bx, dtype=t.dtype, device=dev) for t in dev_outs)
             for rep in range(2):
                 ctx.mark(0)
-                L.check(lib.ctrb_eval_batch(ctx.handle, m.handle, cc.handle, C.byref(cd), Bx, L.ptr(idd), L.ptr(thd),
-                                            L.ptr(rad), L.ptr(obs_d), L.ptr(goal_d), L.ptr(cost_d), L.ptr(coll_d), L.MEM_DEVICE))
+                eval_any(mx, Bx, idd, thd, outs, L.MEM_DEVICE)
                 ctx.mark(1)
-                ms = ctx.elapsed_ms()
-            extra[name] = {"configs_per_s": Bx / (ms * 1e-3), "collide_fraction": float((obs_d[:Bx] < 0).double().mean().item())}
+                ms_ = ctx.elapsed_ms()
+            extra[name] = {"configs_per_s": Bx / (ms_ * 1e-3), "configs": Bx,
+                           "collide_fraction": float((outs[0] < 0).double().mean().item())}
+            if k2 == "static":
+                extra[name]["converged_fraction"] = float((outs[4] == 1).double().mean().item())
+                extra[name]["residual_evaluations_per_config"] = float(outs[5].double().mean().item())
         m2 = Kinematic(2, [np.array([0.02, 0.001]), np.array([0.05, 0.0001, 0.002])], [2, 3], [120, 120], 1,
                        ["linear", "linear"], ctx=ctx)
         rng = np.random.default_rng(1002)
@@ -352,10 +416,13 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "configs_per_step_per_gpu": B,
-                       "model": "3-tube kinematic (linear bases, q_dof [2,3,3]), tube_lengths [33,66,99], delta_x 1",
+                       "model": f"3-tube {kind} (linear bases, q_dof [2,3,3]), tube_lengths [33,66,99], delta_x 1"
+                                + (", last_strain_base degree 2, 30 unknowns, MINPACK hybrd xtol 1.49e-8" if kind == "static" else ""),
                        "environment": "colon_straight.STL (11492 triangles) translated to a mid-lumen pose + Sphere(5) goal",
                        "exposure_per_tube": [lo, hi], "collide_fraction": collide_frac,
-                       "l2": "inputs+outputs are 610 MB per step (> 126 MB L2); no explicit flush",
+                       "l2": f"per step {BYTES_PER_CONFIG * B / 1e6:.0f} MB of inputs+outputs"
+                             + (f" + {128 * 30 * B / 1e6:.0f} MB of section curves" if kind == "static" else "")
+                             + " stream through HBM (L2 is 126 MB); no explicit flush",
                        "parallelism": f"dp{world} (configs sharded, best node gathered over NCCL)" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": B * 3 * 12, "d2h_bytes_per_step": B * 25,

@@ -156,6 +156,11 @@ int ctrb_ctx_create(int device, ctrb_ctx** out) {
         CTRB_CUDA(cudaEventCreate(&c->ev[i]));
         CTRB_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     }
+    for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < 2; ++i) {
+            CTRB_CUDA(cudaEventCreate(&c->kev[k][i]));
+            CTRB_CUDA(cudaEventRecord(c->kev[k][i], c->stream));
+        }
     CTRB_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
     CTRB_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
     cudaDeviceProp prop;
@@ -182,6 +187,8 @@ void ctrb_ctx_destroy(ctrb_ctx* c) {
         cudaEventDestroy(c->ev[i]);
         cudaEventDestroy(c->ev_chunk[i]);
     }
+    for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(c->kev[k][i]);
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->stream2);
     delete c;
@@ -224,6 +231,14 @@ int ctrb_ctx_elapsed_ms(ctrb_ctx* c, float* ms) {
     CTRB_CUDA(cudaSetDevice(c->device));
     CTRB_CUDA(cudaEventSynchronize(c->ev[1]));
     CTRB_CUDA(cudaEventElapsedTime(ms, c->ev[0], c->ev[1]));
+    return CTRB_OK;
+}
+
+int ctrb_ctx_last_kernel_ms(ctrb_ctx* c, int kernel_id, float* ms) {
+    CTRB_REQUIRE(c && ms && kernel_id >= 0 && kernel_id < 4, "ctrb_ctx_last_kernel_ms: bad argument");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaEventSynchronize(c->kev[kernel_id][1]));
+    CTRB_CUDA(cudaEventElapsedTime(ms, c->kev[kernel_id][0], c->kev[kernel_id][1]));
     return CTRB_OK;
 }
 

@@ -439,9 +439,11 @@ int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
     int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * per_sm);
     if (fused) {
         CTRB_CUDA(cudaFuncSetAttribute(chain_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelTimer kt(ctx, CTRB_KERNEL_CHAIN_EVAL);
         chain_eval_kernel<true><<<grid, kCWarps * 32, smem, ctx->stream>>>(P);
     } else {
         CTRB_CUDA(cudaFuncSetAttribute(chain_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelTimer kt(ctx, CTRB_KERNEL_CHAIN_EVAL);
         chain_eval_kernel<false><<<grid, kCWarps * 32, smem, ctx->stream>>>(P);
     }
     ctx->launches++;

@@ -73,6 +73,7 @@ struct ctrb_ctx {
     cudaStream_t stream2;  // second stream for host-memory chunk pipelining
     cudaEvent_t ev[2];
     cudaEvent_t ev_chunk[2];
+    cudaEvent_t kev[4][2];  // per-kernel start/stop of the most recent launch (ctrb_kernel_id)
     int64_t launches;
     // grow-only device scratch
     void* scratch[12];
@@ -155,6 +156,13 @@ struct ctrb_env {
 };
 
 namespace ctrb {
+// records the bracketing events of one of the four hot kernels on the launching stream
+struct KernelTimer {
+    ctrb_ctx* c;
+    int id;
+    KernelTimer(ctrb_ctx* ctx, int kid) : c(ctx), id(kid) { cudaEventRecord(c->kev[id][0], c->stream); }
+    ~KernelTimer() { cudaEventRecord(c->kev[id][1], c->stream); }
+};
 // scratch helper: returns device pointer of at least `bytes` in slot `slot`
 int ctx_scratch(ctrb_ctx* ctx, int slot, size_t bytes, void** out);
 }  // namespace ctrb

@@ -442,6 +442,7 @@ int launch_gcurve(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_t
     long long ngroups = (B + 31) / 32;
     long long blocks_needed = (ngroups + kGWarps - 1) / kGWarps;
     int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * 4);
+    KernelTimer kt(ctx, CTRB_KERNEL_GCURVE);
     if (precision == CTRB_F64) {
         CTRB_CUDA(cudaFuncSetAttribute(kin_gcurve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kin_gcurve_kernel<double><<<grid, kGWarps * 32, smem, ctx->stream>>>(m->mc, m->tables(), B, idx, theta, full, offsets,
@@ -490,6 +491,7 @@ int launch_eta_ftl(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_
     if (B <= 0) return CTRB_OK;
     long long blocks_needed = (B + kEWarps - 1) / kEWarps;
     int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * 8);
+    KernelTimer kt(ctx, CTRB_KERNEL_ETA_FTL);
     kin_eta_ftl_kernel<<<grid, kEWarps * 32, 0, ctx->stream>>>(m->mc, B, prev_idx, new_idx, velocity, delta_theta, prev_g, prev_off,
                                                               eta_out, ftl_out, ftl_mag, err_flag);
     ctx->launches++;

@@ -54,8 +54,13 @@ __device__ __forceinline__ double ipoly3(const double* q, double X) {
     return q[0] * X + q[1] * (0.5 * X * X) + q[2] * (X * X * X * (1.0 / 3.0));
 }
 
+// one out-of-line copy each of the fp64 sincos and of the strain-base switch: the solve kernel is
+// instruction-cache bound if these are inlined at every use (ncu: stall_no_instruction 17 per issue)
+__device__ __noinline__ void sincos_ni(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __noinline__ void strain_omega_ni(const ModelConst& mc, int n, double x, double w[3]) { strain_omega(mc, n, x, w); }
+
 // rows 0..2 of a strain base as a 3 x dof matrix (strain_bases.py:7-224)
-__device__ void strain_base_rows(int kind, int dof, double x, double B[3][CTRB_MAX_DOF]) {
+__device__ __noinline__ void strain_base_rows(int kind, int dof, double x, double B[3][CTRB_MAX_DOF]) {
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -99,7 +104,7 @@ __device__ void strain_base_rows(int kind, int dof, double x, double B[3][CTRB_M
 
 // ------------------------------------------------------------------ per-configuration setup
 // static.py:81-95 section indices; :456-491 quadrature brackets
-__device__ void st_setup(const StModel& sm, const int* idx, const double* theta, StCfg& c) {
+__device__ __noinline__ void st_setup(const StModel& sm, const int* idx, const double* theta, StCfg& c) {
     const int T = sm.mc.T;
     const int* N = sm.mc.npts;
     int i11 = idx[0], i22 = idx[T - 2], i33 = idx[T - 1];
@@ -143,7 +148,7 @@ __device__ void st_setup(const StModel& sm, const int* idx, const double* theta,
 
 // ------------------------------------------------------------------ integrands at one node
 // section 1 (static.py:261-345), three tubes; y = [intc1 (9), intg21 (3), intg31 (3)]
-__device__ void node_sec1(const StModel& sm, const StCfg& c, const double* q, int i, double y[15]) {
+__device__ __noinline__ void node_sec1(const StModel& sm, const StCfg& c, const double* q, int i, double y[15]) {
     const double dx = sm.mc.dx, X = i * dx;
     const double* q11 = q + sm.qoff[0];
     const double* q21 = q + sm.qoff[1];
@@ -151,18 +156,18 @@ __device__ void node_sec1(const StModel& sm, const StCfg& c, const double* q, in
     V3 w1 = {poly3(q11, X), poly3(q11 + 3, X), poly3(q11 + 6, X)};
     const double tg21 = poly3(q21, X), tg31 = poly3(q31, X);
     double s21, c21, s31, c31;
-    sincos(c.th[1] + ipoly3(q21, X), &s21, &c21);  // gg21 = Rx(theta1 + int tau21)
-    sincos(c.th[2] + ipoly3(q31, X), &s31, &c31);
+    sincos_ni(c.th[1] + ipoly3(q21, X), &s21, &c21);  // gg21 = Rx(theta1 + int tau21)
+    sincos_ni(c.th[2] + ipoly3(q31, X), &s31, &c31);
     V3 w21 = rotxT(s21, c21, w1);
     w21.x += tg21;
     V3 w31 = rotxT(s31, c31, w21);
     w31.x += tg31;
     double ws[3];
-    strain_omega(sm.mc, 0, (i + c.i11) * dx, ws);
+    strain_omega_ni(sm.mc, 0, (i + c.i11) * dx, ws);
     V3 m11 = {sm.Kr[0][0] * (w1.x - ws[0]), sm.Kr[0][1] * (w1.y - ws[1]), sm.Kr[0][2] * (w1.z - ws[2])};
-    strain_omega(sm.mc, 1, (i + c.i21) * dx, ws);
+    strain_omega_ni(sm.mc, 1, (i + c.i21) * dx, ws);
     V3 m21 = {sm.Kr[1][0] * (w21.x - ws[0]), sm.Kr[1][1] * (w21.y - ws[1]), sm.Kr[1][2] * (w21.z - ws[2])};
-    strain_omega(sm.mc, 2, (i + c.i31) * dx, ws);
+    strain_omega_ni(sm.mc, 2, (i + c.i31) * dx, ws);
     V3 m31 = {sm.Kr[2][0] * (w31.x - ws[0]), sm.Kr[2][1] * (w31.y - ws[1]), sm.Kr[2][2] * (w31.z - ws[2])};
     V3 r31m = rotx(s31, c31, m31);                 // coAd(gg31) fi_31 (moment part)
     V3 u = {m21.x + r31m.x, m21.y + r31m.y, m21.z + r31m.z};
@@ -183,7 +188,7 @@ __device__ void node_sec1(const StModel& sm, const StCfg& c, const double* q, in
 }
 
 // section 2 (static.py:347-436); y = [intc2 (9), intg32 (3), intg312 (3)]
-__device__ void node_sec2(const StModel& sm, const StCfg& c, const double* q, int i, double s31e, double c31e,
+__device__ __noinline__ void node_sec2(const StModel& sm, const StCfg& c, const double* q, int i, double s31e, double c31e,
                           const double S31e[3], double y[15]) {
     const int T = sm.mc.T;
     const double dx = sm.mc.dx, X = i * dx;
@@ -192,13 +197,13 @@ __device__ void node_sec2(const StModel& sm, const StCfg& c, const double* q, in
     V3 w2 = {poly3(q22, X), poly3(q22 + 3, X), poly3(q22 + 6, X)};
     const double t32 = poly3(q32, X);
     double s32, c32;
-    sincos((T == 2 ? c.th[1] : 0.0) + ipoly3(q32, X), &s32, &c32);
+    sincos_ni((T == 2 ? c.th[1] : 0.0) + ipoly3(q32, X), &s32, &c32);
     V3 w32 = rotxT(s32, c32, rotxT(s31e, c31e, w2));
     w32.x += t32;
     double ws[3];
-    strain_omega(sm.mc, T - 2, (i + c.i22) * dx, ws);
+    strain_omega_ni(sm.mc, T - 2, (i + c.i22) * dx, ws);
     V3 m22 = {sm.Kr[T - 2][0] * (w2.x - ws[0]), sm.Kr[T - 2][1] * (w2.y - ws[1]), sm.Kr[T - 2][2] * (w2.z - ws[2])};
-    strain_omega(sm.mc, T - 1, (i + c.i32) * dx, ws);
+    strain_omega_ni(sm.mc, T - 1, (i + c.i32) * dx, ws);
     V3 m32 = {sm.Kr[T - 1][0] * (w32.x - ws[0]), sm.Kr[T - 1][1] * (w32.y - ws[1]), sm.Kr[T - 1][2] * (w32.z - ws[2])};
     V3 a = rotx(s31e, c31e, rotx(s32, c32, m32));   // coAd31 coAd32 fi_32
     V3 wsum = {m22.x + a.x, m22.y + a.y, m22.z + a.z};
@@ -216,7 +221,7 @@ __device__ void node_sec2(const StModel& sm, const StCfg& c, const double* q, in
 }
 
 // section 3 (static.py:438-452); y = intc3 (dof of the last tube)
-__device__ void node_sec3(const StModel& sm, const StCfg& c, const double* q, int i, double y[CTRB_MAX_DOF]) {
+__device__ __noinline__ void node_sec3(const StModel& sm, const StCfg& c, const double* q, int i, double y[CTRB_MAX_DOF]) {
     const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
     const double* q33 = q + sm.qoff[5];
     double B[3][CTRB_MAX_DOF];
@@ -235,7 +240,7 @@ __device__ void node_sec3(const StModel& sm, const StCfg& c, const double* q, in
 }
 
 // static_equilibrium (static.py:228-259): F(q), n = sm.nq
-__device__ void st_residual(const StModel& sm, const StCfg& c, const double* q, double* F) {
+__device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, const double* q, double* F) {
     const int T = sm.mc.T;
     double s31e = 0.0, c31e = 1.0, S31e[3] = {0.0, 0.0, 0.0};
     double F31[3] = {0.0, 0.0, 0.0};
@@ -244,12 +249,14 @@ __device__ void st_residual(const StModel& sm, const StCfg& c, const double* q, 
 #pragma unroll
         for (int k = 0; k < 15; ++k) acc[k] = 0.0;
         if (c.len[0] > 0.0) {
+#pragma unroll 1
             for (int a = 0; a < 2; ++a) {
-                double ylo[15], yhi[15];
-                node_sec1(sm, c, q, c.lo[0][a], ylo);
-                node_sec1(sm, c, q, c.hi[0][a], yhi);
-#pragma unroll
-                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * (((yhi[k] - ylo[k]) / c.dxs[0][a]) * c.dxn[0][a] + ylo[k]);
+                double y2[2][15];
+#pragma unroll 1
+                for (int e = 0; e < 2; ++e) node_sec1(sm, c, q, e ? c.hi[0][a] : c.lo[0][a], y2[e]);
+                const double inv = 1.0 / c.dxs[0][a];
+#pragma unroll 1
+                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * (((y2[1][k] - y2[0][k]) * inv) * c.dxn[0][a] + y2[0][k]);
             }
         }
         const double h = c.len[0] / 2;
@@ -258,7 +265,7 @@ __device__ void st_residual(const StModel& sm, const StCfg& c, const double* q, 
         for (int k = 0; k < 3; ++k) F31[k] = h * acc[12 + k];
         // final relative frame / basis integral of tube 3 over section 1 (equilibrium_three's return)
         const double Xe = (c.L[0] - 1) * sm.mc.dx;
-        sincos(c.th[2] + ipoly3(q + sm.qoff[2], Xe), &s31e, &c31e);
+        sincos_ni(c.th[2] + ipoly3(q + sm.qoff[2], Xe), &s31e, &c31e);
         S31e[0] = Xe;
         S31e[1] = 0.5 * Xe * Xe;
         S31e[2] = Xe * Xe * Xe * (1.0 / 3.0);
@@ -268,12 +275,14 @@ __device__ void st_residual(const StModel& sm, const StCfg& c, const double* q, 
 #pragma unroll
         for (int k = 0; k < 15; ++k) acc[k] = 0.0;
         if (c.len[1] > 0.0) {
+#pragma unroll 1
             for (int a = 0; a < 2; ++a) {
-                double ylo[15], yhi[15];
-                node_sec2(sm, c, q, c.lo[1][a], s31e, c31e, S31e, ylo);
-                node_sec2(sm, c, q, c.hi[1][a], s31e, c31e, S31e, yhi);
-#pragma unroll
-                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * (((yhi[k] - ylo[k]) / c.dxs[1][a]) * c.dxn[1][a] + ylo[k]);
+                double y2[2][15];
+#pragma unroll 1
+                for (int e = 0; e < 2; ++e) node_sec2(sm, c, q, e ? c.hi[1][a] : c.lo[1][a], s31e, c31e, S31e, y2[e]);
+                const double inv = 1.0 / c.dxs[1][a];
+#pragma unroll 1
+                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * (((y2[1][k] - y2[0][k]) * inv) * c.dxn[1][a] + y2[0][k]);
             }
         }
         const double h = c.len[1] / 2;
@@ -287,11 +296,14 @@ __device__ void st_residual(const StModel& sm, const StCfg& c, const double* q, 
         double acc[CTRB_MAX_DOF];
         for (int k = 0; k < CTRB_MAX_DOF; ++k) acc[k] = 0.0;
         if (c.len[2] > 0.0) {
+#pragma unroll 1
             for (int a = 0; a < 2; ++a) {
-                double ylo[CTRB_MAX_DOF], yhi[CTRB_MAX_DOF];
-                node_sec3(sm, c, q, c.lo[2][a], ylo);
-                node_sec3(sm, c, q, c.hi[2][a], yhi);
-                for (int k = 0; k < dof; ++k) acc[k] += 0.5 * (((yhi[k] - ylo[k]) / c.dxs[2][a]) * c.dxn[2][a] + ylo[k]);
+                double y2[2][CTRB_MAX_DOF];
+#pragma unroll 1
+                for (int e = 0; e < 2; ++e) node_sec3(sm, c, q, e ? c.hi[2][a] : c.lo[2][a], y2[e]);
+                const double inv = 1.0 / c.dxs[2][a];
+#pragma unroll 1
+                for (int k = 0; k < dof; ++k) acc[k] += 0.5 * (((y2[1][k] - y2[0][k]) * inv) * c.dxn[2][a] + y2[0][k]);
             }
         }
         const double h = c.len[2] / 2;
@@ -305,16 +317,27 @@ struct HybrdMem {
     double fjac[kNP * kNP];
     double r[kNP * (kNP + 1) / 2];
     double x[kNP], fvec[kNP], qtf[kNP], diag[kNP], wa1[kNP], wa2[kNP], wa3[kNP], wa4[kNP];
-    double scal[8];  // lane 0 -> warp broadcast slots
-    int iscal[4];
+    double ybuf[12][16];  // node integrands of one cooperative residual evaluation
+    StCfg cfg;
 };
 
-__device__ double st_enorm(int n, const double* x) {
-    // MINPACK enorm: scaled accumulation (the intermediate range is the only one reached here, but
-    // keep the three accumulators so that over/underflow behaves as in the reference)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+__device__ __noinline__ double st_enorm_full(int n, const double* x) {
+    // MINPACK enorm with its three scaled accumulators (only reached outside the intermediate range)
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
     const double agiant = rgiant / (double)n;
+#pragma unroll 1
     for (int i = 0; i < n; ++i) {
         const double xabs = fabs(x[i]);
         if (xabs > rdwarf && xabs < agiant) {
@@ -347,142 +370,205 @@ __device__ double st_enorm(int n, const double* x) {
     return x3max * sqrt(s3);
 }
 
-__device__ void st_dogleg(int n, const double* r, const double* diag, const double* qtb, double delta, double* x,
-                          double* wa1, double* wa2) {
+// MINPACK enorm of a length-n vector held one element per lane (v = 0 in lanes >= n).  In the
+// intermediate range the routine is sqrt(sum x^2); the warp tree-sum only changes the order of the adds.
+__device__ __forceinline__ double enorm_w(int n, double v, const double* x_smem_or_null) {
+    const double xabs = fabs(v);
+    const bool odd = (xabs >= 1.304e19 / (double)n) || (xabs <= 3.834e-20 && xabs != 0.0);
+    if (__any_sync(0xffffffffu, odd) && x_smem_or_null) return st_enorm_full(n, x_smem_or_null);
+    return sqrt(warp_sum(xabs * xabs));
+}
+
+__device__ __forceinline__ int rowoff(int n, int j) { return j * n - (j * (j - 1)) / 2; }  // packed upper-triangular rows
+
+// Cooperative residual: lanes 0..11 evaluate the 12 bracket-node integrands (3 sections x 2 abscissae x
+// {lo, hi}), lanes 0..n-1 then assemble one component each.  q and F are shared-memory vectors.
+__device__ __noinline__ void st_residual_w(const StModel& sm, HybrdMem& M, const double* q, double* F, int lane) {
+    const StCfg& c = M.cfg;
+    const int T = sm.mc.T;
+    double s31e = 0.0, c31e = 1.0, S31e[3] = {0.0, 0.0, 0.0};
+    if (T == 3) {
+        const double Xe = (c.L[0] - 1) * sm.mc.dx;
+        sincos_ni(c.th[2] + ipoly3(q + sm.qoff[2], Xe), &s31e, &c31e);
+        S31e[0] = Xe;
+        S31e[1] = 0.5 * Xe * Xe;
+        S31e[2] = Xe * Xe * Xe * (1.0 / 3.0);
+    }
+    if (lane < 12) {
+        const int sec = lane >> 2, a = (lane >> 1) & 1, e = lane & 1;
+        double* y = M.ybuf[lane];
+        if (c.len[sec] > 0.0 && (sec != 0 || T == 3)) {
+            const int node = e ? c.hi[sec][a] : c.lo[sec][a];
+            if (sec == 0) node_sec1(sm, c, q, node, y);
+            else if (sec == 1) node_sec2(sm, c, q, node, s31e, c31e, S31e, y);
+            else node_sec3(sm, c, q, node, y);
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < 16; ++k) y[k] = 0.0;
+        }
+    }
+    __syncwarp();
+    if (lane < sm.nq) {
+        // which block does component `lane` belong to?  order (1,1),(2,1),(3,1),(2,2),(3,2),(3,3)
+        int blk = 0;
+#pragma unroll
+        for (int b = 1; b < 6; ++b)
+            if (lane >= sm.qoff[b] && sm.ndof[b] > 0) blk = b;
+        const int k = lane - sm.qoff[blk];
+        // (section, offset inside the node vector) of that block; block 2 = intg_31 - intg_312
+        const int sec = blk < 3 ? 0 : (blk < 5 ? 1 : 2);
+        const int yo = (blk == 0 || blk == 3 || blk == 5) ? 0 : ((blk == 1 || blk == 4) ? 9 : 12);
+        double acc = 0.0;
+        if (c.len[sec] > 0.0) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const double ylo = M.ybuf[sec * 4 + a * 2 + 0][yo + k], yhi = M.ybuf[sec * 4 + a * 2 + 1][yo + k];
+                acc += 0.5 * (((yhi - ylo) / c.dxs[sec][a]) * c.dxn[sec][a] + ylo);
+            }
+        }
+        double val = (c.len[sec] / 2) * acc;
+        if (blk == 2) {  // minus the section-2 share (intg_312 lives at offset 12 of the section-2 vectors)
+            double acc2 = 0.0;
+            if (c.len[1] > 0.0) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const double ylo = M.ybuf[4 + a * 2 + 0][12 + k], yhi = M.ybuf[4 + a * 2 + 1][12 + k];
+                    acc2 += 0.5 * (((yhi - ylo) / c.dxs[1][a]) * c.dxn[1][a] + ylo);
+                }
+            }
+            val -= (c.len[1] / 2) * acc2;
+        }
+        F[lane] = val;
+    }
+    __syncwarp();
+}
+
+// dogleg (MINPACK): Gauss-Newton step by back substitution on the packed R, scaled gradient, and their
+// convex combination inside the trust region.  One vector element per lane; returns this lane's p.
+__device__ __noinline__ double dogleg_w(int n, const double* r, double diag_l, const double* qtb, double delta, double* tmp,
+                                        int lane) {
     const double epsmch = DBL_EPSILON;
-    int jj = (n * (n + 1)) / 2;
-    for (int k = 1; k <= n; ++k) {
-        const int j = n - k;
-        jj -= k;
-        int l = jj + 1;
-        double sum = 0;
-        for (int i = j + 1; i < n; ++i) {
-            sum += r[l] * x[i];
-            ++l;
+    double xg = 0.0;  // Gauss-Newton component of this lane
+#pragma unroll 1
+    for (int j = n - 1; j >= 0; --j) {
+        const int ro = rowoff(n, j);
+        const double term = (lane > j && lane < n) ? r[ro + lane - j] * xg : 0.0;
+        const double sum = warp_sum(term);
+        double temp = r[ro];
+        if (temp == 0.0) {
+            const double colv = (lane <= j) ? fabs(r[rowoff(n, lane) + j - lane]) : 0.0;
+            temp = epsmch * warp_max(colv);
+            if (temp == 0.0) temp = epsmch;
         }
-        double temp = r[jj];
-        if (temp == 0) {
-            l = j;
-            for (int i = 0; i <= j; ++i) {
-                temp = fmax(temp, fabs(r[l]));
-                l = l + n - i - 1;
-            }
-            temp = epsmch * temp;
-            if (temp == 0) temp = epsmch;
-        }
-        x[j] = (qtb[j] - sum) / temp;
+        const double xj = (qtb[j] - sum) / temp;
+        if (lane == j) xg = xj;
     }
-    for (int j = 0; j < n; ++j) {
-        wa1[j] = 0;
-        wa2[j] = diag[j] * x[j];
+    const bool act = lane < n;
+    const double qnorm = enorm_w(n, act ? diag_l * xg : 0.0, nullptr);
+    if (qnorm <= delta) return xg;
+    // scaled gradient direction: wa1_i = (sum_{j<=i} r(j,i) qtb_j) / diag_i
+    double g = 0.0;
+    if (act) {
+#pragma unroll 1
+        for (int j = 0; j <= lane; ++j) g += r[rowoff(n, j) + lane - j] * qtb[j];
+        g = g / diag_l;
     }
-    const double qnorm = st_enorm(n, wa2);
-    if (qnorm <= delta) return;
-    int l = 0;
-    for (int j = 0; j < n; ++j) {
-        const double temp = qtb[j];
-        for (int i = j; i < n; ++i) {
-            wa1[i] += r[l] * temp;
-            ++l;
+    const double gnorm = enorm_w(n, g, nullptr);
+    double sgnorm = 0.0, alpha = delta / qnorm;
+    if (gnorm != 0.0) {
+        g = act ? (g / gnorm) / diag_l : 0.0;
+        if (act) tmp[lane] = g;
+        __syncwarp();
+        double w2 = 0.0;
+        if (act) {
+            const int ro = rowoff(n, lane);
+#pragma unroll 1
+            for (int i = lane; i < n; ++i) w2 += r[ro + i - lane] * tmp[i];
         }
-        wa1[j] = wa1[j] / diag[j];
-    }
-    const double gnorm = st_enorm(n, wa1);
-    double sgnorm = 0, alpha = delta / qnorm;
-    if (gnorm != 0) {
-        for (int j = 0; j < n; ++j) wa1[j] = (wa1[j] / gnorm) / diag[j];
-        l = 0;
-        for (int j = 0; j < n; ++j) {
-            double sum = 0;
-            for (int i = j; i < n; ++i) {
-                sum += r[l] * wa1[i];
-                ++l;
-            }
-            wa2[j] = sum;
-        }
-        double temp = st_enorm(n, wa2);
+        double temp = enorm_w(n, w2, nullptr);
         sgnorm = (gnorm / temp) / temp;
-        alpha = 0;
+        alpha = 0.0;
         if (sgnorm < delta) {
-            const double bnorm = st_enorm(n, qtb);
+            const double bnorm = enorm_w(n, act ? qtb[lane] : 0.0, nullptr);
             temp = (bnorm / gnorm) * (bnorm / qnorm) * (sgnorm / delta);
             const double dq = delta / qnorm, sd = sgnorm / delta;
             temp = temp - dq * sd * sd + sqrt((temp - dq) * (temp - dq) + (1 - dq * dq) * (1 - sd * sd));
             alpha = (dq * (1 - sd * sd)) / temp;
         }
+        __syncwarp();
     }
     const double temp = (1 - alpha) * fmin(sgnorm, delta);
-    for (int j = 0; j < n; ++j) x[j] = temp * wa1[j] + alpha * x[j];
+    return temp * g + alpha * xg;
 }
 
-__device__ void st_r1updt(int n, double* s, const double* u, double* v, double* w, int* sing) {
-    const double giant = DBL_MAX;
-    const int m = n;
-    int jj = (n * (2 * m - n + 1)) / 2 - (m - n) - 1;
-    w[n - 1] = s[jj];
+__device__ __forceinline__ void givens(double a, double b, double* c_, double* s_, double* tau) {
+    // the rotation MINPACK builds to annihilate b against a (r1updt): returns cos, sin and the stored tau
+    if (fabs(a) < fabs(b)) {
+        const double cotan = a / b;
+        *s_ = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
+        *c_ = *s_ * cotan;
+        *tau = 1;
+        if (fabs(*c_) * DBL_MAX > 1) *tau = 1 / *c_;
+    } else {
+        const double tn = b / a;
+        *c_ = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
+        *s_ = *c_ * tn;
+        *tau = *s_;
+    }
+}
+
+// r1updt: QR factors of R + u v^T.  Lane i owns w_i and element i of every packed row segment.
+// On return v (smem) and w (smem) hold the rotations for r1mpyq.
+__device__ __noinline__ void r1updt_w(int n, double* s, double u_l, double* v, double* w, int lane) {
+    double wl = 0.0;
+    if (lane == n - 1) wl = s[rowoff(n, n - 1)];
+    double vn = v[n - 1];
+#pragma unroll 1
     for (int j = n - 2; j >= 0; --j) {
-        jj -= (m - j);
-        w[j] = 0;
-        if (v[j] != 0) {
+        if (lane == j) wl = 0.0;
+        const double vj = v[j];
+        __syncwarp();
+        if (vj != 0.0) {
             double c_, s_, tau;
-            if (fabs(v[n - 1]) < fabs(v[j])) {
-                const double cotan = v[n - 1] / v[j];
-                s_ = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
-                c_ = s_ * cotan;
-                tau = 1;
-                if (fabs(c_) * giant > 1) tau = 1 / c_;
-            } else {
-                const double tn = v[j] / v[n - 1];
-                c_ = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
-                s_ = c_ * tn;
-                tau = s_;
-            }
-            v[n - 1] = s_ * v[j] + c_ * v[n - 1];
-            v[j] = tau;
-            int l = jj;
-            for (int i = j; i < m; ++i) {
-                const double temp = c_ * s[l] - s_ * w[i];
-                w[i] = s_ * s[l] + c_ * w[i];
-                s[l] = temp;
-                ++l;
+            givens(vn, vj, &c_, &s_, &tau);
+            vn = s_ * vj + c_ * vn;
+            if (lane == 0) v[j] = tau;
+            if (lane >= j && lane < n) {
+                const int l = rowoff(n, j) + lane - j;
+                const double sl = s[l];
+                s[l] = c_ * sl - s_ * wl;
+                wl = s_ * sl + c_ * wl;
             }
         }
     }
-    for (int i = 0; i < m; ++i) w[i] += v[n - 1] * u[i];
-    *sing = 0;
+    if (lane == 0) v[n - 1] = vn;
+    if (lane < n) wl += vn * u_l;
+#pragma unroll 1
     for (int j = 0; j < n - 1; ++j) {
-        if (w[j] != 0) {
+        const double wj = __shfl_sync(0xffffffffu, wl, j);
+        if (wj != 0.0) {
+            const int ro = rowoff(n, j);
             double c_, s_, tau;
-            if (fabs(s[jj]) < fabs(w[j])) {
-                const double cotan = s[jj] / w[j];
-                s_ = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
-                c_ = s_ * cotan;
-                tau = 1;
-                if (fabs(c_) * giant > 1) tau = 1 / c_;
-            } else {
-                const double tn = w[j] / s[jj];
-                c_ = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
-                s_ = c_ * tn;
-                tau = s_;
+            givens(s[ro], wj, &c_, &s_, &tau);
+            __syncwarp();
+            if (lane >= j && lane < n) {
+                const int l = ro + lane - j;
+                const double sl = s[l];
+                s[l] = c_ * sl + s_ * wl;
+                wl = -s_ * sl + c_ * wl;
             }
-            int l = jj;
-            for (int i = j; i < m; ++i) {
-                const double temp = c_ * s[l] + s_ * w[i];
-                w[i] = -s_ * s[l] + c_ * w[i];
-                s[l] = temp;
-                ++l;
-            }
-            w[j] = tau;
+            if (lane == j) wl = tau;
+            __syncwarp();
         }
-        if (s[jj] == 0) *sing = 1;
-        jj += (m - j);
     }
-    s[jj] = w[n - 1];
-    if (s[jj] == 0) *sing = 1;
+    if (lane == n - 1) s[rowoff(n, n - 1)] = wl;
+    if (lane < n) w[lane] = wl;
+    __syncwarp();
 }
 
-// apply the 2(n-1) Givens rotations stored in v, w to ONE row a[0..n-1] with stride lda (r1mpyq)
-__device__ void st_r1mpyq_row(int n, double* a, int lda, const double* v, const double* w) {
+// apply the 2(n-1) stored rotations to ONE row a[0..n-1] with stride lda (r1mpyq, one row per lane)
+__device__ __noinline__ void st_r1mpyq_row(int n, double* a, int lda, const double* v, const double* w) {
+#pragma unroll 1
     for (int j = n - 2; j >= 0; --j) {
         double c_, s_;
         if (fabs(v[j]) > 1) {
@@ -496,6 +582,7 @@ __device__ void st_r1mpyq_row(int n, double* a, int lda, const double* v, const 
         a[(n - 1) * lda] = s_ * a[j * lda] + c_ * a[(n - 1) * lda];
         a[j * lda] = temp;
     }
+#pragma unroll 1
     for (int j = 0; j < n - 1; ++j) {
         double c_, s_;
         if (fabs(w[j]) > 1) {
@@ -511,223 +598,201 @@ __device__ void st_r1mpyq_row(int n, double* a, int lda, const double* v, const 
     }
 }
 
-// returns info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress); *nfev_out = evaluations
-__device__ int st_hybrd(const StModel& sm, const StCfg& c, HybrdMem& M, int lane, double xtol, int maxfev, double factor,
-                        int* nfev_out) {
+// MINPACK hybrd, warp-cooperative.  Every scalar of the iteration (delta, norms, counters, ratio) is
+// computed redundantly and identically by all lanes; vectors are one element per lane.
+// returns info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress)
+__device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, int lane, double xtol, int maxfev, double factor,
+                                     int* nfev_out) {
     const int n = sm.nq;
+    const bool act = lane < n;
     const double epsmch = DBL_EPSILON, p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double* fjac = M.fjac;
     int info = 0, nfev;
-    if (lane == 0) {
-        st_residual(sm, c, M.x, M.fvec);
-        M.scal[0] = st_enorm(n, M.fvec);
-    }
-    __syncwarp();
+    st_residual_w(sm, M, M.x, M.fvec, lane);
     nfev = 1;
-    double fnorm = M.scal[0];
+    double fnorm = enorm_w(n, act ? M.fvec[lane] : 0.0, M.fvec);
     int iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
     double delta = 0, xnorm = 0;
+    double diag_l = 1.0;
+#pragma unroll 1
     for (;;) {  // outer loop: fresh forward-difference Jacobian
         bool jeval = true;
         // fdjac1 (dense): lane j evaluates the residual at x + h e_j and fills column j
-        if (lane < n) {
+        if (act) {
             double xp[kMaxNq], Fp[kMaxNq];
+#pragma unroll 1
             for (int k = 0; k < n; ++k) xp[k] = M.x[k];
             const double eps = sqrt(epsmch);
             const double temp = xp[lane];
             double h = eps * fabs(temp);
             if (h == 0) h = eps;
             xp[lane] = temp + h;
-            st_residual(sm, c, xp, Fp);
+            st_residual(sm, M.cfg, xp, Fp);
+#pragma unroll 1
             for (int i = 0; i < n; ++i) fjac[i + lane * kNP] = (Fp[i] - M.fvec[i]) / h;
         }
         nfev += n;
         __syncwarp();
-        // qrfac: Householder QR without pivoting; lane k owns column k
-        if (lane < n) {
-            const double an = st_enorm(n, fjac + lane * kNP);
-            M.wa2[lane] = an;  // acnorm
-            M.wa1[lane] = an;  // rdiag (overwritten below)
+        // qrfac: Householder QR without pivoting; lane k owns column k.  acnorm -> wa2, rdiag -> wa1
+        double acnorm_l = 0.0;
+        if (act) {
+            double s2 = 0.0;
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) s2 += fjac[i + lane * kNP] * fjac[i + lane * kNP];
+            acnorm_l = sqrt(s2);
         }
-        __syncwarp();
+#pragma unroll 1
         for (int j = 0; j < n; ++j) {
-            double ajnorm = st_enorm(n - j, fjac + j + j * kNP);  // every lane computes the same value
+            double ajnorm = enorm_w(n, (lane >= j && act) ? fjac[lane + j * kNP] : 0.0, nullptr);  // lane = row
             if (ajnorm != 0) {
                 if (fjac[j + j * kNP] < 0) ajnorm = -ajnorm;
                 __syncwarp();
-                if (lane >= j && lane < n) fjac[lane + j * kNP] /= ajnorm;  // lane = row here
+                if (lane >= j && act) fjac[lane + j * kNP] /= ajnorm;
                 __syncwarp();
                 if (lane == 0) fjac[j + j * kNP] += 1;
                 __syncwarp();
-                if (lane > j && lane < n) {  // lane = column k
+                if (lane > j && act) {  // lane = column k
                     double sum = 0;
+#pragma unroll 1
                     for (int i = j; i < n; ++i) sum += fjac[i + j * kNP] * fjac[i + lane * kNP];
                     const double temp = sum / fjac[j + j * kNP];
+#pragma unroll 1
                     for (int i = j; i < n; ++i) fjac[i + lane * kNP] -= temp * fjac[i + j * kNP];
                 }
             }
             if (lane == 0) M.wa1[j] = -ajnorm;
             __syncwarp();
         }
-        if (lane == 0) {
-            if (iter == 1) {
-                for (int j = 0; j < n; ++j) {
-                    M.diag[j] = M.wa2[j];
-                    if (M.wa2[j] == 0) M.diag[j] = 1;
-                }
-                for (int j = 0; j < n; ++j) M.wa3[j] = M.diag[j] * M.x[j];
-                xnorm = st_enorm(n, M.wa3);
-                delta = factor * xnorm;
-                if (delta == 0) delta = factor;
+        if (iter == 1) {
+            diag_l = acnorm_l == 0 ? 1.0 : acnorm_l;
+            xnorm = enorm_w(n, act ? diag_l * M.x[lane] : 0.0, nullptr);
+            delta = factor * xnorm;
+            if (delta == 0) delta = factor;
+        }
+        // qtf = Q^T fvec through the stored Householder vectors
+        double qtf_l = act ? M.fvec[lane] : 0.0;
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const double fjj = fjac[j + j * kNP];
+            if (fjj != 0) {
+                const double fij = (lane >= j && act) ? fjac[lane + j * kNP] : 0.0;
+                const double sum = warp_sum(fij * qtf_l);
+                qtf_l += fij * (-sum / fjj);
             }
-            for (int i = 0; i < n; ++i) M.qtf[i] = M.fvec[i];
-            for (int j = 0; j < n; ++j) {
-                if (fjac[j + j * kNP] != 0) {
-                    double sum = 0;
-                    for (int i = j; i < n; ++i) sum += fjac[i + j * kNP] * M.qtf[i];
-                    const double temp = -sum / fjac[j + j * kNP];
-                    for (int i = j; i < n; ++i) M.qtf[i] += fjac[i + j * kNP] * temp;
-                }
-            }
-            for (int j = 0; j < n; ++j) {
-                int l = j;
-                for (int i = 0; i < j; ++i) {
-                    M.r[l] = fjac[i + j * kNP];
-                    l = l + n - i - 1;
-                }
-                M.r[l] = M.wa1[j];
-            }
-            M.scal[1] = xnorm;
-            M.scal[2] = delta;
+        }
+        if (act) {
+            M.qtf[lane] = qtf_l;
+            // copy R: strict upper part of column `lane` from fjac, diagonal from rdiag
+#pragma unroll 1
+            for (int i = 0; i < lane; ++i) M.r[rowoff(n, i) + lane - i] = fjac[i + lane * kNP];
+            M.r[rowoff(n, lane)] = M.wa1[lane];
         }
         __syncwarp();
-        xnorm = M.scal[1];
-        delta = M.scal[2];
-        // qform: accumulate Q in fjac; lane = column j of the trailing update
+        // qform: accumulate Q in fjac; lane = column of the trailing update
+#pragma unroll 1
         for (int j = 1; j < n; ++j)
             if (lane < j) fjac[lane + j * kNP] = 0;
         __syncwarp();
+#pragma unroll 1
         for (int l = 0; l < n; ++l) {
             const int k = n - l - 1;
-            if (lane >= k && lane < n) M.wa3[lane] = fjac[lane + k * kNP];  // wa(i) = q(i,k)
+            if (lane >= k && act) M.wa3[lane] = fjac[lane + k * kNP];
             __syncwarp();
-            if (lane >= k && lane < n) fjac[lane + k * kNP] = (lane == k) ? 1.0 : 0.0;
+            if (lane >= k && act) fjac[lane + k * kNP] = (lane == k) ? 1.0 : 0.0;
             __syncwarp();
             if (M.wa3[k] != 0) {
-                if (lane >= k && lane < n) {  // lane = column j
+                if (lane >= k && act) {
                     double sum = 0;
+#pragma unroll 1
                     for (int i = k; i < n; ++i) sum += fjac[i + lane * kNP] * M.wa3[i];
                     const double temp = sum / M.wa3[k];
+#pragma unroll 1
                     for (int i = k; i < n; ++i) fjac[i + lane * kNP] -= temp * M.wa3[i];
                 }
             }
             __syncwarp();
         }
-        if (lane < n) M.diag[lane] = fmax(M.diag[lane], M.wa2[lane]);
-        __syncwarp();
+        diag_l = fmax(diag_l, acnorm_l);
+#pragma unroll 1
         for (;;) {  // inner loop
-            double pnorm = 0, fnorm1 = 0, actred, prered, ratio;
-            if (lane == 0) {
-                st_dogleg(n, M.r, M.diag, M.qtf, delta, M.wa1, M.wa2, M.wa3);
-                for (int j = 0; j < n; ++j) {
-                    M.wa1[j] = -M.wa1[j];
-                    M.wa2[j] = M.x[j] + M.wa1[j];
-                    M.wa3[j] = M.diag[j] * M.wa1[j];
+            // direction p (this lane's component), trial point, scaled step
+            double p_l = -dogleg_w(n, M.r, diag_l, M.qtf, delta, M.wa3, lane);
+            if (!act) p_l = 0.0;
+            if (act) {
+                M.wa1[lane] = p_l;
+                M.wa2[lane] = M.x[lane] + p_l;
+            }
+            const double pnorm = enorm_w(n, diag_l * p_l, nullptr);
+            if (iter == 1) delta = fmin(delta, pnorm);
+            __syncwarp();
+            st_residual_w(sm, M, M.wa2, M.wa4, lane);
+            nfev++;
+            const double fnorm1 = enorm_w(n, act ? M.wa4[lane] : 0.0, M.wa4);
+            double actred = -1;
+            if (fnorm1 < fnorm) actred = 1 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+            // predicted reduction: || qtf + R p ||
+            double w3 = 0.0;
+            if (act) {
+                const int ro = rowoff(n, lane);
+                double sum = 0;
+#pragma unroll 1
+                for (int j = lane; j < n; ++j) sum += M.r[ro + j - lane] * M.wa1[j];
+                w3 = M.qtf[lane] + sum;
+            }
+            const double temp = enorm_w(n, w3, nullptr);
+            double prered = 0;
+            if (temp < fnorm) prered = 1 - (temp / fnorm) * (temp / fnorm);
+            double ratio = 0;
+            if (prered > 0) ratio = actred / prered;
+            if (ratio < p1) {
+                ncsuc = 0;
+                ncfail++;
+                delta = p5 * delta;
+            } else {
+                ncfail = 0;
+                ncsuc++;
+                if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
+                if (fabs(ratio - 1) <= p1) delta = pnorm / p5;
+            }
+            if (ratio >= p0001) {  // successful iteration
+                if (act) {
+                    M.x[lane] = M.wa2[lane];
+                    M.fvec[lane] = M.wa4[lane];
                 }
-                pnorm = st_enorm(n, M.wa3);
-                if (iter == 1) delta = fmin(delta, pnorm);
-                st_residual(sm, c, M.wa2, M.wa4);
-                fnorm1 = st_enorm(n, M.wa4);
-                actred = -1;
-                if (fnorm1 < fnorm) actred = 1 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
-                int l = 0;
-                for (int i = 0; i < n; ++i) {
-                    double sum = 0;
-                    for (int j = i; j < n; ++j) {
-                        sum += M.r[l] * M.wa1[j];
-                        ++l;
-                    }
-                    M.wa3[i] = M.qtf[i] + sum;
-                }
-                const double temp = st_enorm(n, M.wa3);
-                prered = 0;
-                if (temp < fnorm) prered = 1 - (temp / fnorm) * (temp / fnorm);
-                ratio = 0;
-                if (prered > 0) ratio = actred / prered;
-                if (ratio < p1) {
-                    ncsuc = 0;
-                    ncfail++;
-                    delta = p5 * delta;
-                } else {
-                    ncfail = 0;
-                    ncsuc++;
-                    if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
-                    if (fabs(ratio - 1) <= p1) delta = pnorm / p5;
-                }
-                if (ratio >= p0001) {
-                    for (int j = 0; j < n; ++j) {
-                        M.x[j] = M.wa2[j];
-                        M.wa2[j] = M.diag[j] * M.x[j];
-                        M.fvec[j] = M.wa4[j];
-                    }
-                    xnorm = st_enorm(n, M.wa2);
-                    fnorm = fnorm1;
-                    iter++;
-                }
-                nslow1++;
-                if (actred >= p001) nslow1 = 0;
-                if (jeval) nslow2++;
-                if (actred >= p1) nslow2 = 0;
-                int inf = 0;
-                if (delta <= xtol * xnorm || fnorm == 0) inf = 1;
-                if (inf == 0) {
-                    if (nfev + 1 >= maxfev) inf = 2;
-                    if (p1 * fmax(p1 * delta, pnorm) <= epsmch * xnorm) inf = 3;
-                    if (nslow2 == 5) inf = 4;
-                    if (nslow1 == 10) inf = 5;
-                }
-                M.scal[0] = fnorm;
-                M.scal[1] = xnorm;
-                M.scal[2] = delta;
-                M.scal[3] = pnorm;
-                M.scal[4] = ratio;
-                M.iscal[0] = inf;
-                M.iscal[1] = ncfail;
-                M.iscal[2] = iter;
+                xnorm = enorm_w(n, act ? diag_l * M.wa2[lane] : 0.0, nullptr);
+                fnorm = fnorm1;
+                iter++;
+            }
+            nslow1++;
+            if (actred >= p001) nslow1 = 0;
+            if (jeval) nslow2++;
+            if (actred >= p1) nslow2 = 0;
+            if (delta <= xtol * xnorm || fnorm == 0) info = 1;
+            if (info == 0) {
+                if (nfev >= maxfev) info = 2;
+                if (p1 * fmax(p1 * delta, pnorm) <= epsmch * xnorm) info = 3;
+                if (nslow2 == 5) info = 4;
+                if (nslow1 == 10) info = 5;
             }
             __syncwarp();
-            nfev++;
-            fnorm = M.scal[0];
-            xnorm = M.scal[1];
-            delta = M.scal[2];
-            pnorm = M.scal[3];
-            ratio = M.scal[4];
-            info = M.iscal[0];
-            ncfail = M.iscal[1];
-            iter = M.iscal[2];
             if (info != 0) {
                 *nfev_out = nfev;
                 return info;
             }
             if (ncfail == 2) break;  // recompute the Jacobian
-            // rank-one (Broyden) update: lane j forms its entries, lane 0 runs r1updt, lanes apply the
-            // rotations to their row of Q and lane 0 to qtf
-            if (lane < n) {
+            // rank-one (Broyden) update of R, Q and qtf
+            double u_l = 0.0;
+            if (act) {
                 double sum = 0;
+#pragma unroll 1
                 for (int i = 0; i < n; ++i) sum += fjac[i + lane * kNP] * M.wa4[i];
-                const double w2 = (sum - M.wa3[lane]) / pnorm;
-                const double w1 = M.diag[lane] * ((M.diag[lane] * M.wa1[lane]) / pnorm);
-                M.wa2[lane] = w2;
-                M.wa1[lane] = w1;
+                M.wa2[lane] = (sum - w3) / pnorm;                 // v
+                u_l = diag_l * ((diag_l * p_l) / pnorm);          // u
                 if (ratio >= p0001) M.qtf[lane] = sum;
             }
             __syncwarp();
-            if (lane == 0) {
-                int sing;
-                st_r1updt(n, M.r, M.wa1, M.wa2, M.wa3, &sing);
-            }
-            __syncwarp();
-            if (lane < n) st_r1mpyq_row(n, fjac + lane, kNP, M.wa2, M.wa3);
+            r1updt_w(n, M.r, u_l, M.wa2, M.wa3, lane);
+            if (act) st_r1mpyq_row(n, fjac + lane, kNP, M.wa2, M.wa3);
             if (lane == 31) st_r1mpyq_row(n, M.qtf, 1, M.wa2, M.wa3);
             __syncwarp();
             jeval = false;
@@ -741,7 +806,7 @@ __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_
 
 // half_step_integral for a tube==section basis (with bias): the Magnus exponential of one step.
 // wA, wB = omega at the two Gauss points; v = e_x at both.
-__device__ __forceinline__ SE3 magnus_step(const double wA[3], const double wB[3], double dx) {
+__device__ __noinline__ SE3 magnus_step(const double wA[3], const double wB[3], double dx) {
     const double cf = (sqrt(3.0) * dx * dx) / 12;
     // Gamma = dx/2 (xi1^ + xi2^) + cf [xi2^, xi1^];  [.,.] = (w2 x w1, w2 x v1 - w1 x v2), v1 = v2 = e_x
     V3 a = {wA[0], wA[1], wA[2]}, b = {wB[0], wB[1], wB[2]};
@@ -754,7 +819,7 @@ __device__ __forceinline__ SE3 magnus_step(const double wA[3], const double wB[3
 }
 
 // omega of the (tube==section) basis at absolute section coordinate `sidx` (static_bases.py:61-81)
-__device__ __forceinline__ void sect_omega(const StModel& sm, const StCfg& c, const double* qs, int sect, double sidx,
+__device__ __noinline__ void sect_omega(const StModel& sm, const StCfg& c, const double* qs, int sect, double sidx,
                                            double w[3]) {
     const double dx = sm.mc.dx;
     if (sect == 3) {
@@ -776,7 +841,7 @@ __device__ __forceinline__ void sect_omega(const StModel& sm, const StCfg& c, co
 
 // Writes `count` nodes of one section curve: node 0 = g0, node k = g0 * E_1 ... E_k with
 // E_k the Magnus step at absolute index start + k.  Returns the last node (all lanes).
-__device__ SE3 integrate_section(const StModel& sm, const StCfg& c, const double* qs, int sect, int start, int count,
+__device__ __noinline__ SE3 integrate_section(const StModel& sm, const StCfg& c, const double* qs, int sect, int start, int count,
                                  SE3 g0, double* out, int lane) {
     const double dx = sm.mc.dx;
     const double cg1 = 0.5 - sqrt(3.0) / 6, cg2 = 0.5 + sqrt(3.0) / 6;  // static.py:597-599
@@ -837,7 +902,7 @@ __device__ __forceinline__ SE3 se3_rx(double angle) {
     SE3 g;
     se3_identity(g);
     double s, c;
-    sincos(angle, &s, &c);
+    sincos_ni(angle, &s, &c);
     g.r[4] = c; g.r[5] = -s; g.r[7] = s; g.r[8] = c;
     return g;
 }
@@ -856,12 +921,12 @@ __global__ void __launch_bounds__(kSWarps * 32)
     HybrdMem& M = reinterpret_cast<HybrdMem*>(smem_raw)[warp];
     const int T = sm.mc.T, n = sm.nq;
     for (long long b = (long long)blockIdx.x * kSWarps + warp; b < B; b += (long long)gridDim.x * kSWarps) {
-        StCfg c;
-        st_setup(sm, idx + b * T, theta + b * T, c);
+        if (lane == 0) st_setup(sm, idx + b * T, theta + b * T, M.cfg);
         if (lane < n) M.x[lane] = x0 ? x0[(x0_per_config ? b * n : 0) + lane] : sm.x0[lane];
         __syncwarp();
+        const StCfg& c = M.cfg;
         int nfev = 0;
-        const int info = st_hybrd(sm, c, M, lane, xtol, 200 * (n + 1), 100.0, &nfev);
+        const int info = st_hybrd(sm, M, lane, xtol, 200 * (n + 1), 100.0, &nfev);
         __syncwarp();
         if (sol_out && lane < n) sol_out[b * n + lane] = M.x[lane];
         if (lane == 0) {
@@ -958,9 +1023,12 @@ int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int
     CTRB_CUDA(cudaFuncSetAttribute(static_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks_needed = (B + kSWarps - 1) / kSWarps;
     int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * 4);
-    static_solve_kernel<<<grid, kSWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config,
-                                                                  xtol > 0 ? xtol : 1.49012e-8, offsets, g_out, sol_out,
-                                                                  nfev_out, info_out);
+    {
+        KernelTimer kt(ctx, CTRB_KERNEL_STATIC_SOLVE);
+        static_solve_kernel<<<grid, kSWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config,
+                                                                      xtol > 0 ? xtol : 1.49012e-8, offsets, g_out, sol_out,
+                                                                      nfev_out, info_out);
+    }
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());
     return CTRB_OK;

@@ -134,6 +134,16 @@ int64_t ctrb_ctx_launch_count(const ctrb_ctx* ctx);
 int ctrb_ctx_mark(ctrb_ctx* ctx, int which /*0 = start, 1 = stop*/);
 int ctrb_ctx_elapsed_ms(ctrb_ctx* ctx, float* ms);
 
+/* Device duration of the most recent launch of one hot kernel on this ctx (CUDA events recorded
+ * on the launching stream around that launch; synchronises on the stop event). */
+typedef enum {
+    CTRB_KERNEL_CHAIN_EVAL = 0,   /* chain_eval_kernel (fused or given curves) */
+    CTRB_KERNEL_STATIC_SOLVE = 1, /* static_solve_kernel */
+    CTRB_KERNEL_GCURVE = 2,       /* kin_gcurve_kernel */
+    CTRB_KERNEL_ETA_FTL = 3       /* kin_eta_ftl_kernel */
+} ctrb_kernel_id;
+int ctrb_ctx_last_kernel_ms(ctrb_ctx* ctx, int kernel_id, float* ms);
+
 /* Measured CUDA-core FMA peak of this device (dependent-free FMA chains on every SM), the
  * denominator of the compute roofline of the collision kernel: precision CTRB_F32 / CTRB_F64. */
 int ctrb_measure_fma_peak(ctrb_ctx* ctx, int precision, double* tflops);

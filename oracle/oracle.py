@@ -339,6 +339,19 @@ class Env:
         return obs, goal, cost
 
 
+def static_eval_batch(env, s, idx, theta, rad, goal_weight, nthreads=None):
+    """Static.solve_g -> check_collision -> own cost for a batch (pthreads)."""
+    idx = np.ascontiguousarray(idx, np.int32)
+    theta = _f64(theta)
+    B = idx.shape[0]
+    obs, goal, cost = np.zeros(B), np.zeros(B), np.zeros(B)
+    info, nfev = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    lib().orc_static_eval_batch(C.byref(s), C.c_void_p(env._h), B, _ip(idx), _dp(theta), _dp(_f64(rad)),
+                                C.c_double(goal_weight), _dp(obs), _dp(goal), _dp(cost), _ip(info), _ip(nfev),
+                                nthreads or len(os.sched_getaffinity(0)))
+    return obs, goal, cost, info, nfev
+
+
 def solve_g_tips_batch(m, idx, theta, nthreads=None):
     idx = np.ascontiguousarray(idx, np.int32)
     theta = _f64(theta)

@@ -1,0 +1,20 @@
+"""Small static-solve run for ncu: C3 shallow, B configs, device-side only."""
+import pathlib
+import sys
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / "ctr-design-and-path-plan_b200"), str(ROOT / "tests")]
+from util import gpu_static  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 30000
+m = gpu_static("c3_three_tube")
+N = np.asarray(m.num_discrete_points)
+rng = np.random.default_rng(1003)
+e = np.stack([rng.integers(1, 9, B) for t in range(3)], 1)
+idx = (N[None, :] - 1 - e).astype(np.int32)
+th = rng.uniform(0, 2 * np.pi, (B, 3))
+for _ in range(2):
+    res = m.solve_g_batch(idx, th, want_g=True)
+print("converged", res["converged"].mean(), "nfev", res["nfev"].mean(), "ms", m.ctx.last_kernel_ms("static_solve"))
