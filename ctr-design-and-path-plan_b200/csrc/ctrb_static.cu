@@ -77,8 +77,8 @@ __device__ __noinline__ void strain_base_rows(int kind, int dof, double x, doubl
             if (dof > 2) B[1][1] = x * x;
             B[2][dof - 1] = x * x;
             break;
-        case CTRB_BASE_PURE_HELIX: B[1][0] = sin(x / 10); B[2][1] = cos(x / 10); break;
-        case CTRB_BASE_LINEAR_HELIX: B[1][0] = sin(x / 10); B[2][1] = x * cos(x / 10); break;
+        case CTRB_BASE_PURE_HELIX: { double sn, cs; sincos_ni(x / 10, &sn, &cs); B[1][0] = sn; B[2][1] = cs; break; }
+        case CTRB_BASE_LINEAR_HELIX: { double sn, cs; sincos_ni(x / 10, &sn, &cs); B[1][0] = sn; B[2][1] = x * cs; break; }
         case CTRB_BASE_TORSION_HELIX: B[0][0] = 1.0; B[1][1] = 1.0; B[2][2] = 1.0; break;
         case CTRB_BASE_TORSION_LINEAR_HELIX: B[0][0] = 1.0; B[1][1] = 1.0; B[2][2] = x; break;
         case CTRB_BASE_FULL: {
@@ -321,7 +321,7 @@ struct HybrdMem {
     StCfg cfg;
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
+__device__ __noinline__ double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
@@ -372,7 +372,7 @@ __device__ __noinline__ double st_enorm_full(int n, const double* x) {
 
 // MINPACK enorm of a length-n vector held one element per lane (v = 0 in lanes >= n).  In the
 // intermediate range the routine is sqrt(sum x^2); the warp tree-sum only changes the order of the adds.
-__device__ __forceinline__ double enorm_w(int n, double v, const double* x_smem_or_null) {
+__device__ __noinline__ double enorm_w(int n, double v, const double* x_smem_or_null) {
     const double xabs = fabs(v);
     const bool odd = (xabs >= 1.304e19 / (double)n) || (xabs <= 3.834e-20 && xabs != 0.0);
     if (__any_sync(0xffffffffu, odd) && x_smem_or_null) return st_enorm_full(n, x_smem_or_null);
@@ -915,12 +915,17 @@ __global__ void __launch_bounds__(kSWarps * 32)
     static_solve_kernel(StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
                         const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                         double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
-                        int32_t* __restrict__ info_out) {
+                        int32_t* __restrict__ info_out, unsigned long long* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     HybrdMem& M = reinterpret_cast<HybrdMem*>(smem_raw)[warp];
     const int T = sm.mc.T, n = sm.nq;
-    for (long long b = (long long)blockIdx.x * kSWarps + warp; b < B; b += (long long)gridDim.x * kSWarps) {
+    for (;;) {
+        // dynamic schedule: the evaluation count varies from ~30 to 200(n+1) between configurations
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1ULL);
+        const long long b = (long long)__shfl_sync(0xffffffffu, tk, 0);
+        if (b >= B) break;
         if (lane == 0) st_setup(sm, idx + b * T, theta + b * T, M.cfg);
         if (lane < n) M.x[lane] = x0 ? x0[(x0_per_config ? b * n : 0) + lane] : sm.x0[lane];
         __syncwarp();
@@ -1022,12 +1027,15 @@ int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int
     const size_t smem = sizeof(HybrdMem) * kSWarps;
     CTRB_CUDA(cudaFuncSetAttribute(static_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks_needed = (B + kSWarps - 1) / kSWarps;
-    int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * 4);
+    int per_sm = 1;
+    CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, static_solve_kernel, kSWarps * 32, smem));
+    int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * std::max(per_sm, 1));
+    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 5, 0, sizeof(unsigned long long), ctx->stream));
     {
         KernelTimer kt(ctx, CTRB_KERNEL_STATIC_SOLVE);
         static_solve_kernel<<<grid, kSWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config,
                                                                       xtol > 0 ? xtol : 1.49012e-8, offsets, g_out, sol_out,
-                                                                      nfev_out, info_out);
+                                                                      nfev_out, info_out, ctx->d_counters + 5);
     }
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());
