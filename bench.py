@@ -175,6 +175,7 @@ def main():
     import torch.distributed as dist
     import ctypes as C
     from ctrdapp_b200 import _lib as L
+    from ctrdapp_b200 import dist as cdist
     from ctrdapp_b200.collision import CollisionChecker
     from ctrdapp_b200.model.kinematic import Kinematic
 
@@ -207,7 +208,6 @@ def main():
     coll_d = torch.empty(B, dtype=torch.uint8, device=dev)
     rad = np.ascontiguousarray(RAD, np.float64)
     cd = L.CostDesc(L.COST_TYPES["square_obstacle_avg_plus_weighted_goal"], GOAL_WEIGHT, 1, 0.0)
-    gathered = torch.empty(world * 2, dtype=torch.float64, device=dev) if world > 1 else None
     lib = L.lib()
 
     info_d = torch.empty(B, dtype=torch.int32, device=dev)
@@ -234,13 +234,8 @@ def main():
         best_cost, best_index = C.c_double(), C.c_int64()
         L.check(lib.ctrb_argmin_cost(ctx.handle, B, L.ptr(cost_d), rank * B, C.byref(best_cost), C.byref(best_index),
                                      L.MEM_DEVICE))
-        if world > 1:  # gather every rank's best node; the payload is 16 B per rank
-            mine = torch.tensor([best_cost.value, float(best_index.value)], dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(gathered, mine)
-            g = gathered.view(world, 2).cpu().numpy()
-            k = int(np.argmin(g[:, 0]))
-            return float(g[k, 0]), int(g[k, 1])
-        return best_cost.value, best_index.value
+        # every rank's best node is gathered over NCCL; the payload is 16 B per rank
+        return cdist.gather_best(best_cost.value, best_index.value, device=dev)
 
     def barrier():
         if world > 1:
@@ -263,9 +258,7 @@ def main():
         best_cost, best_index = C.c_double(), C.c_int64()
         L.check(lib.ctrb_argmin_cost(ctx.handle, B, L.ptr(cost_d), rank * B, C.byref(best_cost), C.byref(best_index),
                                      L.MEM_DEVICE))
-        if world > 1:
-            mine = torch.tensor([best_cost.value, float(best_index.value)], dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(gathered, mine)
+        cdist.gather_best(best_cost.value, best_index.value, device=dev)
         kern_ms.append(ctx.last_kernel_ms(dom))  # CUDA events around the dominant kernel, on its stream
         if kind == "static":
             aux_ms.append(ctx.last_kernel_ms("chain_eval"))

@@ -84,10 +84,16 @@ __global__ void __launch_bounds__(kGWarps * 32)
     double* sA = reinterpret_cast<double*>(smem_raw);
     int* sIdx = reinterpret_cast<int*>(sA + kGWarps * 32 * T * 12);
     const double* tab = tb.tab;
+    const float* tabR = tb.tabR32;
     if (tab_in_smem) {
         double* st = reinterpret_cast<double*>(smem_raw) + kGWarps * 32 * T * 12 + (kGWarps * 32 * T + 1) / 2;
         for (int i = threadIdx.x; i < 12 * tot; i += blockDim.x) st[i] = tb.tab[i];
         tab = st;
+        if (sizeof(OutT) == 4) {
+            float* sf = reinterpret_cast<float*>(st + 12 * tot);
+            for (int i = threadIdx.x; i < 9 * tot; i += blockDim.x) sf[i] = tb.tabR32[i];
+            tabR = sf;
+        }
         __syncthreads();
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,44 +128,81 @@ __global__ void __launch_bounds__(kGWarps * 32)
             }
         }
         __syncwarp();
-        // ---- phase 2: lane = (node slot, row)
+        // ---- phase 2
         const int ncfg = (int)min((long long)32, B - b0);
-        for (int c = 0; c < ncfg; ++c) {
-            const long long b = b0 + c;
-            for (int n = 0; n < T; ++n) {
-                const int id = wIdx[c * T + n];
-                const int start = full ? 0 : id;                               // kinematic.py:100-103
-                const int cnt = mc.npts[n] - start;
-                const long long obase = offsets[b * T + n];
-                double a0 = 0, a1 = 0, a2 = 0, ap = 0;
-                if (row < 3) {
-                    const double* ar = wA + (c * T + n) * 12 + row * 4;
-                    a0 = ar[0];
-                    a1 = ar[1];
-                    a2 = ar[2];
-                    ap = ar[3];
+        if (sizeof(OutT) == 8) {
+            // fp64: lane = (8 node slots, 4 matrix rows); one 256-bit store per lane, 1 KiB per warp instruction
+            for (int c = 0; c < ncfg; ++c) {
+                const long long b = b0 + c;
+                for (int n = 0; n < T; ++n) {
+                    const int id = wIdx[c * T + n];
+                    const int start = full ? 0 : id;                               // kinematic.py:100-103
+                    const int cnt = mc.npts[n] - start;
+                    const long long obase = offsets[b * T + n];
+                    double a0 = 0, a1 = 0, a2 = 0, ap = 0;
+                    if (row < 3) {
+                        const double* ar = wA + (c * T + n) * 12 + row * 4;
+                        a0 = ar[0];
+                        a1 = ar[1];
+                        a2 = ar[2];
+                        ap = ar[3];
+                    }
+                    const int colbase = mc.node_base[n] + start;
+                    for (int k = slot; k < cnt; k += 8) {
+                        const int col = colbase + k;
+                        double* dst = reinterpret_cast<double*>(out) + ((obase + k) * 16 + row * 4);
+                        if (row == 3) {
+                            RowStore<double>::st(dst, 0.0, 0.0, 0.0, 1.0);
+                        } else {
+                            double o0 = fma(a0, tab[0 * tot + col], fma(a1, tab[3 * tot + col], a2 * tab[6 * tot + col]));
+                            double o1 = fma(a0, tab[1 * tot + col], fma(a1, tab[4 * tot + col], a2 * tab[7 * tot + col]));
+                            double o2 = fma(a0, tab[2 * tot + col], fma(a1, tab[5 * tot + col], a2 * tab[8 * tot + col]));
+                            double o3 = fma(a0, tab[9 * tot + col], fma(a1, tab[10 * tot + col], fma(a2, tab[11 * tot + col], ap)));
+                            RowStore<double>::st(dst, o0, o1, o2, o3);
+                        }
+                    }
                 }
-                const int colbase = mc.node_base[n] + start;
-                for (int k = slot; k < cnt; k += 8) {
-                    const int col = colbase + k;
-                    OutT* dst = out + ((obase + k) * 16 + row * 4);
-                    if (row == 3) {
-                        RowStore<OutT>::st(dst, (OutT)0, (OutT)0, (OutT)0, (OutT)1);
-                    } else if (sizeof(OutT) == 8) {
-                        double o0 = fma(a0, tab[0 * tot + col], fma(a1, tab[3 * tot + col], a2 * tab[6 * tot + col]));
-                        double o1 = fma(a0, tab[1 * tot + col], fma(a1, tab[4 * tot + col], a2 * tab[7 * tot + col]));
-                        double o2 = fma(a0, tab[2 * tot + col], fma(a1, tab[5 * tot + col], a2 * tab[8 * tot + col]));
-                        double o3 = fma(a0, tab[9 * tot + col], fma(a1, tab[10 * tot + col], fma(a2, tab[11 * tot + col], ap)));
-                        RowStore<OutT>::st(dst, (OutT)o0, (OutT)o1, (OutT)o2, (OutT)o3);
-                    } else {
-                        // fp32 path: rotation in fp32, position row in fp64 (the two ~L-sized terms cancel)
-                        const float* tr = tb.tabR32;
-                        float f0 = (float)a0, f1 = (float)a1, f2 = (float)a2;
-                        float o0 = fmaf(f0, tr[0 * tot + col], fmaf(f1, tr[3 * tot + col], f2 * tr[6 * tot + col]));
-                        float o1 = fmaf(f0, tr[1 * tot + col], fmaf(f1, tr[4 * tot + col], f2 * tr[7 * tot + col]));
-                        float o2 = fmaf(f0, tr[2 * tot + col], fmaf(f1, tr[5 * tot + col], f2 * tr[8 * tot + col]));
-                        double o3 = fma(a0, tab[9 * tot + col], fma(a1, tab[10 * tot + col], fma(a2, tab[11 * tot + col], ap)));
-                        RowStore<OutT>::st(dst, (OutT)o0, (OutT)o1, (OutT)o2, (OutT)o3);
+            }
+        } else {
+            // fp32: lane = (16 node slots, 2 row pairs); rows (0,1) or (2,3) = 32 B = one 256-bit store per lane.
+            // Rotation in fp32, the position entry in fp64 (its two ~L-sized terms cancel).
+            const int slot16 = lane >> 1, half = lane & 1;
+            for (int c = 0; c < ncfg; ++c) {
+                const long long b = b0 + c;
+                for (int n = 0; n < T; ++n) {
+                    const int id = wIdx[c * T + n];
+                    const int start = full ? 0 : id;
+                    const int cnt = mc.npts[n] - start;
+                    const long long obase = offsets[b * T + n];
+                    const double* ar = wA + (c * T + n) * 12 + (half ? 8 : 0);   // row 0 or row 2
+                    const double a0 = ar[0], a1 = ar[1], a2 = ar[2], ap = ar[3];
+                    const double b0_ = half ? 0.0 : ar[4], b1_ = half ? 0.0 : ar[5], b2_ = half ? 0.0 : ar[6], bp = half ? 0.0 : ar[7];
+                    const float f0 = (float)a0, f1 = (float)a1, f2 = (float)a2;
+                    const float g0 = (float)b0_, g1 = (float)b1_, g2 = (float)b2_;
+                    const int colbase = mc.node_base[n] + start;
+                    for (int k = slot16; k < cnt; k += 16) {
+                        const int col = colbase + k;
+                        const float r0 = tabR[0 * tot + col], r1 = tabR[1 * tot + col], r2 = tabR[2 * tot + col];
+                        const float r3 = tabR[3 * tot + col], r4 = tabR[4 * tot + col], r5 = tabR[5 * tot + col];
+                        const float r6 = tabR[6 * tot + col], r7 = tabR[7 * tot + col], r8 = tabR[8 * tot + col];
+                        const double px = tab[9 * tot + col], py = tab[10 * tot + col], pz = tab[11 * tot + col];
+                        float o[8];
+                        o[0] = fmaf(f0, r0, fmaf(f1, r3, f2 * r6));
+                        o[1] = fmaf(f0, r1, fmaf(f1, r4, f2 * r7));
+                        o[2] = fmaf(f0, r2, fmaf(f1, r5, f2 * r8));
+                        o[3] = (float)fma(a0, px, fma(a1, py, fma(a2, pz, ap)));
+                        if (half) {
+                            o[4] = 0.f; o[5] = 0.f; o[6] = 0.f; o[7] = 1.f;
+                        } else {
+                            o[4] = fmaf(g0, r0, fmaf(g1, r3, g2 * r6));
+                            o[5] = fmaf(g0, r1, fmaf(g1, r4, g2 * r7));
+                            o[6] = fmaf(g0, r2, fmaf(g1, r5, g2 * r8));
+                            o[7] = (float)fma(b0_, px, fma(b1_, py, fma(b2_, pz, bp)));
+                        }
+                        float* dst = reinterpret_cast<float*>(out) + ((obase + k) * 16 + half * 8);
+                        asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]),
+                                     "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                                     : "memory");
                     }
                 }
             }
@@ -436,7 +479,7 @@ int launch_gcurve(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_t
     if (B <= 0) return CTRB_OK;
     const int T = m->mc.T, tot = m->mc.total_nodes;
     size_t base = (size_t)kGWarps * 32 * T * 12 * sizeof(double) + (((size_t)kGWarps * 32 * T + 1) / 2) * sizeof(double);
-    size_t with_tab = base + (size_t)12 * tot * sizeof(double);
+    size_t with_tab = base + (size_t)12 * tot * sizeof(double) + (precision == CTRB_F32 ? (size_t)9 * tot * sizeof(float) : 0);
     int tab_in_smem = with_tab <= 100 * 1024;
     size_t smem = tab_in_smem ? with_tab : base;
     long long ngroups = (B + 31) / 32;

@@ -28,8 +28,9 @@
 
 namespace ctrb {
 
-constexpr int kSWarps = 4;    // warps (= configurations) per block
-constexpr int kNP = 32;       // padded unknown count / leading dimension
+constexpr int kSWarps = 3;    // warps (= configurations) per block: 5 blocks (15 warps) per SM by smem and registers
+constexpr int kNP = 31;       // leading dimension of the n x n work matrices (odd: conflict-free column access)
+constexpr int kNV = 32;       // padded vector length
 constexpr int kMaxNq = kStaticMaxNq;
 
 struct StCfg {
@@ -314,11 +315,16 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
 // ------------------------------------------------------------------ MINPACK hybrd, warp-cooperative
 // All arrays are shared memory of this warp.  Matrices are column-major with leading dimension kNP.
 struct HybrdMem {
-    double fjac[kNP * kNP];
-    double r[kNP * (kNP + 1) / 2];
-    double x[kNP], fvec[kNP], qtf[kNP], diag[kNP], wa1[kNP], wa2[kNP], wa3[kNP], wa4[kNP];
-    double ybuf[12][16];  // node integrands of one cooperative residual evaluation
+    double fjac[kNP * kMaxNq];
+    double r[kMaxNq * (kMaxNq + 1) / 2];
+    double x[kNV], fvec[kNV], qtf[kNV], wa1[kNV], wa2[kNV], wa3[kNV], wa4[kNV];
+    double ybuf0[12][16];     // node integrands of a residual (3 sections x 2 abscissae x {lo, hi})
     StCfg cfg;
+    // During the forward-difference Jacobian two residuals are evaluated side by side.  R, wa3 and wa4 are
+    // dead then (R is rebuilt from the QR right after), so the second set of node vectors and the two
+    // perturbed unknown vectors alias them.
+    __device__ double (*ybuf(int g))[16] { return g == 0 ? ybuf0 : reinterpret_cast<double(*)[16]>(r); }
+    __device__ double* qbuf(int g) { return g == 0 ? wa3 : wa4; }
 };
 
 __device__ __noinline__ double warp_sum(double v) {
@@ -381,65 +387,71 @@ __device__ __noinline__ double enorm_w(int n, double v, const double* x_smem_or_
 
 __device__ __forceinline__ int rowoff(int n, int j) { return j * n - (j * (j - 1)) / 2; }  // packed upper-triangular rows
 
-// Cooperative residual: lanes 0..11 evaluate the 12 bracket-node integrands (3 sections x 2 abscissae x
-// {lo, hi}), lanes 0..n-1 then assemble one component each.  q and F are shared-memory vectors.
-__device__ __noinline__ void st_residual_w(const StModel& sm, HybrdMem& M, const double* q, double* F, int lane) {
-    const StCfg& c = M.cfg;
+// Cooperative residual, phase 1: work item t in 0..11 = (section, abscissa, bracket end) evaluates one node
+// integrand vector into y (shared memory).  q is a shared-memory vector of the unknowns.
+__device__ __noinline__ void res_node(const StModel& sm, const StCfg& c, const double* q, int t, double* y) {
     const int T = sm.mc.T;
-    double s31e = 0.0, c31e = 1.0, S31e[3] = {0.0, 0.0, 0.0};
-    if (T == 3) {
-        const double Xe = (c.L[0] - 1) * sm.mc.dx;
-        sincos_ni(c.th[2] + ipoly3(q + sm.qoff[2], Xe), &s31e, &c31e);
-        S31e[0] = Xe;
-        S31e[1] = 0.5 * Xe * Xe;
-        S31e[2] = Xe * Xe * Xe * (1.0 / 3.0);
-    }
-    if (lane < 12) {
-        const int sec = lane >> 2, a = (lane >> 1) & 1, e = lane & 1;
-        double* y = M.ybuf[lane];
-        if (c.len[sec] > 0.0 && (sec != 0 || T == 3)) {
-            const int node = e ? c.hi[sec][a] : c.lo[sec][a];
-            if (sec == 0) node_sec1(sm, c, q, node, y);
-            else if (sec == 1) node_sec2(sm, c, q, node, s31e, c31e, S31e, y);
-            else node_sec3(sm, c, q, node, y);
+    const int sec = t >> 2, a = (t >> 1) & 1, e = t & 1;
+    if (c.len[sec] > 0.0 && (sec != 0 || T == 3)) {
+        const int node = e ? c.hi[sec][a] : c.lo[sec][a];
+        if (sec == 0) {
+            node_sec1(sm, c, q, node, y);
+        } else if (sec == 1) {
+            double s31e = 0.0, c31e = 1.0, S31e[3] = {0.0, 0.0, 0.0};
+            if (T == 3) {  // final relative frame / basis integral of tube 3 over section 1 (equilibrium_three's return)
+                const double Xe = (c.L[0] - 1) * sm.mc.dx;
+                sincos_ni(c.th[2] + ipoly3(q + sm.qoff[2], Xe), &s31e, &c31e);
+                S31e[0] = Xe;
+                S31e[1] = 0.5 * Xe * Xe;
+                S31e[2] = Xe * Xe * Xe * (1.0 / 3.0);
+            }
+            node_sec2(sm, c, q, node, s31e, c31e, S31e, y);
         } else {
+            node_sec3(sm, c, q, node, y);
+        }
+    } else {
 #pragma unroll 1
-            for (int k = 0; k < 16; ++k) y[k] = 0.0;
+        for (int k = 0; k < 16; ++k) y[k] = 0.0;
+    }
+}
+
+// phase 2: component k of F from the 12 node vectors (calculate_integral, static.py:456-491)
+__device__ __noinline__ double res_assemble(const StModel& sm, const StCfg& c, const double (*yb)[16], int comp) {
+    int blk = 0;  // order (1,1),(2,1),(3,1),(2,2),(3,2),(3,3)
+#pragma unroll
+    for (int b = 1; b < 6; ++b)
+        if (comp >= sm.qoff[b] && sm.ndof[b] > 0) blk = b;
+    const int k = comp - sm.qoff[blk];
+    const int sec = blk < 3 ? 0 : (blk < 5 ? 1 : 2);
+    const int yo = (blk == 0 || blk == 3 || blk == 5) ? 0 : ((blk == 1 || blk == 4) ? 9 : 12);
+    double acc = 0.0;
+    if (c.len[sec] > 0.0) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const double ylo = yb[sec * 4 + a * 2 + 0][yo + k], yhi = yb[sec * 4 + a * 2 + 1][yo + k];
+            acc += 0.5 * (((yhi - ylo) / c.dxs[sec][a]) * c.dxn[sec][a] + ylo);
         }
     }
-    __syncwarp();
-    if (lane < sm.nq) {
-        // which block does component `lane` belong to?  order (1,1),(2,1),(3,1),(2,2),(3,2),(3,3)
-        int blk = 0;
-#pragma unroll
-        for (int b = 1; b < 6; ++b)
-            if (lane >= sm.qoff[b] && sm.ndof[b] > 0) blk = b;
-        const int k = lane - sm.qoff[blk];
-        // (section, offset inside the node vector) of that block; block 2 = intg_31 - intg_312
-        const int sec = blk < 3 ? 0 : (blk < 5 ? 1 : 2);
-        const int yo = (blk == 0 || blk == 3 || blk == 5) ? 0 : ((blk == 1 || blk == 4) ? 9 : 12);
-        double acc = 0.0;
-        if (c.len[sec] > 0.0) {
+    double val = (c.len[sec] / 2) * acc;
+    if (blk == 2) {  // intg_31 - intg_312: the section-2 share lives at offset 12 of the section-2 vectors
+        double acc2 = 0.0;
+        if (c.len[1] > 0.0) {
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
-                const double ylo = M.ybuf[sec * 4 + a * 2 + 0][yo + k], yhi = M.ybuf[sec * 4 + a * 2 + 1][yo + k];
-                acc += 0.5 * (((yhi - ylo) / c.dxs[sec][a]) * c.dxn[sec][a] + ylo);
+                const double ylo = yb[4 + a * 2 + 0][12 + k], yhi = yb[4 + a * 2 + 1][12 + k];
+                acc2 += 0.5 * (((yhi - ylo) / c.dxs[1][a]) * c.dxn[1][a] + ylo);
             }
         }
-        double val = (c.len[sec] / 2) * acc;
-        if (blk == 2) {  // minus the section-2 share (intg_312 lives at offset 12 of the section-2 vectors)
-            double acc2 = 0.0;
-            if (c.len[1] > 0.0) {
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const double ylo = M.ybuf[4 + a * 2 + 0][12 + k], yhi = M.ybuf[4 + a * 2 + 1][12 + k];
-                    acc2 += 0.5 * (((yhi - ylo) / c.dxs[1][a]) * c.dxn[1][a] + ylo);
-                }
-            }
-            val -= (c.len[1] / 2) * acc2;
-        }
-        F[lane] = val;
+        val -= (c.len[1] / 2) * acc2;
     }
+    return val;
+}
+
+// one residual evaluation F(q) by the whole warp; q and F are shared-memory vectors
+__device__ __forceinline__ void st_residual_w(const StModel& sm, HybrdMem& M, const double* q, double* F, int lane) {
+    if (lane < 12) res_node(sm, M.cfg, q, lane, M.ybuf0[lane]);
+    __syncwarp();
+    if (lane < sm.nq) F[lane] = res_assemble(sm, M.cfg, M.ybuf0, lane);
     __syncwarp();
 }
 
@@ -617,19 +629,39 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, int lane, d
 #pragma unroll 1
     for (;;) {  // outer loop: fresh forward-difference Jacobian
         bool jeval = true;
-        // fdjac1 (dense): lane j evaluates the residual at x + h e_j and fills column j
-        if (act) {
-            double xp[kMaxNq], Fp[kMaxNq];
-#pragma unroll 1
-            for (int k = 0; k < n; ++k) xp[k] = M.x[k];
+        // fdjac1 (dense): columns two at a time -- lanes 0..11 evaluate the node integrands of x + h_j e_j,
+        // lanes 12..23 those of x + h_(j+1) e_(j+1); then lanes 0..n-1 assemble both columns
+        {
             const double eps = sqrt(epsmch);
-            const double temp = xp[lane];
-            double h = eps * fabs(temp);
-            if (h == 0) h = eps;
-            xp[lane] = temp + h;
-            st_residual(sm, M.cfg, xp, Fp);
 #pragma unroll 1
-            for (int i = 0; i < n; ++i) fjac[i + lane * kNP] = (Fp[i] - M.fvec[i]) / h;
+            for (int j0 = 0; j0 < n; j0 += 2) {
+                if (act) {
+                    const double xv = M.x[lane];
+                    double h = eps * fabs(xv);
+                    if (h == 0) h = eps;
+                    M.qbuf(0)[lane] = (lane == j0) ? xv + h : xv;
+                    M.qbuf(1)[lane] = (lane == j0 + 1) ? xv + h : xv;
+                }
+                __syncwarp();
+                if (lane < 24) {
+                    const int g = lane >= 12 ? 1 : 0;
+                    if (j0 + g < n) res_node(sm, M.cfg, M.qbuf(g), lane - 12 * g, M.ybuf(g)[lane - 12 * g]);
+                }
+                __syncwarp();
+                if (act) {
+#pragma unroll 1
+                    for (int g = 0; g < 2; ++g) {
+                        const int j = j0 + g;
+                        if (j >= n) break;
+                        const double xv = M.x[j];
+                        double h = eps * fabs(xv);
+                        if (h == 0) h = eps;
+                        const double Fp = res_assemble(sm, M.cfg, M.ybuf(g), lane);
+                        fjac[lane + j * kNP] = (Fp - M.fvec[lane]) / h;
+                    }
+                }
+                __syncwarp();
+            }
         }
         nfev += n;
         __syncwarp();
@@ -911,7 +943,7 @@ __device__ __forceinline__ SE3 se3_rx(double angle) {
 __device__ __forceinline__ double ipoly3_abs(const double* q, double a, double b) { return ipoly3(q, b) - ipoly3(q, a); }
 
 // ------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(kSWarps * 32)
+__global__ void __launch_bounds__(kSWarps * 32, 5)
     static_solve_kernel(StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
                         const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                         double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
