@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctrb_geom.cuh"
@@ -421,6 +422,228 @@ __global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_
     }
 }
 
+// ------------------------------------------------------------------ packed variant
+// chain_eval_kernel above gives a whole warp to one configuration, which leaves most lanes idle when a
+// configuration has few cylinders (ncu, C3 "shallow": 3.6 of 32 lanes active per instruction).  The packed
+// kernel lets a warp take 32 configurations at a time: lane = configuration for the SE(3) chain, the node
+// positions and the epilogue (no redundant prologue, coalesced result stores), and lane = work item for the
+// BVH walks: the cylinders of as many of those configurations as fit the warp's node pool are flattened into
+// one item list that the lanes drain through a shared-memory ticket.  Bounds / contact flags are per
+// configuration slot.
+constexpr int kPWarps = 8;
+constexpr int kPool = 384;  // node positions (fp64 xyz) per warp
+
+struct PackedWarpMem {
+    double pos[kPool * 3];
+    unsigned int items[kPool];       // node (10 bits) | slot (5 bits) << 10 | tube (2 bits) << 15
+    WarpCtl ctl[32];                 // per configuration slot: bound bits, contact flag
+    unsigned long long best_bits[32];
+    int ticket;
+    int pad[3];
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kPWarps * 32, 2) chain_eval_packed_kernel(EvalParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BvhNode* s_top = reinterpret_cast<BvhNode*>(smem_raw);
+    PackedWarpMem* s_all = reinterpret_cast<PackedWarpMem*>(smem_raw + (size_t)kTopNodes * sizeof(BvhNode));
+
+    const EnvConst& env = *P.env;
+    const int ntop = min(env.obs.nnodes, kTopNodes);
+    for (int i = threadIdx.x; i < ntop * 4; i += blockDim.x)
+        reinterpret_cast<float4*>(s_top)[i] = __ldg(reinterpret_cast<const float4*>(env.obs.nodes) + i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    PackedWarpMem& W = s_all[warp];
+    const int T = FUSED ? P.mc.T : P.tube_num;
+    const bool have_obstacles = env.obs.ntri > 0 || env.nprim > 0;
+    Work wk = {0, 0, 0};
+    unsigned int nconf = 0;
+
+    for (;;) {
+        long long b0;
+        {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(P.counters + 4, 32ULL);
+            b0 = (long long)__shfl_sync(0xffffffffu, t, 0);
+        }
+        if (b0 >= P.B) break;
+        const int nchunk = (int)min((long long)32, P.B - b0);
+        int done = 0;
+        while (done < nchunk) {
+            // ---- lane = configuration: node counts, how many configurations fit the pool
+            const int ci = done + lane;
+            const bool valid = ci < nchunk;
+            const long long b = b0 + ci;
+            int cnt[CTRB_MAX_TUBES];
+            int tn = 0, ncyl = 0;
+#pragma unroll
+            for (int n = 0; n < CTRB_MAX_TUBES; ++n) {
+                cnt[n] = 0;
+                if (valid && n < T) {
+                    if (FUSED) cnt[n] = P.mc.npts[n] - P.idx[b * T + n];  // kinematic.py:100-103 (full=False)
+                    else cnt[n] = (int)(P.offsets[b * T + n + 1] - P.offsets[b * T + n]);
+                    tn += cnt[n];
+                    ncyl += max(cnt[n] - 1, 0);
+                }
+            }
+            int nend = tn, iend = ncyl;  // inclusive scans over lanes
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int a = __shfl_up_sync(0xffffffffu, nend, off), c = __shfl_up_sync(0xffffffffu, iend, off);
+                if (lane >= off) {
+                    nend += a;
+                    iend += c;
+                }
+            }
+            const unsigned fit = __ballot_sync(0xffffffffu, valid && nend <= kPool);
+            int m = __ffs(~fit) - 1;  // leading lanes that fit (the host guarantees one configuration always fits)
+            if (m < 0) m = 32;
+            m = max(m, 1);
+            const bool mine = valid && lane < m;
+            const int nstart = nend - tn, istart = iend - ncyl;
+            const int total_items = __shfl_sync(0xffffffffu, iend, m - 1);
+            // ---- positions of my configuration into the pool, cylinder items into the list
+            if (mine) {
+                nconf++;
+                double* dst = W.pos + (size_t)nstart * 3;
+                unsigned int* it = W.items + istart;
+                int node = nstart;
+                if (FUSED) {
+                    const int tot = P.mc.total_nodes;
+                    SE3 g;
+                    se3_identity(g);
+                    for (int n = 0; n < T; ++n) {
+                        const int id = P.idx[b * T + n];
+                        se3_rot_x(g, P.theta[b * T + n]);
+                        const SE3 a = se3_mul(g, load_tab(P.tb.tab_inv, tot, P.mc.node_base[n] + id));
+                        const int colbase = P.mc.node_base[n] + id;
+#pragma unroll 1
+                        for (int k = 0; k < cnt[n]; ++k) {
+                            const int col = colbase + k;
+                            const double cx = __ldg(P.tb.tab + 9 * tot + col), cy = __ldg(P.tb.tab + 10 * tot + col),
+                                         cz = __ldg(P.tb.tab + 11 * tot + col);
+                            dst[0] = fma(a.r[0], cx, fma(a.r[1], cy, fma(a.r[2], cz, a.p[0])));
+                            dst[1] = fma(a.r[3], cx, fma(a.r[4], cy, fma(a.r[5], cz, a.p[1])));
+                            dst[2] = fma(a.r[6], cx, fma(a.r[7], cy, fma(a.r[8], cz, a.p[2])));
+                            dst += 3;
+                            if (k + 1 < cnt[n]) *it++ = (unsigned)(node + k) | ((unsigned)lane << 10) | ((unsigned)n << 15);
+                        }
+                        node += cnt[n];
+                        g = se3_mul(a, load_tab(P.tb.tab, tot, P.mc.node_base[n] + P.mc.npts[n] - 1));
+                    }
+                } else {
+                    for (int n = 0; n < T; ++n) {
+                        const double* gg = P.g + P.offsets[b * T + n] * 16;
+#pragma unroll 1
+                        for (int k = 0; k < cnt[n]; ++k) {
+                            dst[0] = __ldg(gg + (size_t)k * 16 + 3);
+                            dst[1] = __ldg(gg + (size_t)k * 16 + 7);
+                            dst[2] = __ldg(gg + (size_t)k * 16 + 11);
+                            dst += 3;
+                            if (k + 1 < cnt[n]) *it++ = (unsigned)(node + k) | ((unsigned)lane << 10) | ((unsigned)n << 15);
+                        }
+                        node += cnt[n];
+                    }
+                }
+            }
+            W.ctl[lane].bound_bits = __float_as_int(FLT_MAX);
+            W.ctl[lane].collided = 0;
+            W.best_bits[lane] = (unsigned long long)__double_as_longlong(DBL_MAX);
+            if (lane == 0) W.ticket = 0;
+            __syncwarp();
+            // ---- lane = work item: drain the cylinder list
+            if (have_obstacles) {
+                for (;;) {
+                    const int q = atomicAdd(&W.ticket, 1);
+                    if (q >= total_items) break;
+                    const unsigned code = W.items[q];
+                    const int node = code & 1023, slot = (code >> 10) & 31, n = (code >> 15) & 3;
+                    WarpCtl* ctl = &W.ctl[slot];
+                    if (*(volatile int*)&ctl->collided) continue;
+                    const double* pf = W.pos + (size_t)node * 3;
+                    d3 f = {pf[0], pf[1], pf[2]}, t = {pf[3], pf[4], pf[5]};
+                    d3 vec = t - f;
+                    const double len = sqrt(dot(vec, vec));       // collision_checker.py:130-131
+                    d3 c = f + 0.5 * vec;
+                    d3 a = (1.0 / len) * vec;
+                    const double h = 0.5 * len, r = P.rad[n];
+                    double best = DBL_MAX;
+                    if (env.obs.ntri > 0) cylinder_vs_mesh(env.obs, s_top, ntop, c, a, h, r, ctl, best, wk);
+                    for (int k = 0; k < env.nprim && !*(volatile int*)&ctl->collided; ++k) {
+                        const double d = cylinder_vs_prim(env.prims[k], c, a, h, r, best);
+                        if (d <= 0.0) *(volatile int*)&ctl->collided = 1;
+                        else if (d < best) {
+                            best = d;
+                            atomicMin(&ctl->bound_bits, __float_as_int(__double2float_ru(d)));
+                        }
+                    }
+                    if (best < DBL_MAX) atomicMin(&W.best_bits[slot], (unsigned long long)__double_as_longlong(best));
+                }
+            }
+            __syncwarp();
+            // ---- lane = configuration again: goal distance, cost, results (coalesced across lanes)
+            if (mine) {
+                const bool collided = *(volatile int*)&W.ctl[lane].collided != 0;
+                const double best = __longlong_as_double((long long)W.best_bits[lane]);
+                double gd = DBL_MAX;
+                if (tn > 0 && env.goal.shape != CTRB_SHAPE_NONE) {
+                    const double* pt = W.pos + (size_t)(nstart + tn - 1) * 3;  // curve[-1][-1]
+                    d3 tip = {pt[0], pt[1], pt[2]};
+                    const double tr = P.rad[T - 1];
+                    const DevPrim& gl = env.goal;
+                    if (gl.shape == CTRB_SHAPE_SPHERE) {
+                        d3 dd = tip - d3{gl.center[0], gl.center[1], gl.center[2]};
+                        gd = sqrt(dot(dd, dd)) - gl.dims[0] - tr;
+                    } else if (gl.shape == CTRB_SHAPE_BOX) {
+                        gd = point_box_dist(tip, gl.center, gl.rot, gl.dims) - tr;
+                    } else if (gl.shape == CTRB_SHAPE_CYLINDER) {
+                        d3 ax = {gl.rot[2], gl.rot[5], gl.rot[8]};
+                        gd = point_cyl_dist(tip, d3{gl.center[0], gl.center[1], gl.center[2]}, ax, 0.5 * gl.dims[1], gl.dims[0]) - tr;
+                    } else if (gl.shape == CTRB_SHAPE_MESH && env.goal_mesh.ntri > 0) {
+                        gd = point_vs_mesh(env.goal_mesh, tip, wk) - tr;
+                    }
+                    if (gd <= 0.0) gd = -1.0;
+                }
+                const double om = collided ? -1.0 : (have_obstacles && ncyl > 0 ? best : DBL_MAX);
+                P.obstacle_min[b] = om;
+                P.goal_dist[b] = gd;
+                if (P.collide) P.collide[b] = collided ? 1 : 0;
+                if (P.cost) {
+                    double cst = CUDART_NAN;  // rrt.py:116-129
+                    if (!collided) {
+                        const double g0 = gd < 0.0 ? 0.0 : gd;
+                        if (P.cd.cost_type == CTRB_COST_SOAPWG) {
+                            const double inv = 1.0 / om;
+                            cst = g0 * P.cd.goal_weight + inv * inv;
+                        } else if (P.cd.cost_type == CTRB_COST_ONLY_GOAL) {
+                            cst = g0;
+                        } else {
+                            cst = 0.0;
+                        }
+                    }
+                    P.cost[b] = cst;
+                }
+            }
+            __syncwarp();
+            done += m;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        wk.nodes += __shfl_xor_sync(0xffffffffu, wk.nodes, off);
+        wk.pre += __shfl_xor_sync(0xffffffffu, wk.pre, off);
+        wk.exact += __shfl_xor_sync(0xffffffffu, wk.exact, off);
+        nconf += __shfl_xor_sync(0xffffffffu, nconf, off);
+    }
+    if (lane == 0) {
+        atomicAdd(P.counters + 0, (unsigned long long)wk.nodes);
+        atomicAdd(P.counters + 1, (unsigned long long)wk.pre);
+        atomicAdd(P.counters + 2, (unsigned long long)wk.exact);
+        atomicAdd(P.counters + 3, (unsigned long long)nconf);
+    }
+}
+
 size_t eval_smem_bytes(int max_nodes) {
     return (size_t)kTopNodes * sizeof(BvhNode) + (size_t)kCWarps * max_nodes * 3 * sizeof(double) +
            (size_t)kCWarps * sizeof(WarpCtl);
@@ -428,6 +651,30 @@ size_t eval_smem_bytes(int max_nodes) {
 
 int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
     if (P.B <= 0) return CTRB_OK;
+    // The packed kernel is kept for experiments only (CTRB_EVAL_PACKED=1): measured on a B200 it is 25-30 % SLOWER
+    // than one warp per configuration (18.6 vs 24.5 M configs/s, C3 shallow) although every lane is busy -- the walks
+    // diverge lane by lane and the fp64 exact tests serialise, and with more cylinders in flight per warp the shared
+    // bounds tighten later (exact tests per config 10.6 vs 6.2).  See DESIGN.md section 9.
+    if (P.max_nodes <= kPool && getenv("CTRB_EVAL_PACKED")) {
+        const size_t smem_p = (size_t)kTopNodes * sizeof(BvhNode) + (size_t)kPWarps * sizeof(PackedWarpMem);
+        CTRB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        int per_sm = 1;
+        if (fused) {
+            CTRB_CUDA(cudaFuncSetAttribute(chain_eval_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_eval_packed_kernel<true>, kPWarps * 32, smem_p));
+        } else {
+            CTRB_CUDA(cudaFuncSetAttribute(chain_eval_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_eval_packed_kernel<false>, kPWarps * 32, smem_p));
+        }
+        const long long chunks = (P.B + 31) / 32;
+        const int grid_p = (int)std::min<long long>((chunks + kPWarps - 1) / kPWarps, (long long)ctx->sm_count * std::max(per_sm, 1));
+        KernelTimer kt(ctx, CTRB_KERNEL_CHAIN_EVAL);
+        if (fused) chain_eval_packed_kernel<true><<<grid_p, kPWarps * 32, smem_p, ctx->stream>>>(P);
+        else chain_eval_packed_kernel<false><<<grid_p, kPWarps * 32, smem_p, ctx->stream>>>(P);
+        ctx->launches++;
+        CTRB_CUDA(cudaGetLastError());
+        return CTRB_OK;
+    }
     size_t smem = eval_smem_bytes(P.max_nodes);
     if (smem > 200 * 1024) {
         set_error("configuration has too many nodes (%d) for the shared-memory staging", P.max_nodes);
