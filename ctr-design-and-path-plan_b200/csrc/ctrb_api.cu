@@ -377,10 +377,9 @@ int ctrb_env_create(ctrb_ctx* ctx, const double* obstacle_tris, int32_t n_obs, c
     CTRB_REQUIRE(n_prims == 0 || prims, "prims is NULL");
     CTRB_REQUIRE(n_prims <= kMaxPrims, "at most %d primitive obstacles are supported", kMaxPrims);
     for (int i = 0; i < n_prims; ++i) {
-        if (prims[i].shape != CTRB_SHAPE_SPHERE && prims[i].shape != CTRB_SHAPE_BOX) {
-            // the reference accepts Cylinder obstacles (init_collision.py:131-135); the exact solid
-            // cylinder <-> solid cylinder distance is not built yet
-            set_error("obstacle shape %d not supported (Sphere and Box are)", prims[i].shape);
+        if (prims[i].shape != CTRB_SHAPE_SPHERE && prims[i].shape != CTRB_SHAPE_BOX &&
+            prims[i].shape != CTRB_SHAPE_CYLINDER) {
+            set_error("Shape type %d not supported.", prims[i].shape);  // init_collision.py:140
             return CTRB_ERR_UNSUPPORTED;
         }
     }

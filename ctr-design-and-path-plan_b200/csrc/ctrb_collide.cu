@@ -216,7 +216,7 @@ __device__ void box_corner(const DevPrim& b, int k, d3& out) {
     out = {o[0], o[1], o[2]};
 }
 
-// solid cylinder vs primitive obstacle (fcl.Sphere / fcl.Box, init_collision.py:129-139)
+// solid cylinder vs primitive obstacle (fcl.Sphere / fcl.Cylinder / fcl.Box, init_collision.py:129-139)
 __device__ __noinline__ double cylinder_vs_prim(const DevPrim& o, d3 c, d3 a, double h, double r, double bound) {
     if (o.shape == CTRB_SHAPE_SPHERE) {
         double d = point_cyl_dist(d3{o.center[0], o.center[1], o.center[2]}, c, a, h, r) - o.dims[0];
@@ -237,6 +237,10 @@ __device__ __noinline__ double cylinder_vs_prim(const DevPrim& o, d3 c, d3 a, do
             if (best == 0.0) break;
         }
         return best;
+    }
+    if (o.shape == CTRB_SHAPE_CYLINDER) {  // axis = local z column of rotate_align('direction')
+        return cyl_cyl_dist(c, a, h, r, d3{o.center[0], o.center[1], o.center[2]}, d3{o.rot[2], o.rot[5], o.rot[8]},
+                            0.5 * o.dims[1], o.dims[0]);
     }
     return DBL_MAX;
 }

@@ -209,6 +209,247 @@ __device__ __noinline__ double cyl_tri_dist(d3 c, d3 a, double h, double r, d3 t
     return e;
 }
 
+// ------------------------------------------------------------------ solid cylinder vs solid cylinder (GJK)
+// Obstacle fcl.Cylinder (init_collision.py:131-135) against a tube cylinder.  FCL runs libccd's GJK with a
+// 1e-6 tolerance on this pair; here the same iteration runs to ~1e-14 in fp64.  The simplex is at most 4
+// points of the Minkowski difference; its closest point to the origin comes from the region tests.
+struct GjkCyl {
+    d3 c, a;
+    double h, r;
+};
+
+__device__ __forceinline__ d3 cyl_support(const GjkCyl& C, d3 d) {
+    const double da = dot(d, C.a);
+    d3 w = d - da * C.a;
+    const double wn = sqrt(dot(w, w));
+    const double sg = da >= 0.0 ? 1.0 : -1.0;
+    d3 o = C.c + (sg * C.h) * C.a;
+    if (wn > 0.0) o = o + (C.r / wn) * w;
+    return o;
+}
+
+// closest point to the origin of the simplex W[0..n-1], n <= 3; W is reduced to the supporting face
+__device__ __noinline__ int simplex_closest3(d3* W, int n, d3& v) {
+    if (n == 1) {
+        v = W[0];
+        return 1;
+    }
+    if (n == 2) {
+        d3 ab = W[1] - W[0];
+        double t = -dot(W[0], ab), den = dot(ab, ab);
+        if (t <= 0.0 || den == 0.0) {
+            v = W[0];
+            return 1;
+        }
+        if (t >= den) {
+            W[0] = W[1];
+            v = W[0];
+            return 1;
+        }
+        v = W[0] + (t / den) * ab;
+        return 2;
+    }
+    if (n == 3) {
+        const d3 a = W[0], b = W[1], c = W[2];
+        const d3 ab = b - a, ac = c - a, ap = -1.0 * a;
+        const double d1 = dot(ab, ap), d2 = dot(ac, ap);
+        if (d1 <= 0.0 && d2 <= 0.0) { v = a; return 1; }
+        const d3 bp = -1.0 * b;
+        const double d3v = dot(ab, bp), d4 = dot(ac, bp);
+        if (d3v >= 0.0 && d4 <= d3v) { W[0] = b; v = b; return 1; }
+        const double vc = d1 * d4 - d3v * d2;
+        if (vc <= 0.0 && d1 >= 0.0 && d3v <= 0.0) {
+            v = a + (d1 / (d1 - d3v)) * ab;
+            return 2;
+        }
+        const d3 cp = -1.0 * c;
+        const double d5 = dot(ab, cp), d6 = dot(ac, cp);
+        if (d6 >= 0.0 && d5 <= d6) { W[0] = c; v = c; return 1; }
+        const double vb = d5 * d2 - d1 * d6;
+        if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+            v = a + (d2 / (d2 - d6)) * ac;
+            W[1] = c;
+            return 2;
+        }
+        const double va = d3v * d6 - d5 * d4;
+        if (va <= 0.0 && (d4 - d3v) >= 0.0 && (d5 - d6) >= 0.0) {
+            v = b + ((d4 - d3v) / ((d4 - d3v) + (d5 - d6))) * (c - b);
+            W[0] = b;
+            W[1] = c;
+            return 2;
+        }
+        const double den = 1.0 / (va + vb + vc);
+        v = a + (vb * den) * ab + (vc * den) * ac;
+        return 3;
+    }
+    return 0;
+}
+
+// the same for n <= 4 (no recursion: device stack sizes must be static)
+__device__ __noinline__ int simplex_closest(d3* W, int n, d3& v) {
+    if (n < 4) return simplex_closest3(W, n, v);
+    // tetrahedron: inside iff the four sub-volumes share the sign of the whole volume; else the nearest face
+    const d3 e1 = W[1] - W[0], e2 = W[2] - W[0], e3 = W[3] - W[0];
+    const double vol = dot(cross(e1, e2), e3);
+    const double scale = sqrt(dot(e1, e1) * dot(e2, e2) * dot(e3, e3));
+    if (fabs(vol) > 1e-12 * scale) {
+        bool inside = true;
+#pragma unroll 1
+        for (int f = 0; f < 4 && inside; ++f) {
+            d3 P[4] = {W[0], W[1], W[2], W[3]};
+            P[f] = d3{0.0, 0.0, 0.0};
+            if (dot(cross(P[1] - P[0], P[2] - P[0]), P[3] - P[0]) * vol < 0.0) inside = false;
+        }
+        if (inside) {
+            v = d3{0.0, 0.0, 0.0};
+            return 4;
+        }
+    }
+    double best = 1.7976931348623157e308;
+    d3 bv = {0, 0, 0}, BW[3] = {W[0], W[0], W[0]};
+    int bn = 1;
+#pragma unroll 1
+    for (int f = 0; f < 4; ++f) {
+        d3 T3[3];
+        int k = 0;
+        for (int i = 0; i < 4; ++i)
+            if (i != f) T3[k++] = W[i];
+        d3 tv;
+        const int tn = simplex_closest3(T3, 3, tv);
+        const double dd = dot(tv, tv);
+        if (dd < best) {
+            best = dd;
+            bv = tv;
+            BW[0] = T3[0];
+            BW[1] = T3[1];
+            BW[2] = T3[2];
+            bn = tn;
+        }
+    }
+    W[0] = BW[0];
+    W[1] = BW[1];
+    W[2] = BW[2];
+    v = bv;
+    return bn;
+}
+
+__device__ __noinline__ double gjk_cyl_cyl(d3 c1, d3 a1, double h1, double r1, d3 c2, d3 a2, double h2, double r2) {
+    const GjkCyl A = {c1, a1, h1, r1}, B = {c2, a2, h2, r2};
+    d3 W[4];
+    d3 v = c1 - c2;
+    if (dot(v, v) == 0.0) return 0.0;
+    int n = 0, stall = 0;
+    double best_vv = dot(v, v);
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it) {
+        const d3 w = cyl_support(A, -1.0 * v) - cyl_support(B, v);
+        const double vv = dot(v, v), vw = dot(v, w);
+        // |v| decreases monotonically in exact arithmetic; keep the best value and stop once rounding stalls it
+        if (vv < best_vv * (1.0 - 1e-15)) stall = 0;
+        else ++stall;
+        best_vv = fmin(best_vv, vv);
+        if (vv - vw <= 1e-14 * vv || stall >= 12) return sqrt(best_vv);
+        bool dup = false;
+        for (int k = 0; k < n; ++k) {
+            const d3 e = w - W[k];
+            if (dot(e, e) <= 1e-30 * (1.0 + vv)) dup = true;
+        }
+        if (dup) return sqrt(best_vv);
+        W[n++] = w;
+        n = simplex_closest(W, n, v);
+        if (n == 4) return 0.0;
+        if (dot(v, v) <= 1e-28) return 0.0;
+    }
+    return sqrt(fmin(best_vv, dot(v, v)));
+}
+
+// one rim circle of cylinder 1 (centre o, radius r1, in-plane frame e1, e2) against the solid cylinder 2
+__device__ __forceinline__ double rim_point_dist(double phi, d3 o, d3 e1, d3 e2, double r1, d3 c2, d3 a2, double h2,
+                                                 double r2) {
+    double sn, cs;
+    sincos(phi, &sn, &cs);
+    return point_cyl_dist(o + (r1 * cs) * e1 + (r1 * sn) * e2, c2, a2, h2, r2);
+}
+
+// min over the rim of the distance to the other cylinder: 64 samples, then golden-section refinement of every
+// local-minimum bracket that can still undercut the best sample (point_cyl_dist is 1-Lipschitz)
+__device__ __noinline__ double rim_min(d3 c1, d3 a1, double h1, double r1, double sg, d3 c2, d3 a2, double h2, double r2) {
+    constexpr int NS = 64;
+    const double step = 6.283185307179586 / NS, gr = 0.6180339887498949;
+    d3 t = fabs(a1.x) < 0.6 ? d3{1.0, 0.0, 0.0} : d3{0.0, 1.0, 0.0};
+    d3 e1 = cross(a1, t);
+    e1 = (1.0 / sqrt(dot(e1, e1))) * e1;
+    const d3 e2 = cross(a1, e1);
+    const d3 o = c1 + (sg * h1) * a1;
+    double best = 1.7976931348623157e308, fprev, ffirst, fcur;
+    ffirst = rim_point_dist(0.0, o, e1, e2, r1, c2, a2, h2, r2);
+    if (ffirst == 0.0) return 0.0;
+    best = ffirst;
+#pragma unroll 1
+    for (int i = 1; i < NS; ++i) {
+        const double f = rim_point_dist(i * step, o, e1, e2, r1, c2, a2, h2, r2);
+        if (f == 0.0) return 0.0;
+        best = fmin(best, f);
+    }
+    double res = best;
+    fprev = rim_point_dist(-step, o, e1, e2, r1, c2, a2, h2, r2);
+    fcur = ffirst;
+#pragma unroll 1
+    for (int i = 0; i < NS; ++i) {
+        const double fnext = rim_point_dist((i + 1) * step, o, e1, e2, r1, c2, a2, h2, r2);
+        if (!(fcur > fprev || fcur > fnext || fcur - r1 * step > res)) {
+            double lo = (i - 1) * step, hi = (i + 1) * step;
+            double x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
+            double f1 = rim_point_dist(x1, o, e1, e2, r1, c2, a2, h2, r2);
+            double f2 = rim_point_dist(x2, o, e1, e2, r1, c2, a2, h2, r2);
+#pragma unroll 1
+            for (int it = 0; it < 64; ++it) {
+                if (f1 <= f2) {
+                    hi = x2; x2 = x1; f2 = f1;
+                    x1 = hi - gr * (hi - lo);
+                    f1 = rim_point_dist(x1, o, e1, e2, r1, c2, a2, h2, r2);
+                } else {
+                    lo = x1; x1 = x2; f1 = f2;
+                    x2 = lo + gr * (hi - lo);
+                    f2 = rim_point_dist(x2, o, e1, e2, r1, c2, a2, h2, r2);
+                }
+            }
+            res = fmin(res, fmin(f1, f2));
+        }
+        fprev = fcur;
+        fcur = fnext;
+    }
+    return res;
+}
+
+// Exact solid cylinder vs solid cylinder.  GJK on two curved bodies converges like 1/k^2 (1e-6 after 256
+// iterations), so it is the intersection test only.  Disjoint cylinders: the closest pair has a common normal;
+// each closest point is the support point of its cylinder along it, i.e. a rim point unless the normal is
+// perpendicular or parallel to the axis, and those support sets (generator, cap disk) still meet a rim of one
+// of the bodies except when two generators are closest at interior points = axis distance minus both radii.
+__device__ __noinline__ double cyl_cyl_dist(d3 c1, d3 a1, double h1, double r1, d3 c2, d3 a2, double h2, double r2) {
+    if (gjk_cyl_cyl(c1, a1, h1, r1, c2, a2, h2, r2) == 0.0) return 0.0;
+    const d3 w = c1 - c2;
+    const double b = dot(a1, a2), d = dot(a1, w), e = dot(a2, w), den = 1.0 - b * b;
+    double s = 0.0, t = 0.0;
+    if (den > 1e-12) {
+        s = (b * e - d) / den;
+        t = (e - b * d) / den;
+        if (fabs(s) < h1 && fabs(t) < h2) {
+            const d3 y = w + s * a1 - t * a2;
+            return fmax(sqrt(dot(y, y)) - r1 - r2, 0.0);
+        }
+    }
+    s = fmin(fmax(s, -h1), h1);
+    t = fmin(fmax(t, -h2), h2);
+    if (point_cyl_dist(c1 + s * a1, c2, a2, h2, r2) == 0.0 || point_cyl_dist(c2 + t * a2, c1, a1, h1, r1) == 0.0) return 0.0;
+    double best = rim_min(c1, a1, h1, r1, 1.0, c2, a2, h2, r2);
+    best = fmin(best, rim_min(c1, a1, h1, r1, -1.0, c2, a2, h2, r2));
+    best = fmin(best, rim_min(c2, a2, h2, r2, 1.0, c1, a1, h1, r1));
+    best = fmin(best, rim_min(c2, a2, h2, r2, -1.0, c1, a1, h1, r1));
+    return best;
+}
+
 // distance from a point to a solid box
 __device__ __forceinline__ double point_box_dist(d3 x, const double* center, const double* rot, const double* dims) {
     d3 y = {x.x - center[0], x.y - center[1], x.z - center[2]};

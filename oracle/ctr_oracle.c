@@ -653,6 +653,277 @@ static double cylinder_box(const double c[3], const double a[3], double h, doubl
     return best;
 }
 
+/* ------------------------------------------------------------------ GJK distance between two solid cylinders
+ * (obstacle fcl.Cylinder vs tube fcl.Cylinder, init_collision.py:131-135).  FCL runs libccd's GJK with a 1e-6
+ * tolerance here; this restatement iterates the same algorithm to ~1e-13.  The Minkowski difference of the two
+ * cylinders is searched through its support map; the closest point of the current simplex (<= 4 points) to the
+ * origin is found by the usual region tests. */
+typedef struct { double c[3], a[3], h, r; } gjk_cyl;
+
+static void cyl_support(const gjk_cyl* C, const double d[3], double out[3]) {
+    double da = dot3(d, C->a);
+    double w[3] = {d[0] - da * C->a[0], d[1] - da * C->a[1], d[2] - da * C->a[2]};
+    double wn = sqrt(dot3(w, w));
+    double sg = da >= 0 ? 1.0 : -1.0;
+    for (int k = 0; k < 3; ++k) out[k] = C->c[k] + sg * C->h * C->a[k] + (wn > 0 ? C->r * w[k] / wn : 0.0);
+}
+
+/* closest point to the origin on the simplex W[0..n-1]; reduces W to the supporting face; returns n' */
+static int simplex_closest(double W[4][3], int n, double v[3]) {
+    if (n == 1) {
+        memcpy(v, W[0], 3 * sizeof(double));
+        return 1;
+    }
+    if (n == 2) {
+        double ab[3];
+        sub3(W[1], W[0], ab);
+        double t = -dot3(W[0], ab), den = dot3(ab, ab);
+        if (t <= 0 || den == 0) {
+            memcpy(v, W[0], 3 * sizeof(double));
+            return 1;
+        }
+        if (t >= den) {
+            memcpy(W[0], W[1], 3 * sizeof(double));
+            memcpy(v, W[0], 3 * sizeof(double));
+            return 1;
+        }
+        t /= den;
+        for (int k = 0; k < 3; ++k) v[k] = W[0][k] + t * ab[k];
+        return 2;
+    }
+    if (n == 3) {
+        /* closest point of triangle to the origin (Ericson 5.1.5 with p = 0), keeping the supporting vertices */
+        double *a = W[0], *b = W[1], *c = W[2];
+        double ab[3], ac[3], ap[3] = {-a[0], -a[1], -a[2]};
+        sub3(b, a, ab);
+        sub3(c, a, ac);
+        double d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+        if (d1 <= 0 && d2 <= 0) { memcpy(v, a, 24); return 1; }
+        double bp[3] = {-b[0], -b[1], -b[2]};
+        double d3v = dot3(ab, bp), d4 = dot3(ac, bp);
+        if (d3v >= 0 && d4 <= d3v) { memcpy(W[0], b, 24); memcpy(v, W[0], 24); return 1; }
+        double vc = d1 * d4 - d3v * d2;
+        if (vc <= 0 && d1 >= 0 && d3v <= 0) {
+            double t = d1 / (d1 - d3v);
+            for (int k = 0; k < 3; ++k) v[k] = a[k] + t * ab[k];
+            return 2; /* W[0]=a, W[1]=b */
+        }
+        double cp[3] = {-c[0], -c[1], -c[2]};
+        double d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+        if (d6 >= 0 && d5 <= d6) { memcpy(W[0], c, 24); memcpy(v, W[0], 24); return 1; }
+        double vb = d5 * d2 - d1 * d6;
+        if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+            double t = d2 / (d2 - d6);
+            for (int k = 0; k < 3; ++k) v[k] = a[k] + t * ac[k];
+            memcpy(W[1], c, 24);
+            return 2;
+        }
+        double va = d3v * d6 - d5 * d4;
+        if (va <= 0 && (d4 - d3v) >= 0 && (d5 - d6) >= 0) {
+            double t = (d4 - d3v) / ((d4 - d3v) + (d5 - d6));
+            for (int k = 0; k < 3; ++k) v[k] = b[k] + t * (c[k] - b[k]);
+            memcpy(W[0], b, 24);
+            memcpy(W[1], c, 24);
+            return 2;
+        }
+        double den = 1.0 / (va + vb + vc), s = vb * den, t = vc * den;
+        for (int k = 0; k < 3; ++k) v[k] = a[k] + s * ab[k] + t * ac[k];
+        return 3;
+    }
+    /* tetrahedron: the origin is inside iff the four sub-volumes (origin in place of a vertex) all have the
+     * sign of the whole volume; otherwise the closest point lies on one of the four faces */
+    {
+        static const int F[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+        double e1[3], e2[3], e3[3], cr[3];
+        sub3(W[1], W[0], e1);
+        sub3(W[2], W[0], e2);
+        sub3(W[3], W[0], e3);
+        cross3(e1, e2, cr);
+        double vol = dot3(cr, e3);
+        double scale = sqrt(dot3(e1, e1) * dot3(e2, e2) * dot3(e3, e3));
+        if (fabs(vol) > 1e-12 * scale) {
+            int inside = 1;
+            for (int f = 0; f < 4 && inside; ++f) {
+                /* volume of the tetrahedron with vertex f replaced by the origin, same vertex order */
+                double P[4][3];
+                memcpy(P, W, sizeof P);
+                P[f][0] = P[f][1] = P[f][2] = 0.0;
+                double a1[3], a2[3], a3[3], c2[3];
+                sub3(P[1], P[0], a1);
+                sub3(P[2], P[0], a2);
+                sub3(P[3], P[0], a3);
+                cross3(a1, a2, c2);
+                if (dot3(c2, a3) * vol < 0) inside = 0;
+            }
+            if (inside) {
+                v[0] = v[1] = v[2] = 0.0;
+                return 4;
+            }
+        }
+        double best = DBL_MAX, bv[3] = {0, 0, 0}, BW[4][3];
+        int bn = 0;
+        memset(BW, 0, sizeof BW);
+        for (int f = 0; f < 4; ++f) {
+            double T3[4][3], tv[3];
+            memcpy(T3[0], W[F[f][0]], 24);
+            memcpy(T3[1], W[F[f][1]], 24);
+            memcpy(T3[2], W[F[f][2]], 24);
+            int tn = simplex_closest(T3, 3, tv);
+            double dd = dot3(tv, tv);
+            if (dd < best) {
+                best = dd;
+                memcpy(bv, tv, 24);
+                memcpy(BW, T3, sizeof BW);
+                bn = tn;
+            }
+        }
+        memcpy(W, BW, sizeof BW);
+        memcpy(v, bv, 24);
+        return bn;
+    }
+}
+
+static int g_gjk_iters = 0, g_gjk_exit = 0, g_gjk_cap = 256;
+void orc_gjk_set_cap(int c) { g_gjk_cap = c; }
+int orc_gjk_last_iters(void) { return g_gjk_iters; }
+int orc_gjk_last_exit(void) { return g_gjk_exit; }
+
+static double gjk_cylinder_cylinder(const double c1[3], const double a1[3], double h1, double r1, const double c2[3],
+                                   const double a2[3], double h2, double r2) {
+    gjk_cyl A, B;
+    memcpy(A.c, c1, 24); memcpy(A.a, a1, 24); A.h = h1; A.r = r1;
+    memcpy(B.c, c2, 24); memcpy(B.a, a2, 24); B.h = h2; B.r = r2;
+    double W[4][3], v[3];
+    sub3(A.c, B.c, v);
+    if (dot3(v, v) == 0) return 0.0;
+    int n = 0, stall = 0;
+    double best_vv = dot3(v, v);
+    for (int it = 0; it < g_gjk_cap; ++it) {
+        double dneg[3] = {-v[0], -v[1], -v[2]}, sa[3], sb[3], w[3];
+        cyl_support(&A, dneg, sa);
+        cyl_support(&B, v, sb);
+        sub3(sa, sb, w);
+        double vv = dot3(v, v), vw = dot3(v, w);
+        g_gjk_iters = it;
+        /* |v| decreases monotonically in exact arithmetic; keep the best value and stop once rounding stalls it */
+        if (vv < best_vv * (1 - 1e-15)) stall = 0;
+        else ++stall;
+        if (vv < best_vv) best_vv = vv;
+        if (vv - vw <= 1e-14 * vv) { g_gjk_exit = 1; return sqrt(best_vv); } /* v is the closest point of A - B */
+        if (stall >= 12) { g_gjk_exit = 2; return sqrt(best_vv); }
+        int dup = 0;
+        for (int k = 0; k < n; ++k) {
+            double e[3];
+            sub3(w, W[k], e);
+            if (dot3(e, e) <= 1e-30 * (1 + vv)) dup = 1;
+        }
+        if (dup) { g_gjk_exit = 2; return sqrt(best_vv); }
+        memcpy(W[n++], w, 24);
+        n = simplex_closest(W, n, v);
+        if (n == 4) return 0.0;
+        if (dot3(v, v) <= 1e-28) return 0.0;
+    }
+    g_gjk_exit = 3;
+    {
+        double vv = dot3(v, v);
+        if (vv < best_vv) best_vv = vv;
+    }
+    return sqrt(best_vv);
+}
+
+
+/* minimum over one rim circle of cylinder 1 (centre c1 + sg h1 a1, radius r1) of the distance to the solid
+ * cylinder 2: 64 samples, then a golden-section refinement of every local-minimum bracket that can still
+ * undercut the best sample (the point-cylinder distance is 1-Lipschitz). */
+static double rim_point_dist(double phi, const double o[3], const double e1[3], const double e2[3], double r1,
+                             const double c2[3], const double a2[3], double h2, double r2) {
+    double cs = cos(phi), sn = sin(phi), x[3];
+    for (int k = 0; k < 3; ++k) x[k] = o[k] + r1 * (cs * e1[k] + sn * e2[k]);
+    return orc_point_cylinder(x, c2, a2, h2, r2);
+}
+
+static double rim_min(const double c1[3], const double a1[3], double h1, double r1, double sg, const double c2[3],
+                      const double a2[3], double h2, double r2) {
+    enum { NS = 64 };
+    const double step = 6.283185307179586 / NS, gr = 0.6180339887498949;
+    double t[3] = {0, 0, 0}, e1[3], e2[3], o[3], f[NS];
+    t[fabs(a1[0]) < 0.6 ? 0 : 1] = 1.0;
+    cross3(a1, t, e1);
+    double en = sqrt(dot3(e1, e1));
+    for (int k = 0; k < 3; ++k) e1[k] /= en;
+    cross3(a1, e1, e2);
+    for (int k = 0; k < 3; ++k) o[k] = c1[k] + sg * h1 * a1[k];
+    double best = DBL_MAX;
+    for (int i = 0; i < NS; ++i) {
+        f[i] = rim_point_dist(i * step, o, e1, e2, r1, c2, a2, h2, r2);
+        if (f[i] == 0.0) return 0.0;
+        if (f[i] < best) best = f[i];
+    }
+    double res = best;
+    for (int i = 0; i < NS; ++i) {
+        double fp = f[(i + NS - 1) % NS], fn = f[(i + 1) % NS];
+        if (f[i] > fp || f[i] > fn || f[i] - r1 * step > res) continue;
+        double lo = (i - 1) * step, hi = (i + 1) * step;
+        double x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
+        double f1 = rim_point_dist(x1, o, e1, e2, r1, c2, a2, h2, r2);
+        double f2 = rim_point_dist(x2, o, e1, e2, r1, c2, a2, h2, r2);
+        for (int it = 0; it < 64; ++it) {
+            if (f1 <= f2) {
+                hi = x2; x2 = x1; f2 = f1;
+                x1 = hi - gr * (hi - lo);
+                f1 = rim_point_dist(x1, o, e1, e2, r1, c2, a2, h2, r2);
+            } else {
+                lo = x1; x1 = x2; f1 = f2;
+                x2 = lo + gr * (hi - lo);
+                f2 = rim_point_dist(x2, o, e1, e2, r1, c2, a2, h2, r2);
+            }
+        }
+        double m = f1 < f2 ? f1 : f2;
+        if (m < res) res = m;
+    }
+    return res;
+}
+
+/* Exact distance between two solid flat-capped cylinders (obstacle fcl.Cylinder vs tube cylinder).  GJK on two
+ * curved bodies converges only like 1/k^2 (1e-6 after 256 iterations), so it serves as the intersection test
+ * alone.  For disjoint cylinders the closest pair (x, y) has a common normal n; x is the support point of
+ * cylinder 1 along n, which is a rim point unless n is perpendicular or parallel to the axis -- and in those
+ * cases the support set (a generator or a cap disk) still meets a rim of one of the two bodies, except when two
+ * generators are closest at interior points; that case is the axis-segment distance minus both radii.  Hence
+ *   d = |axis1 - axis2| - r1 - r2   if the closest points of the two axis lines are interior to both segments,
+ *   d = min over the four rims of min_phi dist(rim(phi), other cylinder)   otherwise. */
+double orc_cylinder_cylinder(const double c1[3], const double a1[3], double h1, double r1, const double c2[3],
+                             const double a2[3], double h2, double r2) {
+    if (gjk_cylinder_cylinder(c1, a1, h1, r1, c2, a2, h2, r2) == 0.0) return 0.0;
+    double w[3];
+    sub3(c1, c2, w);
+    const double b = dot3(a1, a2), d = dot3(a1, w), e = dot3(a2, w), den = 1.0 - b * b;
+    double s = 0.0, t = 0.0;
+    if (den > 1e-12) {
+        s = (b * e - d) / den;
+        t = (e - b * d) / den;
+        if (fabs(s) < h1 && fabs(t) < h2) {
+            double y[3] = {w[0] + s * a1[0] - t * a2[0], w[1] + s * a1[1] - t * a2[1], w[2] + s * a1[2] - t * a2[2]};
+            double dd = sqrt(dot3(y, y)) - r1 - r2;
+            return dd > 0 ? dd : 0.0;
+        }
+    }
+    /* the axis point of each cylinder nearest the other axis line, clamped: inside the other body => contact */
+    s = s > h1 ? h1 : (s < -h1 ? -h1 : s);
+    t = t > h2 ? h2 : (t < -h2 ? -h2 : t);
+    double p1[3] = {c1[0] + s * a1[0], c1[1] + s * a1[1], c1[2] + s * a1[2]};
+    double p2[3] = {c2[0] + t * a2[0], c2[1] + t * a2[1], c2[2] + t * a2[2]};
+    if (orc_point_cylinder(p1, c2, a2, h2, r2) == 0.0 || orc_point_cylinder(p2, c1, a1, h1, r1) == 0.0) return 0.0;
+    double best = rim_min(c1, a1, h1, r1, 1.0, c2, a2, h2, r2);
+    double m = rim_min(c1, a1, h1, r1, -1.0, c2, a2, h2, r2);
+    if (m < best) best = m;
+    m = rim_min(c2, a2, h2, r2, 1.0, c1, a1, h1, r1);
+    if (m < best) best = m;
+    m = rim_min(c2, a2, h2, r2, -1.0, c1, a1, h1, r1);
+    if (m < best) best = m;
+    return best;
+}
+
 /* ------------------------------------------------------------------ */
 /* environment with a plain median-split AABB tree (CPU baseline speed) */
 /* ------------------------------------------------------------------ */
@@ -882,8 +1153,12 @@ int orc_env_check_collision(const orc_env* env, const double* pos, const int* co
                     if (d < 0) d = 0;
                 } else if (o->shape == ORC_SHAPE_BOX) {
                     d = cylinder_box(c, a, h, r, o);
+                } else if (o->shape == ORC_SHAPE_CYLINDER) {
+                    double oa[3];
+                    prim_axis(o, oa);
+                    d = orc_cylinder_cylinder(c, a, h, r, o->center, oa, 0.5 * o->dims[1], o->dims[0]);
                 } else {
-                    return -3; /* cylinder obstacle vs cylinder tube: not restated */
+                    return -3;
                 }
                 if (d < best) best = d;
             }

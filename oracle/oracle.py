@@ -216,6 +216,13 @@ def cylinder_triangle(c, a, h, r, t0, t1, t2):
     return lib().orc_cylinder_triangle(_dp(_f64(c)), _dp(_f64(a)), h, r, _dp(_f64(t0)), _dp(_f64(t1)), _dp(_f64(t2)))
 
 
+def cylinder_cylinder(c1, a1, h1, r1, c2, a2, h2, r2):
+    f = lib().orc_cylinder_cylinder
+    f.restype = C.c_double
+    f.argtypes = [C.POINTER(C.c_double)] * 2 + [C.c_double] * 2 + [C.POINTER(C.c_double)] * 2 + [C.c_double] * 2
+    return f(_dp(_f64(c1)), _dp(_f64(a1)), h1, r1, _dp(_f64(c2)), _dp(_f64(a2)), h2, r2)
+
+
 def point_triangle(x, t0, t1, t2):
     return lib().orc_point_triangle(_dp(_f64(x)), _dp(_f64(t0)), _dp(_f64(t1)), _dp(_f64(t2)))
 

@@ -137,7 +137,8 @@ def test_primitive_obstacles_and_goals():
     idx, theta = random_configs(m.num_discrete_points, 500, rng, 1, 30)
     rot = orc.rotate_align(np.array([1.0, 2.0, 2.0]) / 3.0)
     obstacles = [prim(L.SHAPE_SPHERE, (30, 8, -3), (4, 0, 0)), prim(L.SHAPE_BOX, (25, -12, 6), (6, 8, 10)),
-                 prim(L.SHAPE_SPHERE, (45, 0, 12), (6, 0, 0))]
+                 prim(L.SHAPE_SPHERE, (45, 0, 12), (6, 0, 0)),
+                 prim(L.SHAPE_CYLINDER, (20, 9, 9), (2.5, 14, 0), orc.rotate_align(np.array([2.0, -1.0, 2.0]) / 3.0))]
     goals = [prim(L.SHAPE_SPHERE, (60, 5, 5), (5, 0, 0)), prim(L.SHAPE_BOX, (50, 0, 0), (10, 12, 14)),
              prim(L.SHAPE_CYLINDER, (40, 10, 5), (4, 20, 0), rot)]
     for gp, go in goals:
@@ -170,8 +171,19 @@ def test_mesh_goal_no_obstacles():
 
 def test_unsupported_and_edge_cases():
     from ctrdapp_b200.collision import CollisionChecker
-    with pytest.raises(NotImplementedError):
-        CollisionChecker(FIXTURES / "init_cylinder_test.json")  # Cylinder obstacles: exact solid-solid distance not built
+    # the reference's own cylinder fixture (test/test_collision.py:77-92): axis-aligned Cylinder(1, 10) obstacles
+    from oracle import oracle as orc
+    cyl = CollisionChecker(FIXTURES / "init_cylinder_test.json")
+    oenv = orc.Env.from_json(FIXTURES / "init_cylinder_test.json")
+    rng = np.random.default_rng(2)
+    for _ in range(40):
+        p0 = rng.uniform(-7, 7, 3)
+        d = rng.normal(size=3)
+        p1 = p0 + d / np.linalg.norm(d)
+        curve = [[se3(p0), se3(p1), se3(p1 + (p1 - p0))]]
+        got, want = cyl.check_collision(curve, [0.5]), oenv.check_collision(curve, [0.5])
+        assert (got[0] < 0) == (want[0] < 0) and abs(got[0] - want[0]) < 1e-6 and abs(got[1] - want[1]) < 1e-6
+    assert cyl.check_collision([[se3([3.0, 3.0, 0.0]), se3([4.0, 3.0, 0.0])]], [0.5])[0] == pytest.approx(1.5, abs=1e-12)
     m = gpu_model("c3_three_tube")
     cc = CollisionChecker(FIXTURES / "env_colon_straight_new.json")
     out = cc.evaluate_batch(m, np.zeros((0, 3), np.int32), np.zeros((0, 3)), RAD3)

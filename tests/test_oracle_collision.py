@@ -170,3 +170,57 @@ def test_empty_obstacles_and_mesh_goal():
     obs, goal = env.check_collision([[se3([0, 0, 0]), se3([5, 0, 0])]], [5])
     assert obs == orc.DBL_MAX  # collision_checker.py:89-95 with no obstacles: DistanceResult default
     assert goal > 0 or goal == -1.0
+
+
+def test_cylinder_cylinder_gjk():
+    """Obstacle Cylinder vs tube cylinder: closed-form cases and an independent SLSQP minimisation of the
+    (convex) point-to-cylinder distance over the other cylinder."""
+    from scipy.optimize import minimize
+    z, y = np.array([0, 0, 1.0]), np.array([0, 1.0, 0])
+    assert orc.cylinder_cylinder([0, 0, 0], z, 1, 1, [0, 0, 4], z, 2, 0.5) == pytest.approx(1.0, abs=1e-12)
+    assert orc.cylinder_cylinder([0, 0, 0], z, 1, 1, [2.5, 0, 0.3], z, 1, 1) == pytest.approx(0.5, abs=1e-12)
+    assert orc.cylinder_cylinder([0, 0, 0], z, 5, 1, [3, 0, 0], y, 5, 1) == pytest.approx(1.0, abs=1e-12)
+    assert orc.cylinder_cylinder([0, 0, 0], z, 5, 1, [1.5, 0, 0], y, 5, 1) == 0.0
+    assert orc.cylinder_cylinder([0, 0, 0], z, 1, 1, [3, 0, 3], z, 1, 1) == pytest.approx(np.sqrt(2), abs=1e-12)
+    rng = np.random.default_rng(11)
+
+    def pc(x, c, a, h, r):
+        yv = x - c
+        t = yv @ a
+        return np.hypot(max(abs(t) - h, 0), max(np.linalg.norm(yv - t * a) - r, 0))
+
+    n_pos = 0
+    for _ in range(60):
+        c1, c2 = rng.normal(size=3) * 2, rng.normal(size=3) * 3
+        a1, a2 = rng.normal(size=3), rng.normal(size=3)
+        a1, a2 = a1 / np.linalg.norm(a1), a2 / np.linalg.norm(a2)
+        h1, r1, h2, r2 = rng.uniform(.3, 2), rng.uniform(.3, 1.5), rng.uniform(.3, 3), rng.uniform(.3, 2)
+        d = orc.cylinder_cylinder(c1, a1, h1, r1, c2, a2, h2, r2)
+        e1 = np.cross(a2, [1, 0, 0])
+        e1 /= np.linalg.norm(e1)
+        e2 = np.cross(a2, e1)
+        f = lambda p: pc(c2 + p[0] * a2 + p[1] * e1 + p[2] * e2, c1, a1, h1, r1) ** 2  # noqa: E731
+        best = np.inf
+        for _s in range(5):
+            p0 = np.array([rng.uniform(-h2, h2), rng.uniform(-r2, r2) / 2, rng.uniform(-r2, r2) / 2])
+            res = minimize(f, p0, method="SLSQP", bounds=[(-h2, h2), (None, None), (None, None)],
+                           constraints=[{"type": "ineq", "fun": lambda p: r2 * r2 - p[1] ** 2 - p[2] ** 2}],
+                           options={"ftol": 1e-16, "maxiter": 500})
+            best = min(best, np.sqrt(max(res.fun, 0)))
+        if d > 0:
+            n_pos += 1
+            assert d <= best + 1e-7 and best - d < 1e-5  # SLSQP satisfies its constraint only to ~1e-8
+        else:
+            assert best < 1e-4
+    assert n_pos > 25
+
+
+def test_reference_cylinder_fixture_loads():
+    """init_cylinder_test.json (test/test_collision.py:77-92) now goes through check_collision end to end."""
+    env = orc.Env.from_json(FIXTURES / "init_cylinder_test.json")
+    # tube (r = 0.5) along x at y = 3: 3 - 1 - 0.5 = 1.5 from the x- and y-aligned Cylinder(1, 10) obstacles
+    obs, goal = env.check_collision([[se3([3.0, 3.0, 0.0]), se3([4.0, 3.0, 0.0])]], [0.5])
+    assert obs == pytest.approx(1.5, abs=1e-12)
+    # inside the z-aligned one
+    obs, _ = env.check_collision([[se3([0.2, 0.3, 3.0]), se3([1.2, 0.3, 3.0])]], [0.5])
+    assert obs == -1.0
