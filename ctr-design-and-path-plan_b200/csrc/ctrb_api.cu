@@ -156,7 +156,7 @@ int ctrb_ctx_create(int device, ctrb_ctx** out) {
         CTRB_CUDA(cudaEventCreate(&c->ev[i]));
         CTRB_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     }
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 5; ++k)
         for (int i = 0; i < 2; ++i) {
             CTRB_CUDA(cudaEventCreate(&c->kev[k][i]));
             CTRB_CUDA(cudaEventRecord(c->kev[k][i], c->stream));
@@ -180,14 +180,14 @@ void ctrb_ctx_destroy(ctrb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2);
-    for (int i = 0; i < 12; ++i)
+    for (int i = 0; i < 16; ++i)
         if (c->scratch[i]) cudaFree(c->scratch[i]);
     cudaFree(c->d_counters);
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(c->ev[i]);
         cudaEventDestroy(c->ev_chunk[i]);
     }
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 5; ++k)
         for (int i = 0; i < 2; ++i) cudaEventDestroy(c->kev[k][i]);
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->stream2);
@@ -235,10 +235,20 @@ int ctrb_ctx_elapsed_ms(ctrb_ctx* c, float* ms) {
 }
 
 int ctrb_ctx_last_kernel_ms(ctrb_ctx* c, int kernel_id, float* ms) {
-    CTRB_REQUIRE(c && ms && kernel_id >= 0 && kernel_id < 4, "ctrb_ctx_last_kernel_ms: bad argument");
+    CTRB_REQUIRE(c && ms && kernel_id >= 0 && kernel_id < 5, "ctrb_ctx_last_kernel_ms: bad argument");
     CTRB_CUDA(cudaSetDevice(c->device));
     CTRB_CUDA(cudaEventSynchronize(c->kev[kernel_id][1]));
     CTRB_CUDA(cudaEventElapsedTime(ms, c->kev[kernel_id][0], c->kev[kernel_id][1]));
+    return CTRB_OK;
+}
+
+int ctrb_static_last_fallbacks(ctrb_ctx* c, uint64_t* count) {
+    CTRB_REQUIRE(c && count, "ctrb_static_last_fallbacks: bad argument");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long h = 0;
+    CTRB_CUDA(cudaMemcpy(&h, c->d_counters + 7, sizeof h, cudaMemcpyDeviceToHost));
+    *count = h;
     return CTRB_OK;
 }
 

@@ -73,11 +73,11 @@ struct ctrb_ctx {
     cudaStream_t stream2;  // second stream for host-memory chunk pipelining
     cudaEvent_t ev[2];
     cudaEvent_t ev_chunk[2];
-    cudaEvent_t kev[4][2];  // per-kernel start/stop of the most recent launch (ctrb_kernel_id)
+    cudaEvent_t kev[5][2];  // per-kernel start/stop of the most recent launch (ctrb_kernel_id)
     int64_t launches;
     // grow-only device scratch
-    void* scratch[12];
-    size_t scratch_bytes[12];
+    void* scratch[16];
+    size_t scratch_bytes[16];
     unsigned long long* d_counters;  // [8] work counters + scheduler tickets
     int sm_count;
 };

@@ -1,0 +1,488 @@
+// ctrb_static_common.cuh -- device code shared by the two static-model solve kernels:
+//   ctrb_static.cu       MINPACK hybrd with its QR factors (the literal algorithm; fallback + degenerate sections)
+//   ctrb_static_fast.cu  the same iteration carried on the explicit Jacobian and its inverse (Sherman-Morrison)
+// per-configuration setup (static.py:81-95), the closed-form node integrands of the residual
+// (static.py:228-454), calculate_integral's assembly (:456-491), warp norms and the curve integration
+// (integrate_g, :165-198).
+#pragma once
+#include <float.h>
+#include <math_constants.h>
+
+#include "ctrb_se3.cuh"
+
+namespace ctrb {
+namespace {  // internal linkage: two translation units include this header
+
+constexpr int kMaxNq = kStaticMaxNq;
+
+struct StCfg {
+    int i11, i21, i31, i22, i32, i33;
+    int L[3];  // nodes of sections 1..3
+    double th[3];
+    // calculate_integral's two abscissae per section: bracketing nodes and interpolation terms
+    int lo[3][2], hi[3][2];
+    double dxs[3][2], dxn[3][2], len[3];
+};
+
+// ------------------------------------------------------------------ small helpers
+struct V3 {
+    double x, y, z;
+};
+__device__ __forceinline__ V3 rotx(double s, double c, V3 v) { return {v.x, c * v.y - s * v.z, s * v.y + c * v.z}; }
+__device__ __forceinline__ V3 rotxT(double s, double c, V3 v) { return {v.x, c * v.y + s * v.z, -s * v.y + c * v.z}; }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ double poly3(const double* q, double x) { return q[0] + q[1] * x + q[2] * (x * x); }
+// closed-form integral of q . (1, x, x^2) from 0 to X
+__device__ __forceinline__ double ipoly3(const double* q, double X) {
+    return q[0] * X + q[1] * (0.5 * X * X) + q[2] * (X * X * X * (1.0 / 3.0));
+}
+
+// one out-of-line copy each of the fp64 sincos and of the strain-base switch: the solve kernel is
+// instruction-cache bound if these are inlined at every use (ncu: stall_no_instruction 17 per issue)
+__device__ __noinline__ void sincos_ni(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __noinline__ void strain_omega_ni(const ModelConst& mc, int n, double x, double w[3]) { strain_omega(mc, n, x, w); }
+
+// rows 0..2 of a strain base as a 3 x dof matrix (strain_bases.py:7-224)
+__device__ __noinline__ void strain_base_rows(int kind, int dof, double x, double B[3][CTRB_MAX_DOF]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < CTRB_MAX_DOF; ++k) B[r][k] = 0.0;
+    switch (kind) {
+        case CTRB_BASE_CONSTANT: B[1][0] = 1.0; break;
+        case CTRB_BASE_LINEAR:
+            B[1][0] = 1.0;
+            if (dof > 2) B[1][1] = x;
+            B[2][dof - 1] = x;
+            break;
+        case CTRB_BASE_QUADRATIC:
+            B[1][0] = 1.0;
+            if (dof > 2) B[1][1] = x * x;
+            B[2][dof - 1] = x * x;
+            break;
+        case CTRB_BASE_PURE_HELIX: { double sn, cs; sincos_ni(x / 10, &sn, &cs); B[1][0] = sn; B[2][1] = cs; break; }
+        case CTRB_BASE_LINEAR_HELIX: { double sn, cs; sincos_ni(x / 10, &sn, &cs); B[1][0] = sn; B[2][1] = x * cs; break; }
+        case CTRB_BASE_TORSION_HELIX: B[0][0] = 1.0; B[1][1] = 1.0; B[2][2] = 1.0; break;
+        case CTRB_BASE_TORSION_LINEAR_HELIX: B[0][0] = 1.0; B[1][1] = 1.0; B[2][2] = x; break;
+        case CTRB_BASE_FULL: {
+            int bs = (dof & 1) ? 1 : 2;
+            B[0][0] = 1.0;
+            if (!(dof & 1)) B[0][1] = x;
+            B[1][bs] = 1.0;
+            B[1][bs + 1] = x;
+            if (dof <= 6) {
+                B[2][bs + 2] = 1.0;
+                B[2][bs + 3] = x;
+            } else {
+                B[1][bs + 2] = x * x;
+                B[2][bs + 3] = 1.0;
+                B[2][bs + 4] = x;
+                B[2][bs + 5] = x * x;
+            }
+            break;
+        }
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------ per-configuration setup
+// static.py:81-95 section indices; :456-491 quadrature brackets
+__device__ __noinline__ void st_setup(const StModel& sm, const int* idx, const double* theta, StCfg& c) {
+    const int T = sm.mc.T;
+    const int* N = sm.mc.npts;
+    int i11 = idx[0], i22 = idx[T - 2], i33 = idx[T - 1];
+    int i21 = i22 - (N[0] - i11 - 1);
+    int i32 = i33 - (N[T - 2] - i22 - 1);
+    int i31 = i32 - (N[0] - i11 - 1);
+    if (T == 2) i11 = i21 = i31 = 0;
+    c.i11 = i11; c.i21 = i21; c.i31 = i31; c.i22 = i22; c.i32 = i32; c.i33 = i33;
+    c.L[0] = T == 3 ? N[0] - i11 : 1;
+    c.L[1] = N[T - 2] - i22;
+    c.L[2] = N[T - 1] - i33;
+    for (int n = 0; n < 3; ++n) c.th[n] = n < T ? theta[n] : 0.0;
+    const double cs[2] = {(1.0 / sqrt(3.0) + 1.0) / 2.0, (-1.0 / sqrt(3.0) + 1.0) / 2.0};  // static.py:601-603
+    for (int s = 0; s < 3; ++s) {
+        const int np = c.L[s];
+        const double length = (np - 1) * sm.mc.dx;
+        c.len[s] = length;
+        for (int a = 0; a < 2; ++a) {
+            c.lo[s][a] = c.hi[s][a] = 0;
+            c.dxs[s][a] = 1.0;
+            c.dxn[s][a] = 0.0;
+            if (!(length > 0.0)) continue;
+            const double step = length / (np - 1);  // np.linspace(0, length, num_points)
+            const double xn = cs[a] * length;
+            // searchsorted(x_vals, xn, side='left') clipped to [1, np-1]
+            int hi = (int)ceil(xn / step);
+            if (hi < 0) hi = 0;
+            if (hi > np - 1) hi = np - 1;
+            while (hi < np - 1 && ((hi == np - 1) ? length : hi * step) < xn) ++hi;
+            while (hi > 0 && (((hi - 1) == np - 1) ? length : (hi - 1) * step) >= xn) --hi;
+            if (hi < 1) hi = 1;
+            const int lo = hi - 1;
+            const double xlo = lo * step, xhi = (hi == np - 1) ? length : hi * step;
+            c.lo[s][a] = lo;
+            c.hi[s][a] = hi;
+            c.dxs[s][a] = xhi - xlo;
+            c.dxn[s][a] = xn - xlo;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ integrands at one node
+// The unknown vector as the node functions read it: shared-memory vector q with, optionally, component jp
+// displaced by hp -- the forward-difference Jacobian's x + h e_j without materialising a second vector
+// (q[k] + 0.0 is exact, so unperturbed components are bit-identical to a plain read).
+struct QV {
+    const double* q;
+    int jp;
+    double hp;
+    __device__ __forceinline__ double operator()(int k) const { return k == jp ? q[k] + hp : q[k]; }
+};
+__device__ __forceinline__ double poly3v(QV q, int o, double x) { return q(o) + q(o + 1) * x + q(o + 2) * (x * x); }
+__device__ __forceinline__ double ipoly3v(QV q, int o, double X) {
+    return q(o) * X + q(o + 1) * (0.5 * X * X) + q(o + 2) * (X * X * X * (1.0 / 3.0));
+}
+// section 1 (static.py:261-345), three tubes; y = [intc1 (9), intg21 (3), intg31 (3)]
+__device__ __noinline__ void node_sec1(const StModel& sm, const StCfg& c, QV q, int i, double y[15]) {
+    const double dx = sm.mc.dx, X = i * dx;
+    const int q11 = sm.qoff[0], q21 = sm.qoff[1], q31 = sm.qoff[2];
+    V3 w1 = {poly3v(q, q11, X), poly3v(q, q11 + 3, X), poly3v(q, q11 + 6, X)};
+    const double tg21 = poly3v(q, q21, X), tg31 = poly3v(q, q31, X);
+    double s21, c21, s31, c31;
+    sincos_ni(c.th[1] + ipoly3v(q, q21, X), &s21, &c21);  // gg21 = Rx(theta1 + int tau21)
+    sincos_ni(c.th[2] + ipoly3v(q, q31, X), &s31, &c31);
+    V3 w21 = rotxT(s21, c21, w1);
+    w21.x += tg21;
+    V3 w31 = rotxT(s31, c31, w21);
+    w31.x += tg31;
+    double ws[3];
+    strain_omega_ni(sm.mc, 0, (i + c.i11) * dx, ws);
+    V3 m11 = {sm.Kr[0][0] * (w1.x - ws[0]), sm.Kr[0][1] * (w1.y - ws[1]), sm.Kr[0][2] * (w1.z - ws[2])};
+    strain_omega_ni(sm.mc, 1, (i + c.i21) * dx, ws);
+    V3 m21 = {sm.Kr[1][0] * (w21.x - ws[0]), sm.Kr[1][1] * (w21.y - ws[1]), sm.Kr[1][2] * (w21.z - ws[2])};
+    strain_omega_ni(sm.mc, 2, (i + c.i31) * dx, ws);
+    V3 m31 = {sm.Kr[2][0] * (w31.x - ws[0]), sm.Kr[2][1] * (w31.y - ws[1]), sm.Kr[2][2] * (w31.z - ws[2])};
+    V3 r31m = rotx(s31, c31, m31);                 // coAd(gg31) fi_31 (moment part)
+    V3 u = {m21.x + r31m.x, m21.y + r31m.y, m21.z + r31m.z};
+    V3 ru = rotx(s21, c21, u);                      // coAd21 (fi_21 + coAd31 fi_31)
+    V3 wsum = {m11.x + ru.x, m11.y + ru.y, m11.z + ru.z};
+    V3 z21 = cross3(w1, ru);                        // coad(ksi_1) (...)
+    V3 z31 = cross3(w1, rotx(s21, c21, r31m));
+    const double P[3] = {1.0, X, X * X};
+    const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};  // sg (row 0) = int of the basis
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        y[k] = P[k] * wsum.x;
+        y[3 + k] = P[k] * wsum.y;
+        y[6 + k] = P[k] * wsum.z;
+        y[9 + k] = P[k] * (m21.x + m31.x) - S[k] * z21.x;
+        y[12 + k] = P[k] * m31.x - S[k] * z31.x;
+    }
+}
+
+// section 2 (static.py:347-436); y = [intc2 (9), intg32 (3), intg312 (3)]
+__device__ __noinline__ void node_sec2(const StModel& sm, const StCfg& c, QV q, int i, double s31e, double c31e,
+                          const double S31e[3], double y[15]) {
+    const int T = sm.mc.T;
+    const double dx = sm.mc.dx, X = i * dx;
+    const int q22 = sm.qoff[3], q32 = sm.qoff[4];
+    V3 w2 = {poly3v(q, q22, X), poly3v(q, q22 + 3, X), poly3v(q, q22 + 6, X)};
+    const double t32 = poly3v(q, q32, X);
+    double s32, c32;
+    sincos_ni((T == 2 ? c.th[1] : 0.0) + ipoly3v(q, q32, X), &s32, &c32);
+    V3 w32 = rotxT(s32, c32, rotxT(s31e, c31e, w2));
+    w32.x += t32;
+    double ws[3];
+    strain_omega_ni(sm.mc, T - 2, (i + c.i22) * dx, ws);
+    V3 m22 = {sm.Kr[T - 2][0] * (w2.x - ws[0]), sm.Kr[T - 2][1] * (w2.y - ws[1]), sm.Kr[T - 2][2] * (w2.z - ws[2])};
+    strain_omega_ni(sm.mc, T - 1, (i + c.i32) * dx, ws);
+    V3 m32 = {sm.Kr[T - 1][0] * (w32.x - ws[0]), sm.Kr[T - 1][1] * (w32.y - ws[1]), sm.Kr[T - 1][2] * (w32.z - ws[2])};
+    V3 a = rotx(s31e, c31e, rotx(s32, c32, m32));   // coAd31 coAd32 fi_32
+    V3 wsum = {m22.x + a.x, m22.y + a.y, m22.z + a.z};
+    V3 z = cross3(w2, a);
+    const double P[3] = {1.0, X, X * X};
+    const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        y[k] = P[k] * wsum.x;
+        y[3 + k] = P[k] * wsum.y;
+        y[6 + k] = P[k] * wsum.z;
+        y[9 + k] = P[k] * m32.x - S[k] * z.x;
+        y[12 + k] = S31e[k] * z.x;
+    }
+}
+
+// section 3 (static.py:438-452); y = intc3 (dof of the last tube)
+__device__ __noinline__ void node_sec3(const StModel& sm, const StCfg& c, QV q, int i, double y[CTRB_MAX_DOF]) {
+    const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
+    const int q33 = sm.qoff[5];
+    double B[3][CTRB_MAX_DOF];
+    strain_base_rows(sm.mc.kind[T - 1], dof, (i + c.i33) * sm.mc.dx, B);
+    double m[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < dof; ++k) {
+            a += B[r][k] * q(q33 + k);
+            b += B[r][k] * sm.mc.q[T - 1][k];
+        }
+        m[r] = sm.Kr[T - 1][r] * (a - b);
+    }
+    for (int k = 0; k < dof; ++k) y[k] = B[0][k] * m[0] + B[1][k] * m[1] + B[2][k] * m[2];
+}
+
+__device__ __noinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+__device__ __noinline__ double st_enorm_full(int n, const double* x) {
+    // MINPACK enorm with its three scaled accumulators (only reached outside the intermediate range)
+    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+    double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
+    const double agiant = rgiant / (double)n;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const double xabs = fabs(x[i]);
+        if (xabs > rdwarf && xabs < agiant) {
+            s2 += xabs * xabs;
+        } else if (xabs <= rdwarf) {
+            if (xabs > x3max) {
+                const double rr = x3max / xabs;
+                s3 = 1 + s3 * rr * rr;
+                x3max = xabs;
+            } else if (xabs != 0) {
+                const double rr = xabs / x3max;
+                s3 += rr * rr;
+            }
+        } else {
+            if (xabs > x1max) {
+                const double rr = x1max / xabs;
+                s1 = 1 + s1 * rr * rr;
+                x1max = xabs;
+            } else {
+                const double rr = xabs / x1max;
+                s1 += rr * rr;
+            }
+        }
+    }
+    if (s1 != 0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0) {
+        if (s2 >= x3max) return sqrt(s2 * (1 + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    }
+    return x3max * sqrt(s3);
+}
+
+// MINPACK enorm of a length-n vector held one element per lane (v = 0 in lanes >= n).  In the
+// intermediate range the routine is sqrt(sum x^2); the warp tree-sum only changes the order of the adds.
+__device__ __noinline__ double enorm_w(int n, double v, const double* x_smem_or_null) {
+    const double xabs = fabs(v);
+    const bool odd = (xabs >= 1.304e19 / (double)n) || (xabs <= 3.834e-20 && xabs != 0.0);
+    if (__any_sync(0xffffffffu, odd) && x_smem_or_null) return st_enorm_full(n, x_smem_or_null);
+    return sqrt(warp_sum(xabs * xabs));
+}
+
+// Cooperative residual, phase 1: work item t in 0..11 = (section, abscissa, bracket end) evaluates one node
+// integrand vector into y (shared memory).  q is a shared-memory vector of the unknowns.
+__device__ __noinline__ void res_node(const StModel& sm, const StCfg& c, QV q, int t, double* y) {
+    const int T = sm.mc.T;
+    const int sec = t >> 2, a = (t >> 1) & 1, e = t & 1;
+    if (c.len[sec] > 0.0 && (sec != 0 || T == 3)) {
+        const int node = e ? c.hi[sec][a] : c.lo[sec][a];
+        if (sec == 0) {
+            node_sec1(sm, c, q, node, y);
+        } else if (sec == 1) {
+            double s31e = 0.0, c31e = 1.0, S31e[3] = {0.0, 0.0, 0.0};
+            if (T == 3) {  // final relative frame / basis integral of tube 3 over section 1 (equilibrium_three's return)
+                const double Xe = (c.L[0] - 1) * sm.mc.dx;
+                sincos_ni(c.th[2] + ipoly3v(q, sm.qoff[2], Xe), &s31e, &c31e);
+                S31e[0] = Xe;
+                S31e[1] = 0.5 * Xe * Xe;
+                S31e[2] = Xe * Xe * Xe * (1.0 / 3.0);
+            }
+            node_sec2(sm, c, q, node, s31e, c31e, S31e, y);
+        } else {
+            node_sec3(sm, c, q, node, y);
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) y[k] = 0.0;
+    }
+}
+
+// phase 2: component k of F from the 12 node vectors (calculate_integral, static.py:456-491)
+__device__ __noinline__ double res_assemble(const StModel& sm, const StCfg& c, const double (*yb)[16], int comp) {
+    int blk = 0;  // order (1,1),(2,1),(3,1),(2,2),(3,2),(3,3)
+#pragma unroll
+    for (int b = 1; b < 6; ++b)
+        if (comp >= sm.qoff[b] && sm.ndof[b] > 0) blk = b;
+    const int k = comp - sm.qoff[blk];
+    const int sec = blk < 3 ? 0 : (blk < 5 ? 1 : 2);
+    const int yo = (blk == 0 || blk == 3 || blk == 5) ? 0 : ((blk == 1 || blk == 4) ? 9 : 12);
+    double acc = 0.0;
+    if (c.len[sec] > 0.0) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const double ylo = yb[sec * 4 + a * 2 + 0][yo + k], yhi = yb[sec * 4 + a * 2 + 1][yo + k];
+            acc += 0.5 * (((yhi - ylo) / c.dxs[sec][a]) * c.dxn[sec][a] + ylo);
+        }
+    }
+    double val = (c.len[sec] / 2) * acc;
+    if (blk == 2) {  // intg_31 - intg_312: the section-2 share lives at offset 12 of the section-2 vectors
+        double acc2 = 0.0;
+        if (c.len[1] > 0.0) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const double ylo = yb[4 + a * 2 + 0][12 + k], yhi = yb[4 + a * 2 + 1][12 + k];
+                acc2 += 0.5 * (((yhi - ylo) / c.dxs[1][a]) * c.dxn[1][a] + ylo);
+            }
+        }
+        val -= (c.len[1] / 2) * acc2;
+    }
+    return val;
+}
+
+// ------------------------------------------------------------------ curve integration (integrate_g)
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+
+// half_step_integral for a tube==section basis (with bias): the Magnus exponential of one step.
+// wA, wB = omega at the two Gauss points; v = e_x at both.
+__device__ __noinline__ SE3 magnus_step(const double wA[3], const double wB[3], double dx) {
+    const double cf = (sqrt(3.0) * dx * dx) / 12;
+    // Gamma = dx/2 (xi1^ + xi2^) + cf [xi2^, xi1^];  [.,.] = (w2 x w1, w2 x v1 - w1 x v2), v1 = v2 = e_x
+    V3 a = {wA[0], wA[1], wA[2]}, b = {wB[0], wB[1], wB[2]};
+    V3 cw = cross3(b, a);
+    V3 d = {b.x - a.x, b.y - a.y, b.z - a.z};
+    V3 cv = cross3(d, V3{1.0, 0.0, 0.0});
+    double w[3] = {(dx / 2) * (a.x + b.x) + cf * cw.x, (dx / 2) * (a.y + b.y) + cf * cw.y, (dx / 2) * (a.z + b.z) + cf * cw.z};
+    double v[3] = {(dx / 2) * 2.0 + cf * cv.x, cf * cv.y, cf * cv.z};
+    return se3_exp(w, v, 1.0);
+}
+
+// omega of the (tube==section) basis at absolute section coordinate `sidx` (static_bases.py:61-81)
+__device__ __noinline__ void sect_omega(const StModel& sm, const StCfg& c, const double* qs, int sect, double sidx,
+                                           double w[3]) {
+    const double dx = sm.mc.dx;
+    if (sect == 3) {
+        const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
+        double B[3][CTRB_MAX_DOF];
+        strain_base_rows(sm.mc.kind[T - 1], dof, (sidx + c.i33) * dx, B);  // _easy_last_basis adds idx33 (again)
+        for (int r = 0; r < 3; ++r) {
+            double a = 0.0;
+            for (int k = 0; k < dof; ++k) a += B[r][k] * qs[k];
+            w[r] = a;
+        }
+    } else {
+        const double x = sidx * dx;
+        w[0] = poly3(qs, x);
+        w[1] = poly3(qs + 3, x);
+        w[2] = poly3(qs + 6, x);
+    }
+}
+
+// Writes `count` nodes of one section curve: node 0 = g0, node k = g0 * E_1 ... E_k with
+// E_k the Magnus step at absolute index start + k.  Returns the last node (all lanes).
+__device__ __noinline__ SE3 integrate_section(const StModel& sm, const StCfg& c, const double* qs, int sect, int start, int count,
+                                 SE3 g0, double* out, int lane) {
+    const double dx = sm.mc.dx;
+    const double cg1 = 0.5 - sqrt(3.0) / 6, cg2 = 0.5 + sqrt(3.0) / 6;  // static.py:597-599
+    if (lane == 0 && out) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            out[r * 4 + 0] = g0.r[r * 3 + 0];
+            out[r * 4 + 1] = g0.r[r * 3 + 1];
+            out[r * 4 + 2] = g0.r[r * 3 + 2];
+            out[r * 4 + 3] = g0.p[r];
+        }
+        out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;
+    }
+    SE3 carry = g0;
+    for (int base = 1; base < count; base += 32) {
+        const int k = base + lane;
+        SE3 e;
+        se3_identity(e);
+        if (k < count) {
+            const double si = (double)(start + k);
+            double wA[3], wB[3];
+            sect_omega(sm, c, qs, sect, si + cg1 - 1, wA);
+            sect_omega(sm, c, qs, sect, si + cg2 - 1, wB);
+            e = magnus_step(wA, wB, dx);
+        }
+        // inclusive scan of SE(3) products across lanes (Hillis-Steele)
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            SE3 o;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) o.r[t] = shfl_up_d(e.r[t], off);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) o.p[t] = shfl_up_d(e.p[t], off);
+            if (lane >= off) e = se3_mul(o, e);
+        }
+        SE3 g = se3_mul(carry, e);
+        if (k < count && out) {
+            double* dst = out + (size_t)k * 16;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                dst[r * 4 + 0] = g.r[r * 3 + 0];
+                dst[r * 4 + 1] = g.r[r * 3 + 1];
+                dst[r * 4 + 2] = g.r[r * 3 + 2];
+                dst[r * 4 + 3] = g.p[r];
+            }
+            dst[12] = 0; dst[13] = 0; dst[14] = 0; dst[15] = 1;
+        }
+        const int last = min(31, count - 1 - base);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) carry.r[t] = shfl_d(g.r[t], last);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) carry.p[t] = shfl_d(g.p[t], last);
+    }
+    return carry;
+}
+
+__device__ __forceinline__ SE3 se3_rx(double angle) {
+    SE3 g;
+    se3_identity(g);
+    double s, c;
+    sincos_ni(angle, &s, &c);
+    g.r[4] = c; g.r[5] = -s; g.r[7] = s; g.r[8] = c;
+    return g;
+}
+
+// integral of q.(1,x,x^2) over the ABSOLUTE interval integrate_g walks (static.py:192-195)
+__device__ __forceinline__ double ipoly3_abs(const double* q, double a, double b) { return ipoly3(q, b) - ipoly3(q, a); }
+
+// Static.solve_g's curve assembly (static.py:110-130) from a solved q (shared-memory vector): the whole warp
+// writes the T section curves of configuration b into the packed g_out.
+__device__ __noinline__ void st_write_curves(const StModel& sm, const StCfg& c, const double* q, const long long* offsets,
+                                             long long b, double* g_out, int lane) {
+    const int T = sm.mc.T;
+    const double dx = sm.mc.dx;
+    SE3 g11_last, g21_last, g31_last;
+    se3_identity(g11_last);
+    if (T == 3) {
+        g11_last = integrate_section(sm, c, q + sm.qoff[0], 1, c.i11, c.L[0], se3_rx(c.th[0]),
+                                     g_out + offsets[b * T + 0] * 16, lane);
+        g21_last = se3_rx(c.th[1] + ipoly3_abs(q + sm.qoff[1], c.i21 * dx, (c.i21 + c.L[0] - 1) * dx));
+        g31_last = se3_rx(c.th[2] + ipoly3_abs(q + sm.qoff[2], c.i31 * dx, (c.i31 + c.L[0] - 1) * dx));
+    } else {
+        g21_last = se3_rx(c.th[0]);  // static.py:114-118
+        g31_last = se3_rx(c.th[1]);
+    }
+    SE3 g22_last = integrate_section(sm, c, q + sm.qoff[3], 2, c.i22, c.L[1], se3_mul(g11_last, g21_last),
+                                     g_out + offsets[b * T + (T - 2)] * 16, lane);
+    SE3 g32_last = se3_rx(ipoly3_abs(q + sm.qoff[4], c.i32 * dx, (c.i32 + c.L[1] - 1) * dx));
+    integrate_section(sm, c, q + sm.qoff[5], 3, c.i33, c.L[2], se3_mul(se3_mul(g22_last, g31_last), g32_last),
+                      g_out + offsets[b * T + (T - 1)] * 16, lane);
+}
+
+}  // namespace
+}  // namespace ctrb

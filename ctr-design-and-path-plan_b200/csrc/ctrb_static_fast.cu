@@ -1,0 +1,480 @@
+// ctrb_static_fast.cu -- Static.solve_g's root find (static.py:102, scipy.optimize.root 'hybr') carried on the
+// explicit Jacobian and its inverse instead of MINPACK's QR factors.  One warp per configuration, sm_100a.
+//
+// hybrd's iteration only ever uses its factors J = Q R through four products (dogleg, hybrd, More/Garbow/Hillstrom):
+//     Gauss-Newton step  R^-1 Q^T f      = J^-1 f
+//     scaled gradient    R^T Q^T f / D   = J^T f / D
+//     |R g|, |Q^T f + R p|               = |J g|, |f + J p|       (Q is orthogonal)
+// and updates them with Broyden's rank-one formula J+ = J + u v^T.  Holding J and H = J^-1 explicitly and
+// updating H by Sherman-Morrison,  H+ = H - (H u)(v^T H) / (1 + v^T H u),  gives the same iterates in exact
+// arithmetic, and every step becomes a lane-parallel matrix-vector product (lane i owns row i / column i /
+// element i) with no serial Givens chain: r1updt + r1mpyq + the back substitution were 60 % of the QR kernel's
+// instructions (profiles/README.md).  On 700 random three-tube configurations the CPU restatement of this
+// variant follows the literal hybrd as closely as hybrd follows itself under a 1e-13 perturbation of its
+// initial guess.
+//
+// What it cannot do is MINPACK's treatment of a singular R (a zero diagonal is replaced by eps * |column|):
+// a one-step section makes two Jacobian columns identical.  The Gauss-Jordan inversion
+// detects that (pivot below 1e-12 of the column norm) and the configuration is appended to a fallback list
+// that static_solve_kernel -- the literal QR algorithm -- solves in the same launch sequence.
+//
+// The forward-difference Jacobian uses the block structure of the residual: perturbing an unknown of block
+// (tube, section) only changes the node integrands of that section (and of section 2 for the (3,1) torsion,
+// through the relative frame at the end of section 1), so a column needs 4 (or 8) node evaluations, not 12,
+// and the untouched entries are exact zeros either way.
+#include <algorithm>
+#include <cstring>
+
+#include "ctrb_static_common.cuh"
+
+namespace ctrb {
+
+constexpr int kFWarps = 4;   // warps (= configurations in flight) per block
+constexpr int kLD = 31;      // leading dimension, column-major: element (i, j) at i + j * kLD.  Odd, so both
+                             // "lane = row" (stride 1) and "lane = column" (stride 31) accesses are conflict-free
+constexpr unsigned kFull = 0xffffffffu;
+
+struct FastMem {
+    double J[kLD * kMaxNq];
+    double H[kLD * kMaxNq + 34];  // + slack: lanes 30, 31 read (and discard) one column past the end
+    double x[32], f[32], va[32], vb[32], vc[32];
+    double y[12][16];             // node integrands of the most recent residual
+    StCfg cfg;
+    // during the forward-difference Jacobian H is dead (it is rebuilt from J right after) and holds the node
+    // integrands of 8 column slots x 4 nodes
+    __device__ double (*ybuf())[16] { return reinterpret_cast<double(*)[16]>(H); }
+};
+
+// per-lane description of residual row `lane` (which block of static.py:63 it belongs to)
+struct RowMeta {
+    int blk, k, sec, yo;
+};
+
+__device__ __forceinline__ RowMeta row_meta(const StModel& sm, int comp) {
+    RowMeta r;
+    r.blk = 0;
+#pragma unroll
+    for (int b = 1; b < 6; ++b)
+        if (comp >= sm.qoff[b] && sm.ndof[b] > 0) r.blk = b;
+    r.k = comp - sm.qoff[r.blk];
+    r.sec = r.blk < 3 ? 0 : (r.blk < 5 ? 1 : 2);
+    r.yo = (r.blk == 0 || r.blk == 3 || r.blk == 5) ? 0 : ((r.blk == 1 || r.blk == 4) ? 9 : 12);
+    return r;
+}
+
+// calculate_integral (static.py:456-491) of one integrand component over one section: the four node values are
+// yb[base + 2 a + e][off] (a = Gauss abscissa, e = lower / upper bracketing node)
+__device__ __forceinline__ double asm_part(const StCfg& c, const double (*yb)[16], int base, int sec, int off) {
+    if (!(c.len[sec] > 0.0)) return 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const double ylo = yb[base + a * 2 + 0][off], yhi = yb[base + a * 2 + 1][off];
+        acc += 0.5 * (((yhi - ylo) / c.dxs[sec][a]) * c.dxn[sec][a] + ylo);
+    }
+    return (c.len[sec] / 2) * acc;
+}
+
+// y_i = sum_j M[i][j] v[j]: lane = row i, v broadcast from shared memory
+__device__ __forceinline__ double matvec_row(const double* M, const double* v, int n, int lane) {
+    const double* m = M + lane;
+    double a0 = 0.0, a1 = 0.0;
+    int j = 0;
+#pragma unroll 2
+    for (; j + 1 < n; j += 2) {
+        a0 = fma(m[j * kLD], v[j], a0);
+        a1 = fma(m[(j + 1) * kLD], v[j + 1], a1);
+    }
+    if (j < n) a0 = fma(m[j * kLD], v[j], a0);
+    return a0 + a1;
+}
+
+// y_j = sum_i M[i][j] v[i]: lane = column j
+__device__ __forceinline__ double matvec_col(const double* M, const double* v, int n, int lane) {
+    const double* m = M + lane * kLD;
+    double a0 = 0.0, a1 = 0.0;
+    int i = 0;
+#pragma unroll 2
+    for (; i + 1 < n; i += 2) {
+        a0 = fma(m[i], v[i], a0);
+        a1 = fma(m[i + 1], v[i + 1], a1);
+    }
+    if (i < n) a0 = fma(m[i], v[i], a0);
+    return a0 + a1;
+}
+
+__device__ __forceinline__ double wnorm(double v) { return sqrt(warp_sum(v * v)); }
+
+// F(q) by the whole warp: 12 node integrands (3 sections x 2 abscissae x 2 bracketing nodes), then one residual
+// component per lane.  Returns this lane's component; p1 / p2 are its section shares (row block (3,1) is
+// intg_31 - intg_312, static.py:250-252; p2 = 0 elsewhere).
+__device__ __forceinline__ double fast_residual(const StModel& sm, FastMem& M, const double* q, const RowMeta& rm, bool act,
+                                                int lane, double* p1, double* p2) {
+    if (lane < 12) res_node(sm, M.cfg, QV{q, -1, 0.0}, lane, M.y[lane]);
+    __syncwarp();
+    double a = 0.0, b = 0.0;
+    if (act) {
+        a = asm_part(M.cfg, M.y, rm.sec * 4, rm.sec, rm.yo + rm.k);
+        if (rm.blk == 2) b = asm_part(M.cfg, M.y, 4, 1, 12 + rm.k);
+    }
+    __syncwarp();
+    *p1 = a;
+    *p2 = b;
+    return rm.blk == 2 ? a - b : a;
+}
+
+// H = J^-1 by Gauss-Jordan exchange steps with implicit partial pivoting; lane = row.  Returns false when a
+// pivot falls below 1e-12 of its column norm (numerically singular Jacobian).
+__device__ __noinline__ bool fast_invert(FastMem& M, int n, double acnorm_l, int lane) {
+    const bool act = lane < n;
+    double* Tm = M.H;
+    for (int e = lane; e < kLD * n; e += 32) Tm[e] = M.J[e];
+    __syncwarp();
+    bool used = false;
+    int mycol = 0, prow = 0;  // lane r: column it pivoted; lane k: pivot row of column k
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) {
+        const double a = act ? Tm[lane + k * kLD] : 0.0;
+        const unsigned long long key = (act && !used) ? (unsigned long long)__double_as_longlong(fabs(a)) : 0ULL;
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mh = __reduce_max_sync(kFull, hi);
+        const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
+        const int r = __ffs(__ballot_sync(kFull, hi == mh && lo == ml && act && !used)) - 1;
+        const double thr = 1e-12 * __shfl_sync(kFull, acnorm_l, k);
+        const double piv = __shfl_sync(kFull, a, r < 0 ? 0 : r);
+        if (r < 0 || !(fabs(piv) > thr) || !(fabs(piv) < 1.7e308)) return false;
+        const double ipiv = 1.0 / piv;
+        const double m = (lane == r) ? 0.0 : a * ipiv;
+        if (act && lane != r) {
+            const double* pr = Tm + r;
+            double* tr = Tm + lane;
+#pragma unroll 2
+            for (int j = 0; j < n; ++j) tr[j * kLD] = fma(-m, pr[j * kLD], tr[j * kLD]);
+        }
+        __syncwarp();
+        if (act) Tm[r + lane * kLD] *= ipiv;  // lane = column j of the pivot row
+        __syncwarp();
+        if (act) Tm[lane + k * kLD] = (lane == r) ? ipiv : -m;
+        __syncwarp();
+        if (lane == r) {
+            used = true;
+            mycol = k;
+        }
+        if (lane == k) prow = r;
+    }
+    // unscramble: H[mycol(i)][prow(j)] = T[i][j]
+    double row[kMaxNq];
+#pragma unroll
+    for (int j = 0; j < kMaxNq; ++j) row[j] = (j < n && act) ? Tm[lane + j * kLD] : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kMaxNq; ++j) {
+        const int pj = __shfl_sync(kFull, prow, j);
+        if (j < n && act) M.H[mycol + pj * kLD] = row[j];
+    }
+    __syncwarp();
+    return true;
+}
+
+// column-slot table of the forward-difference Jacobian: slot = (unknown j, section whose 4 nodes are re-evaluated)
+struct SlotTable {
+    signed char j[48], sec[48], col_blk[32];
+    int nslots;
+};
+
+// forward-difference Jacobian (MINPACK fdjac1, dense band) using the block structure; f_l / p1b / p2b are this
+// lane's residual component at x and its section shares.  Writes M.J; returns this lane's column norm.
+__device__ __noinline__ double fast_fdjac(const StModel& sm, FastMem& M, const SlotTable& st, const RowMeta& rm, double f_l,
+                                          double p1b, double p2b, int lane) {
+    const int n = sm.nq;
+    const bool act = lane < n;
+    const double eps = sqrt(DBL_EPSILON);
+    double (*yb)[16] = M.ybuf();
+    for (int base = 0; base < st.nslots; base += 8) {
+        {
+            const int slot = base + (lane >> 2);
+            if (slot < st.nslots) {
+                const int j = st.j[slot];
+                const double xv = M.x[j];
+                double h = eps * fabs(xv);
+                if (h == 0.0) h = eps;
+                res_node(sm, M.cfg, QV{M.x, j, h}, st.sec[slot] * 4 + (lane & 3), yb[lane]);
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int s8 = 0; s8 < 8; ++s8) {
+            const int slot = base + s8;
+            if (slot >= st.nslots) break;
+            const int j = st.j[slot], sec = st.sec[slot];
+            const bool pair = st.col_blk[j] == 2;  // (3,1) torsion: sections 1 and 2 both move; slots (s, s + 1)
+            if (pair && sec == 1) continue;
+            if (act) {
+                const bool hit1 = rm.sec == sec || (pair && rm.sec == 1);
+                const bool hit2 = rm.blk == 2 && (sec == 1 || pair);
+                double val = 0.0;
+                if (hit1 || hit2) {
+                    const int b1 = (pair && rm.sec == 1) ? (s8 + 1) * 4 : s8 * 4;
+                    const double p1 = hit1 ? asm_part(M.cfg, yb, b1, rm.sec, rm.yo + rm.k) : p1b;
+                    double Fp = p1;
+                    if (rm.blk == 2) {
+                        const int b2 = pair ? (s8 + 1) * 4 : s8 * 4;
+                        const double p2 = hit2 ? asm_part(M.cfg, yb, b2, 1, 12 + rm.k) : p2b;
+                        Fp = p1 - p2;
+                    }
+                    const double xv = M.x[j];
+                    double h = eps * fabs(xv);
+                    if (h == 0.0) h = eps;
+                    val = (Fp - f_l) / h;
+                }
+                M.J[lane + j * kLD] = val;
+            }
+        }
+        __syncwarp();
+    }
+    double s2 = 0.0;
+    if (act) {
+        const double* m = M.J + lane * kLD;
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) s2 = fma(m[i], m[i], s2);
+    }
+    return sqrt(s2);
+}
+
+// returns MINPACK's info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress), or -1 when the
+// configuration has to go through the QR kernel
+__device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
+                                       double factor, int* nfev_out) {
+    const int n = sm.nq;
+    const bool act = lane < n;
+    const RowMeta rm = row_meta(sm, act ? lane : 0);
+    const double epsmch = DBL_EPSILON, p1c = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
+    double x_l = act ? M.x[lane] : 0.0;
+    double pa, pb;
+    double f_l = fast_residual(sm, M, M.x, rm, act, lane, &pa, &pb);
+    int nfev = 1, info = 0;
+    double fnorm = wnorm(f_l);
+    if (!(fnorm < 1.7e308)) return -1;
+    int iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
+    double delta = 0.0, xnorm = 0.0, diag_l = 1.0;
+#pragma unroll 1
+    for (;;) {
+        bool jeval = true;
+        const double acnorm_l = fast_fdjac(sm, M, st, rm, f_l, pa, pb, lane);
+        nfev += n;
+        if (!fast_invert(M, n, acnorm_l, lane)) return -1;
+        if (iter == 1) {
+            diag_l = acnorm_l == 0.0 ? 1.0 : acnorm_l;
+            xnorm = wnorm(act ? diag_l * x_l : 0.0);
+            delta = factor * xnorm;
+            if (delta == 0.0) delta = factor;
+        }
+        diag_l = fmax(diag_l, acnorm_l);
+        if (act) M.f[lane] = f_l;
+        __syncwarp();
+#pragma unroll 1
+        for (;;) {
+            // ---- dogleg (MINPACK): Gauss-Newton step H f, scaled gradient J^T f / D, their trust-region blend
+            const double xg = act ? matvec_row(M.H, M.f, n, lane) : 0.0;
+            const double qnorm = wnorm(diag_l * xg);
+            double step = xg;
+            if (!(qnorm <= delta)) {
+                double g = act ? matvec_col(M.J, M.f, n, lane) / diag_l : 0.0;
+                const double gnorm = wnorm(g);
+                double sgnorm = 0.0, alpha = delta / qnorm;
+                if (gnorm != 0.0) {
+                    g = act ? (g / gnorm) / diag_l : 0.0;
+                    if (act) M.va[lane] = g;
+                    __syncwarp();
+                    const double w2 = act ? matvec_row(M.J, M.va, n, lane) : 0.0;
+                    double temp = wnorm(w2);
+                    sgnorm = (gnorm / temp) / temp;
+                    alpha = 0.0;
+                    if (sgnorm < delta) {
+                        const double bnorm = fnorm;  // |Q^T f| = |f|
+                        temp = (bnorm / gnorm) * (bnorm / qnorm) * (sgnorm / delta);
+                        const double dq = delta / qnorm, sd = sgnorm / delta;
+                        temp = temp - dq * sd * sd + sqrt((temp - dq) * (temp - dq) + (1 - dq * dq) * (1 - sd * sd));
+                        alpha = (dq * (1 - sd * sd)) / temp;
+                    }
+                    __syncwarp();
+                }
+                const double temp = (1 - alpha) * fmin(sgnorm, delta);
+                step = temp * g + alpha * xg;
+            }
+            const double p_l = act ? -step : 0.0;
+            const double xt_l = x_l + p_l;
+            const double pnorm = wnorm(diag_l * p_l);
+            if (iter == 1) delta = fmin(delta, pnorm);
+            if (act) {
+                M.va[lane] = p_l;
+                M.vb[lane] = xt_l;
+            }
+            __syncwarp();
+            double qa, qb;
+            const double fn_l = fast_residual(sm, M, M.vb, rm, act, lane, &qa, &qb);
+            nfev++;
+            const double fnorm1 = wnorm(fn_l);
+            if (!(fnorm1 < 1.7e308) || !(pnorm < 1.7e308)) return -1;  // non-finite: let the QR kernel decide
+            double actred = -1.0;
+            if (fnorm1 < fnorm) actred = 1 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
+            const double w3 = act ? f_l + matvec_row(M.J, M.va, n, lane) : 0.0;  // f + J p
+            const double temp = wnorm(w3);
+            double prered = 0.0;
+            if (temp < fnorm) prered = 1 - (temp / fnorm) * (temp / fnorm);
+            double ratio = 0.0;
+            if (prered > 0) ratio = actred / prered;
+            if (ratio < p1c) {
+                ncsuc = 0;
+                ncfail++;
+                delta = p5 * delta;
+            } else {
+                ncfail = 0;
+                ncsuc++;
+                if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
+                if (fabs(ratio - 1) <= p1c) delta = pnorm / p5;
+            }
+            // Broyden vectors (hybrd: wa2 = (Q^T f+ - (Q^T f + R p)) / pnorm, wa1 = D ((D p) / pnorm))
+            const double u_l = act ? (fn_l - w3) / pnorm : 0.0;
+            const double v_l = act ? diag_l * ((diag_l * p_l) / pnorm) : 0.0;
+            if (ratio >= p0001) {  // successful iteration
+                x_l = xt_l;
+                f_l = fn_l;
+                pa = qa;
+                pb = qb;
+                if (act) {
+                    M.x[lane] = x_l;
+                    M.f[lane] = f_l;
+                }
+                xnorm = wnorm(act ? diag_l * x_l : 0.0);
+                fnorm = fnorm1;
+                iter++;
+            }
+            nslow1++;
+            if (actred >= p001) nslow1 = 0;
+            if (jeval) nslow2++;
+            if (actred >= p1c) nslow2 = 0;
+            if (delta <= xtol * xnorm || fnorm == 0) info = 1;
+            if (info == 0) {
+                if (nfev >= maxfev) info = 2;
+                if (p1c * fmax(p1c * delta, pnorm) <= epsmch * xnorm) info = 3;
+                if (nslow2 == 5) info = 4;
+                if (nslow1 == 10) info = 5;
+            }
+            __syncwarp();
+            if (info != 0) {
+                *nfev_out = nfev;
+                return info;
+            }
+            if (ncfail == 2) break;  // recompute the Jacobian
+            // ---- rank-one update of J and, by Sherman-Morrison, of H
+            if (act) {
+                M.vb[lane] = u_l;
+                M.vc[lane] = v_l;
+            }
+            __syncwarp();
+            const double Hu = act ? matvec_row(M.H, M.vb, n, lane) : 0.0;
+            const double vH = act ? matvec_col(M.H, M.vc, n, lane) : 0.0;
+            const double den = 1.0 + warp_sum(v_l * Hu);
+            if (!(fabs(den) > 1e-8) || !(fabs(den) < 1e100)) return -1;  // J+ is (numerically) singular
+            __syncwarp();
+            if (act) M.vb[lane] = vH;
+            __syncwarp();
+            if (act) {
+                const double hs = -Hu / den;
+                double* jr = M.J + lane;
+                double* hr = M.H + lane;
+#pragma unroll 2
+                for (int j = 0; j < n; ++j) {
+                    jr[j * kLD] = fma(u_l, M.vc[j], jr[j * kLD]);
+                    hr[j * kLD] = fma(hs, M.vb[j], hr[j * kLD]);
+                }
+            }
+            __syncwarp();
+            jeval = false;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFWarps * 32, 3)
+    static_fast_kernel(StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
+                       const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
+                       double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
+                       int32_t* __restrict__ info_out, long long* __restrict__ fb_list,
+                       unsigned long long* __restrict__ fb_count, unsigned long long* __restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SlotTable st;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FastMem& M = reinterpret_cast<FastMem*>(smem_raw)[warp];
+    const int T = sm.mc.T, n = sm.nq;
+    if (threadIdx.x == 0) {
+        int ns = 0;
+        for (int b = 0; b < 6; ++b)
+            for (int k = 0; k < sm.ndof[b]; ++k) st.col_blk[sm.qoff[b] + k] = (signed char)b;
+        // the two-slot columns first, so that a pair never straddles a round of 8 slots
+        for (int k = 0; k < sm.ndof[2]; ++k)
+            for (int s = 0; s < 2; ++s) {
+                st.j[ns] = (signed char)(sm.qoff[2] + k);
+                st.sec[ns++] = (signed char)s;
+            }
+        for (int b = 0; b < 6; ++b) {
+            if (b == 2) continue;
+            for (int k = 0; k < sm.ndof[b]; ++k) {
+                st.j[ns] = (signed char)(sm.qoff[b] + k);
+                st.sec[ns++] = (signed char)(b < 3 ? 0 : (b < 5 ? 1 : 2));
+            }
+        }
+        st.nslots = ns;
+    }
+    __syncthreads();
+    for (;;) {
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1ULL);
+        const long long b = (long long)__shfl_sync(kFull, tk, 0);
+        if (b >= B) break;
+        if (lane == 0) st_setup(sm, idx + b * T, theta + b * T, M.cfg);
+        M.x[lane] = lane < n ? (x0 ? x0[(x0_per_config ? b * n : 0) + lane] : sm.x0[lane]) : 0.0;
+        M.f[lane] = 0.0;
+        M.va[lane] = 0.0;
+        M.vb[lane] = 0.0;
+        M.vc[lane] = 0.0;
+        __syncwarp();
+        const StCfg& c = M.cfg;
+        // zero-length sections make whole residual blocks vanish (static.py:478-479): singular by construction
+        // and a one-step section 1 or 2 gives the x and x^2 curvature coefficients identical columns
+        const bool degenerate = (T == 3 && c.L[0] < 3) || c.L[1] < 3 || c.L[2] < 2;
+        int nfev = 0;
+        const int info = degenerate ? -1 : fast_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, &nfev);
+        __syncwarp();
+        if (info < 0) {
+            if (lane == 0) fb_list[atomicAdd(fb_count, 1ULL)] = b;
+            continue;
+        }
+        if (sol_out && lane < n) sol_out[b * n + lane] = M.x[lane];
+        if (lane == 0) {
+            if (nfev_out) nfev_out[b] = nfev;
+            if (info_out) info_out[b] = info;
+        }
+        if (g_out) st_write_curves(sm, c, M.x, offsets, b, g_out, lane);
+        __syncwarp();
+    }
+}
+
+int launch_static_fast(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
+                       const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
+                       double* sol_out, int32_t* nfev_out, int32_t* info_out, long long* fb_list,
+                       unsigned long long* fb_count, unsigned long long* ticket) {
+    const size_t smem = sizeof(FastMem) * kFWarps;
+    CTRB_CUDA(cudaFuncSetAttribute(static_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, static_fast_kernel, kFWarps * 32, smem));
+    const long long blocks_needed = (B + kFWarps - 1) / kFWarps;
+    const int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * std::max(per_sm, 1));
+    static_fast_kernel<<<grid, kFWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out,
+                                                                 sol_out, nfev_out, info_out, fb_list, fb_count, ticket);
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
+    return CTRB_OK;
+}
+
+}  // namespace ctrb

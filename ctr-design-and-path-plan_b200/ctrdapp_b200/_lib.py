@@ -59,6 +59,7 @@ SYMBOLS = {
     "ctrb_ctx_mark": (C.c_int, [_vp, C.c_int]),
     "ctrb_ctx_elapsed_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ctrb_ctx_last_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
+    "ctrb_static_last_fallbacks": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "ctrb_ctx_work_counters": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "ctrb_model_create": (C.c_int, [_vp, C.POINTER(ModelDesc), C.POINTER(_vp)]),
     "ctrb_model_destroy": (None, [_vp]),
@@ -184,12 +185,17 @@ class Context:
         check(lib().ctrb_ctx_elapsed_ms(self._h, C.byref(ms)))
         return ms.value
 
-    KERNELS = {"chain_eval": 0, "static_solve": 1, "gcurve": 2, "eta_ftl": 3}
+    KERNELS = {"chain_eval": 0, "static_solve": 1, "gcurve": 2, "eta_ftl": 3, "static_fast": 4}
 
     def last_kernel_ms(self, name):
         ms = C.c_float()
         check(lib().ctrb_ctx_last_kernel_ms(self._h, self.KERNELS[name], C.byref(ms)))
         return ms.value
+
+    def static_fallbacks(self):
+        n = C.c_uint64()
+        check(lib().ctrb_static_last_fallbacks(self._h, C.byref(n)))
+        return int(n.value)
 
     def work_counters(self):
         out = (C.c_uint64 * 4)()

@@ -140,7 +140,8 @@ typedef enum {
     CTRB_KERNEL_CHAIN_EVAL = 0,   /* chain_eval_kernel (fused or given curves) */
     CTRB_KERNEL_STATIC_SOLVE = 1, /* static_solve_kernel */
     CTRB_KERNEL_GCURVE = 2,       /* kin_gcurve_kernel */
-    CTRB_KERNEL_ETA_FTL = 3       /* kin_eta_ftl_kernel */
+    CTRB_KERNEL_ETA_FTL = 3,      /* kin_eta_ftl_kernel */
+    CTRB_KERNEL_STATIC_FAST = 4   /* static_fast_kernel alone (STATIC_SOLVE spans it and the QR kernel) */
 } ctrb_kernel_id;
 int ctrb_ctx_last_kernel_ms(ctrb_ctx* ctx, int kernel_id, float* ms);
 
@@ -207,6 +208,9 @@ int ctrb_eta_ftl_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int3
  *      reports 2 more), info [B] (MINPACK info: 1 = converged -- what solution.success means) may be NULL. ---- */
 int ctrb_static_num_unknowns(const ctrb_model* m, int32_t* nq);
 int ctrb_static_initial_guess(const ctrb_model* m, double* x0 /*[nq], host*/);
+/* configurations of the most recent static solve on this ctx that the explicit-inverse kernel handed to the
+ * QR kernel (singular Jacobian: one-step / zero-length sections).  Synchronises. */
+int ctrb_static_last_fallbacks(ctrb_ctx* ctx, uint64_t* count);
 int ctrb_static_residual_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx /*[B][T]*/,
                                const double* theta /*[B][T]*/, const double* q /*[B][nq]*/, double* F /*[B][nq]*/,
                                int mem);
