@@ -66,6 +66,7 @@ int launch_eval_curves_cost(ctrb_ctx* ctx, const ctrb_env* env, const ctrb_cost_
                             double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide);
 int launch_fma_peak(ctrb_ctx* ctx, int precision, double* tflops);
 int static_model_init(const ctrb_model_desc* d, const ModelConst& mc, StModel* out);
+int launch_static_tables(ctrb_ctx* ctx, ctrb_model* m);
 int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
                         const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
                         double* sol_out, int32_t* nfev_out, int32_t* info_out);
@@ -325,6 +326,7 @@ int ctrb_model_create(ctrb_ctx* ctx, const ctrb_model_desc* d, ctrb_model** out)
     CTRB_CUDA(cudaMalloc(&m->d_tab_inv, (size_t)12 * tot * sizeof(double)));
     CTRB_CUDA(cudaMalloc(&m->d_tabR32, (size_t)9 * tot * sizeof(float)));
     int rc = launch_table(ctx, m);
+    if (rc == CTRB_OK && m->is_static) rc = launch_static_tables(ctx, m);
     if (rc) {
         ctrb_model_destroy(m);
         return rc;
@@ -340,6 +342,8 @@ void ctrb_model_destroy(ctrb_model* m) {
     cudaFree(m->d_tab);
     cudaFree(m->d_tab_inv);
     cudaFree(m->d_tabR32);
+    cudaFree(m->d_ws_tab);
+    cudaFree(m->d_b3_tab);
     delete m;
 }
 

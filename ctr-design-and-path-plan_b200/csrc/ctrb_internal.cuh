@@ -62,6 +62,11 @@ struct StModel {
     int ndof[6];                   // order (1,1),(2,1),(3,1),(2,2),(3,2),(3,3)  (static.py:63)
     int qoff[6];
     double x0[kStaticMaxNq];       // get_init_vals (static_bases.py:142-168)
+    // per-design tables (device memory, built once at ctrb_model_create by static_tables_kernel):
+    const double* ws_tab;          // [total_nodes][3]: omega of the tube's own pre-curvature ksi* at node j (get_ksi_star)
+    const double* b3_tab;          // [npts_last][CTRB_MAX_DOF + 3]: last tube's strain base at node j, one value per
+                                   // column (every base has one non-zero per column), then (B q*)[0:3]
+    int b3_row[CTRB_MAX_DOF];      // the row of that non-zero
 };
 
 }  // namespace ctrb
@@ -91,6 +96,8 @@ struct ctrb_model {
     float* d_tabR32;
     int is_static;
     ctrb::StModel sm;
+    double* d_ws_tab;
+    double* d_b3_tab;
     ctrb::ModelTables tables() const { return ctrb::ModelTables{d_tab, d_tab_inv, d_tabR32}; }
 };
 

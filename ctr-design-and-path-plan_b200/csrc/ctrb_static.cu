@@ -34,7 +34,7 @@ constexpr int kNV = 32;       // padded vector length
 __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, const double* qp, double* F) {
     const int T = sm.mc.T;
     const QV q = {qp, -1, 0.0};
-    double s31e = 0.0, c31e = 1.0, S31e[3] = {0.0, 0.0, 0.0};
+    double s31e = 0.0, c31e = 1.0, Xe31 = 0.0;
     double F31[3] = {0.0, 0.0, 0.0};
     if (T == 3) {
         double acc[15];
@@ -46,9 +46,8 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
                 double y2[2][15];
 #pragma unroll 1
                 for (int e = 0; e < 2; ++e) node_sec1(sm, c, q, e ? c.hi[0][a] : c.lo[0][a], y2[e]);
-                const double inv = 1.0 / c.dxs[0][a];
 #pragma unroll 1
-                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * (((y2[1][k] - y2[0][k]) * inv) * c.dxn[0][a] + y2[0][k]);
+                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * ((y2[1][k] - y2[0][k]) * c.wq[0][a] + y2[0][k]);
             }
         }
         const double h = c.len[0] / 2;
@@ -57,10 +56,10 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
         for (int k = 0; k < 3; ++k) F31[k] = h * acc[12 + k];
         // final relative frame / basis integral of tube 3 over section 1 (equilibrium_three's return)
         const double Xe = (c.L[0] - 1) * sm.mc.dx;
-        sincos_ni(c.th[2] + ipoly3(qp + sm.qoff[2], Xe), &s31e, &c31e);
-        S31e[0] = Xe;
-        S31e[1] = 0.5 * Xe * Xe;
-        S31e[2] = Xe * Xe * Xe * (1.0 / 3.0);
+        const SinCos r31 = sincos_ni(c.th[2] + ipoly3(qp + sm.qoff[2], Xe));
+        s31e = r31.s;
+        c31e = r31.c;
+        Xe31 = Xe;
     }
     {
         double acc[15];
@@ -71,10 +70,9 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
             for (int a = 0; a < 2; ++a) {
                 double y2[2][15];
 #pragma unroll 1
-                for (int e = 0; e < 2; ++e) node_sec2(sm, c, q, e ? c.hi[1][a] : c.lo[1][a], s31e, c31e, S31e, y2[e]);
-                const double inv = 1.0 / c.dxs[1][a];
+                for (int e = 0; e < 2; ++e) node_sec2(sm, c, q, e ? c.hi[1][a] : c.lo[1][a], s31e, c31e, Xe31, y2[e]);
 #pragma unroll 1
-                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * (((y2[1][k] - y2[0][k]) * inv) * c.dxn[1][a] + y2[0][k]);
+                for (int k = 0; k < 15; ++k) acc[k] += 0.5 * ((y2[1][k] - y2[0][k]) * c.wq[1][a] + y2[0][k]);
             }
         }
         const double h = c.len[1] / 2;
@@ -93,9 +91,8 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
                 double y2[2][CTRB_MAX_DOF];
 #pragma unroll 1
                 for (int e = 0; e < 2; ++e) node_sec3(sm, c, q, e ? c.hi[2][a] : c.lo[2][a], y2[e]);
-                const double inv = 1.0 / c.dxs[2][a];
 #pragma unroll 1
-                for (int k = 0; k < dof; ++k) acc[k] += 0.5 * (((y2[1][k] - y2[0][k]) * inv) * c.dxn[2][a] + y2[0][k]);
+                for (int k = 0; k < dof; ++k) acc[k] += 0.5 * ((y2[1][k] - y2[0][k]) * c.wq[2][a] + y2[0][k]);
             }
         }
         const double h = c.len[2] / 2;
@@ -556,6 +553,36 @@ __global__ void static_residual_kernel(StModel sm, long long B, const int32_t* _
     for (int k = 0; k < sm.nq; ++k) F[b * sm.nq + k] = Fl[k];
 }
 
+// per-design tables of StModel: one thread per node
+__global__ void static_tables_kernel(StModel sm, double* __restrict__ ws, double* __restrict__ b3) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int T = sm.mc.T;
+    if (j < sm.mc.total_nodes) {
+        int n = 0;
+        while (n + 1 < T && j >= sm.mc.node_base[n + 1]) ++n;
+        double w[3];
+        strain_omega(sm.mc, n, (j - sm.mc.node_base[n]) * sm.mc.dx, w);  // get_ksi_star: index * delta_x
+        ws[3 * j + 0] = w[0];
+        ws[3 * j + 1] = w[1];
+        ws[3 * j + 2] = w[2];
+    }
+    if (j < sm.mc.npts[T - 1]) {
+        const int dof = sm.mc.dof[T - 1];
+        double* o = b3 + (CTRB_MAX_DOF + 3) * j;
+        double bq[3] = {0.0, 0.0, 0.0};
+        for (int k = 0; k < CTRB_MAX_DOF; ++k) {
+            int r = 1;
+            double v = 0.0;
+            if (k < dof) strain_base_col(sm.mc.kind[T - 1], dof, k, j * sm.mc.dx, &r, &v);
+            o[k] = v;
+            if (k < dof) bq[r] += v * sm.mc.q[T - 1][k];
+        }
+        o[CTRB_MAX_DOF + 0] = bq[0];
+        o[CTRB_MAX_DOF + 1] = bq[1];
+        o[CTRB_MAX_DOF + 2] = bq[2];
+    }
+}
+
 // ------------------------------------------------------------------ host side
 int static_model_init(const ctrb_model_desc* d, const ModelConst& mc, StModel* out) {
     StModel sm;
@@ -596,7 +623,25 @@ int static_model_init(const ctrb_model_desc* d, const ModelConst& mc, StModel* o
     const int first = o - nd[5];  // static_bases.py:142-168
     for (int k = 0; k < first; ++k) sm.x0[k] = (k % da == 0) ? 0.01 : 0.0;
     for (int k = 0; k < nd[5]; ++k) sm.x0[first + k] = mc.q[T - 1][k];
+    for (int k = 0; k < CTRB_MAX_DOF; ++k) {
+        int r = 1;
+        double v = 0.0;
+        if (k < mc.dof[T - 1]) strain_base_col(mc.kind[T - 1], mc.dof[T - 1], k, 1.0, &r, &v);
+        sm.b3_row[k] = r;
+    }
     *out = sm;
+    return CTRB_OK;
+}
+
+int launch_static_tables(ctrb_ctx* ctx, ctrb_model* m) {
+    const int tot = m->mc.total_nodes, T = m->mc.T;
+    CTRB_CUDA(cudaMalloc(&m->d_ws_tab, (size_t)tot * 3 * sizeof(double)));
+    CTRB_CUDA(cudaMalloc(&m->d_b3_tab, (size_t)m->mc.npts[T - 1] * (CTRB_MAX_DOF + 3) * sizeof(double)));
+    m->sm.ws_tab = m->d_ws_tab;
+    m->sm.b3_tab = m->d_b3_tab;
+    static_tables_kernel<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(m->sm, m->d_ws_tab, m->d_b3_tab);
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
     return CTRB_OK;
 }
 

@@ -21,7 +21,7 @@ struct StCfg {
     double th[3];
     // calculate_integral's two abscissae per section: bracketing nodes and interpolation terms
     int lo[3][2], hi[3][2];
-    double dxs[3][2], dxn[3][2], len[3];
+    double wq[3][2], len[3];  // (x_new - x_lo) / (x_hi - x_lo) of interp1d at the two abscissae; section length
 };
 
 // ------------------------------------------------------------------ small helpers
@@ -37,52 +37,58 @@ __device__ __forceinline__ double ipoly3(const double* q, double X) {
     return q[0] * X + q[1] * (0.5 * X * X) + q[2] * (X * X * X * (1.0 / 3.0));
 }
 
-// one out-of-line copy each of the fp64 sincos and of the strain-base switch: the solve kernel is
-// instruction-cache bound if these are inlined at every use (ncu: stall_no_instruction 17 per issue)
-__device__ __noinline__ void sincos_ni(double a, double* s, double* c) { sincos(a, s, c); }
-__device__ __noinline__ void strain_omega_ni(const ModelConst& mc, int n, double x, double w[3]) { strain_omega(mc, n, x, w); }
+// one out-of-line copy of the fp64 sincos: the solve kernels are instruction-cache bound if it is inlined at
+// every use (ncu: stall_no_instruction is the top stall); results come back in registers
+struct SinCos {
+    double s, c;
+};
+__device__ __noinline__ SinCos sincos_ni(double a) {
+    SinCos r;
+    sincos(a, &r.s, &r.c);
+    return r;
+}
 
-// rows 0..2 of a strain base as a 3 x dof matrix (strain_bases.py:7-224)
-__device__ __noinline__ void strain_base_rows(int kind, int dof, double x, double B[3][CTRB_MAX_DOF]) {
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int k = 0; k < CTRB_MAX_DOF; ++k) B[r][k] = 0.0;
+// one non-zero per column of a strain base (strain_bases.py:7-224): its row (0..2) and its value at x
+__host__ __device__ __forceinline__ void strain_base_col(int kind, int dof, int k, double x, int* row, double* val) {
+    int r = 1;
+    double v = 1.0;
     switch (kind) {
-        case CTRB_BASE_CONSTANT: B[1][0] = 1.0; break;
+        case CTRB_BASE_CONSTANT: break;
         case CTRB_BASE_LINEAR:
-            B[1][0] = 1.0;
-            if (dof > 2) B[1][1] = x;
-            B[2][dof - 1] = x;
+            if (k == dof - 1) { r = 2; v = x; } else if (k == 1) { v = x; }
             break;
         case CTRB_BASE_QUADRATIC:
-            B[1][0] = 1.0;
-            if (dof > 2) B[1][1] = x * x;
-            B[2][dof - 1] = x * x;
+            if (k == dof - 1) { r = 2; v = x * x; } else if (k == 1) { v = x * x; }
             break;
-        case CTRB_BASE_PURE_HELIX: { double sn, cs; sincos_ni(x / 10, &sn, &cs); B[1][0] = sn; B[2][1] = cs; break; }
-        case CTRB_BASE_LINEAR_HELIX: { double sn, cs; sincos_ni(x / 10, &sn, &cs); B[1][0] = sn; B[2][1] = x * cs; break; }
-        case CTRB_BASE_TORSION_HELIX: B[0][0] = 1.0; B[1][1] = 1.0; B[2][2] = 1.0; break;
-        case CTRB_BASE_TORSION_LINEAR_HELIX: B[0][0] = 1.0; B[1][1] = 1.0; B[2][2] = x; break;
+        case CTRB_BASE_PURE_HELIX:
+            if (k == 0) { v = sin(x / 10); } else { r = 2; v = cos(x / 10); }
+            break;
+        case CTRB_BASE_LINEAR_HELIX:
+            if (k == 0) { v = sin(x / 10); } else { r = 2; v = x * cos(x / 10); }
+            break;
+        case CTRB_BASE_TORSION_HELIX: r = k; break;
+        case CTRB_BASE_TORSION_LINEAR_HELIX:
+            r = k;
+            if (k == 2) v = x;
+            break;
         case CTRB_BASE_FULL: {
-            int bs = (dof & 1) ? 1 : 2;
-            B[0][0] = 1.0;
-            if (!(dof & 1)) B[0][1] = x;
-            B[1][bs] = 1.0;
-            B[1][bs + 1] = x;
-            if (dof <= 6) {
-                B[2][bs + 2] = 1.0;
-                B[2][bs + 3] = x;
+            const int bs = (dof & 1) ? 1 : 2;  // torsion columns
+            const int nb = (dof - bs) / 2;     // columns per bending direction (2 or 3)
+            if (k < bs) {
+                r = 0;
+                v = k == 0 ? 1.0 : x;
             } else {
-                B[1][bs + 2] = x * x;
-                B[2][bs + 3] = 1.0;
-                B[2][bs + 4] = x;
-                B[2][bs + 5] = x * x;
+                const int kk = k - bs;
+                r = kk < nb ? 1 : 2;
+                const int pw = kk < nb ? kk : kk - nb;
+                v = pw == 0 ? 1.0 : (pw == 1 ? x : x * x);
             }
             break;
         }
         default: break;
     }
+    *row = r;
+    *val = v;
 }
 
 // ------------------------------------------------------------------ per-configuration setup
@@ -107,8 +113,7 @@ __device__ __noinline__ void st_setup(const StModel& sm, const int* idx, const d
         c.len[s] = length;
         for (int a = 0; a < 2; ++a) {
             c.lo[s][a] = c.hi[s][a] = 0;
-            c.dxs[s][a] = 1.0;
-            c.dxn[s][a] = 0.0;
+            c.wq[s][a] = 0.0;
             if (!(length > 0.0)) continue;
             const double step = length / (np - 1);  // np.linspace(0, length, num_points)
             const double xn = cs[a] * length;
@@ -123,8 +128,7 @@ __device__ __noinline__ void st_setup(const StModel& sm, const int* idx, const d
             const double xlo = lo * step, xhi = (hi == np - 1) ? length : hi * step;
             c.lo[s][a] = lo;
             c.hi[s][a] = hi;
-            c.dxs[s][a] = xhi - xlo;
-            c.dxn[s][a] = xn - xlo;
+            c.wq[s][a] = (xn - xlo) / (xhi - xlo);
         }
     }
 }
@@ -144,25 +148,39 @@ __device__ __forceinline__ double ipoly3v(QV q, int o, double X) {
     return q(o) * X + q(o + 1) * (0.5 * X * X) + q(o + 2) * (X * X * X * (1.0 / 3.0));
 }
 // section 1 (static.py:261-345), three tubes; y = [intc1 (9), intg21 (3), intg31 (3)]
+// omega of tube n's own pre-curvature at absolute node `node` (get_ksi_star, static.py:618-634): per-design table,
+// or the formula when a derived section index runs outside the tube (negative idx21 / idx31 / idx32)
+__device__ __noinline__ V3 ksi_star_cold(const ModelConst& mc, int n, double x) {
+    double w[3];
+    strain_omega(mc, n, x, w);
+    return V3{w[0], w[1], w[2]};
+}
+__device__ __forceinline__ V3 ksi_star_w(const StModel& sm, int n, int node) {
+    if (node >= 0 && node < sm.mc.npts[n]) {
+        const double* ws = sm.ws_tab + 3 * (sm.mc.node_base[n] + node);
+        return V3{ws[0], ws[1], ws[2]};
+    }
+    return ksi_star_cold(sm.mc, n, node * sm.mc.dx);
+}
+
 __device__ __noinline__ void node_sec1(const StModel& sm, const StCfg& c, QV q, int i, double y[15]) {
     const double dx = sm.mc.dx, X = i * dx;
     const int q11 = sm.qoff[0], q21 = sm.qoff[1], q31 = sm.qoff[2];
     V3 w1 = {poly3v(q, q11, X), poly3v(q, q11 + 3, X), poly3v(q, q11 + 6, X)};
     const double tg21 = poly3v(q, q21, X), tg31 = poly3v(q, q31, X);
-    double s21, c21, s31, c31;
-    sincos_ni(c.th[1] + ipoly3v(q, q21, X), &s21, &c21);  // gg21 = Rx(theta1 + int tau21)
-    sincos_ni(c.th[2] + ipoly3v(q, q31, X), &s31, &c31);
+    const SinCos r21 = sincos_ni(c.th[1] + ipoly3v(q, q21, X));  // gg21 = Rx(theta1 + int tau21)
+    const SinCos r31 = sincos_ni(c.th[2] + ipoly3v(q, q31, X));
+    const double s21 = r21.s, c21 = r21.c, s31 = r31.s, c31 = r31.c;
     V3 w21 = rotxT(s21, c21, w1);
     w21.x += tg21;
     V3 w31 = rotxT(s31, c31, w21);
     w31.x += tg31;
-    double ws[3];
-    strain_omega_ni(sm.mc, 0, (i + c.i11) * dx, ws);
-    V3 m11 = {sm.Kr[0][0] * (w1.x - ws[0]), sm.Kr[0][1] * (w1.y - ws[1]), sm.Kr[0][2] * (w1.z - ws[2])};
-    strain_omega_ni(sm.mc, 1, (i + c.i21) * dx, ws);
-    V3 m21 = {sm.Kr[1][0] * (w21.x - ws[0]), sm.Kr[1][1] * (w21.y - ws[1]), sm.Kr[1][2] * (w21.z - ws[2])};
-    strain_omega_ni(sm.mc, 2, (i + c.i31) * dx, ws);
-    V3 m31 = {sm.Kr[2][0] * (w31.x - ws[0]), sm.Kr[2][1] * (w31.y - ws[1]), sm.Kr[2][2] * (w31.z - ws[2])};
+    V3 ws = ksi_star_w(sm, 0, i + c.i11);
+    V3 m11 = {sm.Kr[0][0] * (w1.x - ws.x), sm.Kr[0][1] * (w1.y - ws.y), sm.Kr[0][2] * (w1.z - ws.z)};
+    ws = ksi_star_w(sm, 1, i + c.i21);
+    V3 m21 = {sm.Kr[1][0] * (w21.x - ws.x), sm.Kr[1][1] * (w21.y - ws.y), sm.Kr[1][2] * (w21.z - ws.z)};
+    ws = ksi_star_w(sm, 2, i + c.i31);
+    V3 m31 = {sm.Kr[2][0] * (w31.x - ws.x), sm.Kr[2][1] * (w31.y - ws.y), sm.Kr[2][2] * (w31.z - ws.z)};
     V3 r31m = rotx(s31, c31, m31);                 // coAd(gg31) fi_31 (moment part)
     V3 u = {m21.x + r31m.x, m21.y + r31m.y, m21.z + r31m.z};
     V3 ru = rotx(s21, c21, u);                      // coAd21 (fi_21 + coAd31 fi_31)
@@ -183,26 +201,26 @@ __device__ __noinline__ void node_sec1(const StModel& sm, const StCfg& c, QV q, 
 
 // section 2 (static.py:347-436); y = [intc2 (9), intg32 (3), intg312 (3)]
 __device__ __noinline__ void node_sec2(const StModel& sm, const StCfg& c, QV q, int i, double s31e, double c31e,
-                          const double S31e[3], double y[15]) {
+                                       double Xe, double y[15]) {
     const int T = sm.mc.T;
     const double dx = sm.mc.dx, X = i * dx;
     const int q22 = sm.qoff[3], q32 = sm.qoff[4];
     V3 w2 = {poly3v(q, q22, X), poly3v(q, q22 + 3, X), poly3v(q, q22 + 6, X)};
     const double t32 = poly3v(q, q32, X);
-    double s32, c32;
-    sincos_ni((T == 2 ? c.th[1] : 0.0) + ipoly3v(q, q32, X), &s32, &c32);
+    const SinCos r32 = sincos_ni((T == 2 ? c.th[1] : 0.0) + ipoly3v(q, q32, X));
+    const double s32 = r32.s, c32 = r32.c;
     V3 w32 = rotxT(s32, c32, rotxT(s31e, c31e, w2));
     w32.x += t32;
-    double ws[3];
-    strain_omega_ni(sm.mc, T - 2, (i + c.i22) * dx, ws);
-    V3 m22 = {sm.Kr[T - 2][0] * (w2.x - ws[0]), sm.Kr[T - 2][1] * (w2.y - ws[1]), sm.Kr[T - 2][2] * (w2.z - ws[2])};
-    strain_omega_ni(sm.mc, T - 1, (i + c.i32) * dx, ws);
-    V3 m32 = {sm.Kr[T - 1][0] * (w32.x - ws[0]), sm.Kr[T - 1][1] * (w32.y - ws[1]), sm.Kr[T - 1][2] * (w32.z - ws[2])};
+    V3 ws = ksi_star_w(sm, T - 2, i + c.i22);
+    V3 m22 = {sm.Kr[T - 2][0] * (w2.x - ws.x), sm.Kr[T - 2][1] * (w2.y - ws.y), sm.Kr[T - 2][2] * (w2.z - ws.z)};
+    ws = ksi_star_w(sm, T - 1, i + c.i32);
+    V3 m32 = {sm.Kr[T - 1][0] * (w32.x - ws.x), sm.Kr[T - 1][1] * (w32.y - ws.y), sm.Kr[T - 1][2] * (w32.z - ws.z)};
     V3 a = rotx(s31e, c31e, rotx(s32, c32, m32));   // coAd31 coAd32 fi_32
     V3 wsum = {m22.x + a.x, m22.y + a.y, m22.z + a.z};
     V3 z = cross3(w2, a);
     const double P[3] = {1.0, X, X * X};
     const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};
+    const double S31e[3] = {Xe, 0.5 * Xe * Xe, Xe * Xe * Xe * (1.0 / 3.0)};  // sg31 at the end of section 1
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         y[k] = P[k] * wsum.x;
@@ -213,23 +231,33 @@ __device__ __noinline__ void node_sec2(const StModel& sm, const StCfg& c, QV q, 
     }
 }
 
-// section 3 (static.py:438-452); y = intc3 (dof of the last tube)
+// section 3 (static.py:438-452); y = intc3 (dof of the last tube): B^T K (B q33 - B q*) with the base's single
+// non-zero per column taken from the per-design table
 __device__ __noinline__ void node_sec3(const StModel& sm, const StCfg& c, QV q, int i, double y[CTRB_MAX_DOF]) {
     const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
     const int q33 = sm.qoff[5];
-    double B[3][CTRB_MAX_DOF];
-    strain_base_rows(sm.mc.kind[T - 1], dof, (i + c.i33) * sm.mc.dx, B);
-    double m[3];
+    const double* bt = sm.b3_tab + (CTRB_MAX_DOF + 3) * (i + c.i33);
+    // B q33 and B q* are accumulated by the same explicitly rounded operations: with q33 == q* (the initial
+    // guess, static_bases.py:164-166) the difference must be exactly zero, as it is in the reference
+    double a[3] = {0.0, 0.0, 0.0}, b[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int k = 0; k < dof; ++k) {
+        const double ta = __dmul_rn(bt[k], q(q33 + k)), tb = __dmul_rn(bt[k], sm.mc.q[T - 1][k]);
+        const int r = sm.b3_row[k];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < dof; ++k) {
-            a += B[r][k] * q(q33 + k);
-            b += B[r][k] * sm.mc.q[T - 1][k];
+        for (int rr = 0; rr < 3; ++rr) {
+            a[rr] = __dadd_rn(a[rr], r == rr ? ta : 0.0);
+            b[rr] = __dadd_rn(b[rr], r == rr ? tb : 0.0);
         }
-        m[r] = sm.Kr[T - 1][r] * (a - b);
     }
-    for (int k = 0; k < dof; ++k) y[k] = B[0][k] * m[0] + B[1][k] * m[1] + B[2][k] * m[2];
+    const double m0 = sm.Kr[T - 1][0] * (a[0] - b[0]);
+    const double m1 = sm.Kr[T - 1][1] * (a[1] - b[1]);
+    const double m2 = sm.Kr[T - 1][2] * (a[2] - b[2]);
+#pragma unroll 1
+    for (int k = 0; k < dof; ++k) {
+        const int r = sm.b3_row[k];
+        y[k] = bt[k] * (r == 0 ? m0 : (r == 1 ? m1 : m2));
+    }
 }
 
 __device__ __noinline__ double warp_sum(double v) {
@@ -300,15 +328,14 @@ __device__ __noinline__ void res_node(const StModel& sm, const StCfg& c, QV q, i
         if (sec == 0) {
             node_sec1(sm, c, q, node, y);
         } else if (sec == 1) {
-            double s31e = 0.0, c31e = 1.0, S31e[3] = {0.0, 0.0, 0.0};
+            double s31e = 0.0, c31e = 1.0, Xe = 0.0;
             if (T == 3) {  // final relative frame / basis integral of tube 3 over section 1 (equilibrium_three's return)
-                const double Xe = (c.L[0] - 1) * sm.mc.dx;
-                sincos_ni(c.th[2] + ipoly3v(q, sm.qoff[2], Xe), &s31e, &c31e);
-                S31e[0] = Xe;
-                S31e[1] = 0.5 * Xe * Xe;
-                S31e[2] = Xe * Xe * Xe * (1.0 / 3.0);
+                Xe = (c.L[0] - 1) * sm.mc.dx;
+                const SinCos r = sincos_ni(c.th[2] + ipoly3v(q, sm.qoff[2], Xe));
+                s31e = r.s;
+                c31e = r.c;
             }
-            node_sec2(sm, c, q, node, s31e, c31e, S31e, y);
+            node_sec2(sm, c, q, node, s31e, c31e, Xe, y);
         } else {
             node_sec3(sm, c, q, node, y);
         }
@@ -332,7 +359,7 @@ __device__ __noinline__ double res_assemble(const StModel& sm, const StCfg& c, c
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const double ylo = yb[sec * 4 + a * 2 + 0][yo + k], yhi = yb[sec * 4 + a * 2 + 1][yo + k];
-            acc += 0.5 * (((yhi - ylo) / c.dxs[sec][a]) * c.dxn[sec][a] + ylo);
+            acc += 0.5 * ((yhi - ylo) * c.wq[sec][a] + ylo);
         }
     }
     double val = (c.len[sec] / 2) * acc;
@@ -342,7 +369,7 @@ __device__ __noinline__ double res_assemble(const StModel& sm, const StCfg& c, c
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const double ylo = yb[4 + a * 2 + 0][12 + k], yhi = yb[4 + a * 2 + 1][12 + k];
-                acc2 += 0.5 * (((yhi - ylo) / c.dxs[1][a]) * c.dxn[1][a] + ylo);
+                acc2 += 0.5 * ((yhi - ylo) * c.wq[1][a] + ylo);
             }
         }
         val -= (c.len[1] / 2) * acc2;
@@ -374,12 +401,17 @@ __device__ __noinline__ void sect_omega(const StModel& sm, const StCfg& c, const
     const double dx = sm.mc.dx;
     if (sect == 3) {
         const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
-        double B[3][CTRB_MAX_DOF];
-        strain_base_rows(sm.mc.kind[T - 1], dof, (sidx + c.i33) * dx, B);  // _easy_last_basis adds idx33 (again)
-        for (int r = 0; r < 3; ++r) {
-            double a = 0.0;
-            for (int k = 0; k < dof; ++k) a += B[r][k] * qs[k];
-            w[r] = a;
+        const double x = (sidx + c.i33) * dx;  // _easy_last_basis adds idx33 (again)
+        w[0] = w[1] = w[2] = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < dof; ++k) {
+            int r;
+            double v;
+            strain_base_col(sm.mc.kind[T - 1], dof, k, x, &r, &v);
+            const double t = v * qs[k];
+            w[0] += r == 0 ? t : 0.0;
+            w[1] += r == 1 ? t : 0.0;
+            w[2] += r == 2 ? t : 0.0;
         }
     } else {
         const double x = sidx * dx;
@@ -451,8 +483,8 @@ __device__ __noinline__ SE3 integrate_section(const StModel& sm, const StCfg& c,
 __device__ __forceinline__ SE3 se3_rx(double angle) {
     SE3 g;
     se3_identity(g);
-    double s, c;
-    sincos_ni(angle, &s, &c);
+    const SinCos r = sincos_ni(angle);
+    const double s = r.s, c = r.c;
     g.r[4] = c; g.r[5] = -s; g.r[7] = s; g.r[8] = c;
     return g;
 }

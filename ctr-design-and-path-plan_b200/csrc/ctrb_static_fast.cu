@@ -70,13 +70,13 @@ __device__ __forceinline__ double asm_part(const StCfg& c, const double (*yb)[16
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         const double ylo = yb[base + a * 2 + 0][off], yhi = yb[base + a * 2 + 1][off];
-        acc += 0.5 * (((yhi - ylo) / c.dxs[sec][a]) * c.dxn[sec][a] + ylo);
+        acc += 0.5 * ((yhi - ylo) * c.wq[sec][a] + ylo);
     }
     return (c.len[sec] / 2) * acc;
 }
 
 // y_i = sum_j M[i][j] v[j]: lane = row i, v broadcast from shared memory
-__device__ __forceinline__ double matvec_row(const double* M, const double* v, int n, int lane) {
+__device__ __noinline__ double matvec_row(const double* M, const double* v, int n, int lane) {
     const double* m = M + lane;
     double a0 = 0.0, a1 = 0.0;
     int j = 0;
@@ -90,7 +90,7 @@ __device__ __forceinline__ double matvec_row(const double* M, const double* v, i
 }
 
 // y_j = sum_i M[i][j] v[i]: lane = column j
-__device__ __forceinline__ double matvec_col(const double* M, const double* v, int n, int lane) {
+__device__ __noinline__ double matvec_col(const double* M, const double* v, int n, int lane) {
     const double* m = M + lane * kLD;
     double a0 = 0.0, a1 = 0.0;
     int i = 0;
@@ -270,6 +270,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
             if (delta == 0.0) delta = factor;
         }
         diag_l = fmax(diag_l, acnorm_l);
+        const double rdiag_l = 1.0 / diag_l;  // divisions by per-lane / per-iteration quantities become multiplications
         if (act) M.f[lane] = f_l;
         __syncwarp();
 #pragma unroll 1
@@ -279,11 +280,11 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
             const double qnorm = wnorm(diag_l * xg);
             double step = xg;
             if (!(qnorm <= delta)) {
-                double g = act ? matvec_col(M.J, M.f, n, lane) / diag_l : 0.0;
+                double g = act ? matvec_col(M.J, M.f, n, lane) * rdiag_l : 0.0;
                 const double gnorm = wnorm(g);
                 double sgnorm = 0.0, alpha = delta / qnorm;
                 if (gnorm != 0.0) {
-                    g = act ? (g / gnorm) / diag_l : 0.0;
+                    g = act ? (g * (1.0 / gnorm)) * rdiag_l : 0.0;
                     if (act) M.va[lane] = g;
                     __syncwarp();
                     const double w2 = act ? matvec_row(M.J, M.va, n, lane) : 0.0;
@@ -335,8 +336,9 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
                 if (fabs(ratio - 1) <= p1c) delta = pnorm / p5;
             }
             // Broyden vectors (hybrd: wa2 = (Q^T f+ - (Q^T f + R p)) / pnorm, wa1 = D ((D p) / pnorm))
-            const double u_l = act ? (fn_l - w3) / pnorm : 0.0;
-            const double v_l = act ? diag_l * ((diag_l * p_l) / pnorm) : 0.0;
+            const double ipn = 1.0 / pnorm;
+            const double u_l = act ? (fn_l - w3) * ipn : 0.0;
+            const double v_l = act ? diag_l * ((diag_l * p_l) * ipn) : 0.0;
             if (ratio >= p0001) {  // successful iteration
                 x_l = xt_l;
                 f_l = fn_l;
@@ -381,7 +383,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
             if (act) M.vb[lane] = vH;
             __syncwarp();
             if (act) {
-                const double hs = -Hu / den;
+                const double hs = -Hu * (1.0 / den);
                 double* jr = M.J + lane;
                 double* hr = M.H + lane;
 #pragma unroll 2

@@ -9,12 +9,15 @@ sys.path[:0] = [str(ROOT), str(ROOT / "ctr-design-and-path-plan_b200"), str(ROOT
 from util import gpu_static  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 30000
+LO = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+HI = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 m = gpu_static("c3_three_tube")
 N = np.asarray(m.num_discrete_points)
 rng = np.random.default_rng(1003)
-e = np.stack([rng.integers(1, 9, B) for t in range(3)], 1)
+e = np.stack([rng.integers(LO, HI + 1, B) for t in range(3)], 1)
 idx = (N[None, :] - 1 - e).astype(np.int32)
 th = rng.uniform(0, 2 * np.pi, (B, 3))
 for _ in range(2):
     res = m.solve_g_batch(idx, th, want_g=True)
-print("converged", res["converged"].mean(), "nfev", res["nfev"].mean(), "ms", m.ctx.last_kernel_ms("static_solve"))
+print("converged", res["converged"].mean(), "nfev", res["nfev"].mean(), "ms", m.ctx.last_kernel_ms("static_solve"),
+      "fast ms", m.ctx.last_kernel_ms("static_fast"), "fallbacks", m.ctx.static_fallbacks())
