@@ -105,45 +105,45 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
 struct HybrdMem {
     double fjac[kNP * kMaxNq];
     double r[kMaxNq * (kMaxNq + 1) / 2];
-    double x[kNV], fvec[kNV], qtf[kNV], wa1[kNV], wa2[kNV], wa3[kNV], wa4[kNV];
+    double wa1[kNV], wa2[kNV], wa3[kNV], wa4[kNV];
+    double x[kNV], fvec[kNV], qtf[kNV];
     double ybuf0[12][16];     // node integrands of a residual (3 sections x 2 abscissae x {lo, hi})
     StCfg cfg;
-    // During the forward-difference Jacobian two residuals are evaluated side by side.  R, wa3 and wa4 are
-    // dead then (R is rebuilt from the QR right after), so the second set of node vectors and the two
-    // perturbed unknown vectors alias them.
-    __device__ double (*ybuf(int g))[16] { return g == 0 ? ybuf0 : reinterpret_cast<double(*)[16]>(r); }
-    __device__ double* qbuf(int g) { return g == 0 ? wa3 : wa4; }
+    // During the forward-difference Jacobian R and wa1..wa4 are dead (R is rebuilt from the QR right after):
+    // the 32 node vectors of a round of column slots alias them (465 + 128 >= 512 doubles).
+    __device__ double (*ybuf32())[16] { return reinterpret_cast<double(*)[16]>(r); }
 };
+static_assert(kMaxNq * (kMaxNq + 1) / 2 + 4 * kNV >= 32 * 16, "fdjac scratch does not fit in R + wa1..wa4");
 
 __device__ __forceinline__ int rowoff(int n, int j) { return j * n - (j * (j - 1)) / 2; }  // packed upper-triangular rows
 
 // one residual evaluation F(q) by the whole warp; q and F are shared-memory vectors
-__device__ __forceinline__ void st_residual_w(const StModel& sm, HybrdMem& M, const double* q, double* F, int lane) {
-    if (lane < 12) res_node(sm, M.cfg, QV{q, -1, 0.0}, lane, M.ybuf0[lane]);
-    __syncwarp();
-    if (lane < sm.nq) F[lane] = res_assemble(sm, M.cfg, M.ybuf0, lane);
-    __syncwarp();
-}
-
 // dogleg (MINPACK): Gauss-Newton step by back substitution on the packed R, scaled gradient, and their
 // convex combination inside the trust region.  One vector element per lane; returns this lane's p.
 __device__ __noinline__ double dogleg_w(int n, const double* r, double diag_l, const double* qtb, double delta, double* tmp,
                                         int lane) {
     const double epsmch = DBL_EPSILON;
+    // Gauss-Newton step R x = qtb by column-oriented back substitution: lane i carries b_i; once x_j is known every
+    // lane i < j subtracts R[i][j] x_j.  1 / R[j][j] is formed by all lanes at once (a zero diagonal is replaced by
+    // eps * max |column|, as dogleg does).
+    double rd = 1.0, bl = 0.0;
+    if (lane < n) {
+        double temp = r[rowoff(n, lane)];
+        if (temp == 0.0) {
+#pragma unroll 1
+            for (int i = 0; i <= lane; ++i) temp = fmax(temp, fabs(r[rowoff(n, i) + lane - i]));
+            temp = epsmch * temp;
+            if (temp == 0.0) temp = epsmch;
+        }
+        rd = 1.0 / temp;
+        bl = qtb[lane];
+    }
     double xg = 0.0;  // Gauss-Newton component of this lane
 #pragma unroll 1
     for (int j = n - 1; j >= 0; --j) {
-        const int ro = rowoff(n, j);
-        const double term = (lane > j && lane < n) ? r[ro + lane - j] * xg : 0.0;
-        const double sum = warp_sum(term);
-        double temp = r[ro];
-        if (temp == 0.0) {
-            const double colv = (lane <= j) ? fabs(r[rowoff(n, lane) + j - lane]) : 0.0;
-            temp = epsmch * warp_max(colv);
-            if (temp == 0.0) temp = epsmch;
-        }
-        const double xj = (qtb[j] - sum) / temp;
+        const double xj = __shfl_sync(0xffffffffu, bl * rd, j);
         if (lane == j) xg = xj;
+        if (lane < j) bl = fma(-r[rowoff(n, lane) + j - lane], xj, bl);
     }
     const bool act = lane < n;
     const double qnorm = enorm_w(n, act ? diag_l * xg : 0.0, nullptr);
@@ -183,114 +183,120 @@ __device__ __noinline__ double dogleg_w(int n, const double* r, double diag_l, c
     return temp * g + alpha * xg;
 }
 
-__device__ __forceinline__ void givens(double a, double b, double* c_, double* s_, double* tau) {
-    // the rotation MINPACK builds to annihilate b against a (r1updt): returns cos, sin and the stored tau
-    if (fabs(a) < fabs(b)) {
-        const double cotan = a / b;
-        *s_ = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
-        *c_ = *s_ * cotan;
-        *tau = 1;
-        if (fabs(*c_) * DBL_MAX > 1) *tau = 1 / *c_;
-    } else {
-        const double tn = b / a;
-        *c_ = 0.5 / sqrt(0.25 + 0.25 * tn * tn);
-        *s_ = *c_ * tn;
-        *tau = *s_;
-    }
+// The plane rotation (c, s) = (a, b) / hypot(a, b); identity when both vanish.  MINPACK stores its rotations as
+// one number (tau) and rebuilds cos / sin with a square root wherever they are applied; here they are kept as pairs.
+__device__ __forceinline__ void rot_of(double a, double b, double* c_, double* s_) {
+    const double h2 = fma(a, a, b * b);
+    const double ri = h2 > 0.0 ? rsqrt(h2) : 0.0;
+    *c_ = h2 > 0.0 ? a * ri : 1.0;
+    *s_ = b * ri;
 }
 
-// r1updt: QR factors of R + u v^T.  Lane i owns w_i and element i of every packed row segment.
-// On return v (smem) and w (smem) hold the rotations for r1mpyq.
-__device__ __noinline__ void r1updt_w(int n, double* s, double u_l, double* v, double* w, int lane) {
+// r1updt: QR factors of R + u v^T (R packed by rows in s).  Lane l owns w_l and element l of every row.
+// First sweep (rotations that fold v into v_{n-1} e_{n-1}): |v_{n-1}| after step j is sqrt(sum_{k>=j} v_k^2), so all
+// n-1 rotations come from one suffix scan; second sweep (Hessenberg -> triangular) is sequential in j.
+// Outputs the rotations as c1/s1 (first sweep) and c2/s2 (second sweep), j = 0 .. n-2, for r1mpyq.
+__device__ __noinline__ void r1updt_w(int n, double* s, double u_l, const double* v, double* c1, double* s1, double* c2,
+                                      double* s2, int lane) {
+    const bool act = lane < n;
+    const double vl = act ? v[lane] : 0.0;
+    double S = vl * vl;  // suffix sums of squares
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double t = __shfl_down_sync(0xffffffffu, S, off);
+        if (lane + off < 32) S += t;
+    }
+    const double vlast = __shfl_sync(0xffffffffu, vl, n - 1);
+    const double Snext = __shfl_down_sync(0xffffffffu, S, 1);
+    const double S0 = __shfl_sync(0xffffffffu, S, 0);
+    __syncwarp();
+    if (lane < n - 1) {
+        double c_ = 1.0, s_ = 0.0;
+        if (vl != 0.0) {
+            const double ri = rsqrt(S);
+            const double vn = (lane == n - 2) ? vlast : sqrt(Snext);  // v_{n-1} before this step
+            c_ = vn * ri;
+            s_ = vl * ri;
+        }
+        c1[lane] = c_;
+        s1[lane] = s_;
+    }
+    const double vn_final = (S0 - vlast * vlast > 0.0) ? sqrt(S0) : vlast;
+    __syncwarp();
     double wl = 0.0;
     if (lane == n - 1) wl = s[rowoff(n, n - 1)];
-    double vn = v[n - 1];
 #pragma unroll 1
     for (int j = n - 2; j >= 0; --j) {
-        if (lane == j) wl = 0.0;
-        const double vj = v[j];
-        __syncwarp();
-        if (vj != 0.0) {
-            double c_, s_, tau;
-            givens(vn, vj, &c_, &s_, &tau);
-            vn = s_ * vj + c_ * vn;
-            if (lane == 0) v[j] = tau;
-            if (lane >= j && lane < n) {
-                const int l = rowoff(n, j) + lane - j;
-                const double sl = s[l];
-                s[l] = c_ * sl - s_ * wl;
-                wl = s_ * sl + c_ * wl;
-            }
+        const double s_ = s1[j];
+        if (s_ != 0.0 && lane >= j && act) {
+            const double c_ = c1[j];
+            const int l = rowoff(n, j) + lane - j;
+            const double sl = s[l];
+            s[l] = c_ * sl - s_ * wl;
+            wl = s_ * sl + c_ * wl;
         }
     }
-    if (lane == 0) v[n - 1] = vn;
-    if (lane < n) wl += vn * u_l;
+    if (act) wl = fma(vn_final, u_l, wl);
+    __syncwarp();
 #pragma unroll 1
     for (int j = 0; j < n - 1; ++j) {
-        const double wj = __shfl_sync(0xffffffffu, wl, j);
-        if (wj != 0.0) {
-            const int ro = rowoff(n, j);
-            double c_, s_, tau;
-            givens(s[ro], wj, &c_, &s_, &tau);
-            __syncwarp();
-            if (lane >= j && lane < n) {
-                const int l = ro + lane - j;
-                const double sl = s[l];
-                s[l] = c_ * sl + s_ * wl;
-                wl = -s_ * sl + c_ * wl;
-            }
-            if (lane == j) wl = tau;
-            __syncwarp();
+        const int ro = rowoff(n, j);
+        if (lane == j) {
+            double c_, s_;
+            rot_of(s[ro], wl, &c_, &s_);
+            c2[j] = c_;
+            s2[j] = s_;
+        }
+        __syncwarp();
+        const double s_ = s2[j];
+        if (s_ != 0.0 && lane >= j && act) {
+            const double c_ = c2[j];
+            const int l = ro + lane - j;
+            const double sl = s[l];
+            s[l] = c_ * sl + s_ * wl;
+            wl = -s_ * sl + c_ * wl;
         }
     }
     if (lane == n - 1) s[rowoff(n, n - 1)] = wl;
-    if (lane < n) w[lane] = wl;
     __syncwarp();
 }
 
-// apply the 2(n-1) stored rotations to ONE row a[0..n-1] with stride lda (r1mpyq, one row per lane)
-__device__ __noinline__ void st_r1mpyq_row(int n, double* a, int lda, const double* v, const double* w) {
-#pragma unroll 1
+// apply the 2(n-1) rotations to ONE row a[0..n-1] with stride lda (r1mpyq, one row per lane)
+__device__ __noinline__ void st_r1mpyq_row(int n, double* a, int lda, const double* c1, const double* s1, const double* c2,
+                                           const double* s2) {
+    double an = a[(n - 1) * lda];
+#pragma unroll 2
     for (int j = n - 2; j >= 0; --j) {
-        double c_, s_;
-        if (fabs(v[j]) > 1) {
-            c_ = 1 / v[j];
-            s_ = sqrt(1 - c_ * c_);
-        } else {
-            s_ = v[j];
-            c_ = sqrt(1 - s_ * s_);
-        }
-        const double temp = c_ * a[j * lda] - s_ * a[(n - 1) * lda];
-        a[(n - 1) * lda] = s_ * a[j * lda] + c_ * a[(n - 1) * lda];
-        a[j * lda] = temp;
+        const double c_ = c1[j], s_ = s1[j], aj = a[j * lda];
+        a[j * lda] = c_ * aj - s_ * an;
+        an = s_ * aj + c_ * an;
     }
-#pragma unroll 1
+#pragma unroll 2
     for (int j = 0; j < n - 1; ++j) {
-        double c_, s_;
-        if (fabs(w[j]) > 1) {
-            c_ = 1 / w[j];
-            s_ = sqrt(1 - c_ * c_);
-        } else {
-            s_ = w[j];
-            c_ = sqrt(1 - s_ * s_);
-        }
-        const double temp = c_ * a[j * lda] + s_ * a[(n - 1) * lda];
-        a[(n - 1) * lda] = -s_ * a[j * lda] + c_ * a[(n - 1) * lda];
-        a[j * lda] = temp;
+        const double c_ = c2[j], s_ = s2[j], aj = a[j * lda];
+        a[j * lda] = c_ * aj + s_ * an;
+        an = -s_ * aj + c_ * an;
     }
+    a[(n - 1) * lda] = an;
 }
 
 // MINPACK hybrd, warp-cooperative.  Every scalar of the iteration (delta, norms, counters, ratio) is
 // computed redundantly and identically by all lanes; vectors are one element per lane.
 // returns info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress)
-__device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, int lane, double xtol, int maxfev, double factor,
-                                     int* nfev_out) {
+__device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
+                                     double factor, int* nfev_out) {
     const int n = sm.nq;
     const bool act = lane < n;
     const double epsmch = DBL_EPSILON, p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double* fjac = M.fjac;
     int info = 0, nfev;
-    st_residual_w(sm, M, M.x, M.fvec, lane);
+    const RowMeta rm = row_meta(sm, act ? lane : 0);
+    double pa, pb;  // section shares of this lane's residual component at the accepted x (for the sparse fdjac)
+    {
+        const double f0 = warp_residual(sm, M.cfg, M.ybuf0, M.x, rm, act, lane, &pa, &pb);
+        if (act) M.fvec[lane] = f0;
+        __syncwarp();
+    }
     nfev = 1;
     double fnorm = enorm_w(n, act ? M.fvec[lane] : 0.0, M.fvec);
     int iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
@@ -299,40 +305,8 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, int lane, d
 #pragma unroll 1
     for (;;) {  // outer loop: fresh forward-difference Jacobian
         bool jeval = true;
-        // fdjac1 (dense): columns two at a time -- lanes 0..11 evaluate the node integrands of x + h_j e_j,
-        // lanes 12..23 those of x + h_(j+1) e_(j+1); then lanes 0..n-1 assemble both columns
-        {
-            const double eps = sqrt(epsmch);
-#pragma unroll 1
-            for (int j0 = 0; j0 < n; j0 += 2) {
-                if (act) {
-                    const double xv = M.x[lane];
-                    double h = eps * fabs(xv);
-                    if (h == 0) h = eps;
-                    M.qbuf(0)[lane] = (lane == j0) ? xv + h : xv;
-                    M.qbuf(1)[lane] = (lane == j0 + 1) ? xv + h : xv;
-                }
-                __syncwarp();
-                if (lane < 24) {
-                    const int g = lane >= 12 ? 1 : 0;
-                    if (j0 + g < n) res_node(sm, M.cfg, QV{M.qbuf(g), -1, 0.0}, lane - 12 * g, M.ybuf(g)[lane - 12 * g]);
-                }
-                __syncwarp();
-                if (act) {
-#pragma unroll 1
-                    for (int g = 0; g < 2; ++g) {
-                        const int j = j0 + g;
-                        if (j >= n) break;
-                        const double xv = M.x[j];
-                        double h = eps * fabs(xv);
-                        if (h == 0) h = eps;
-                        const double Fp = res_assemble(sm, M.cfg, M.ybuf(g), lane);
-                        fjac[lane + j * kNP] = (Fp - M.fvec[lane]) / h;
-                    }
-                }
-                __syncwarp();
-            }
-        }
+        // fdjac1 (dense band) through the block structure of the residual: 4 (8) node evaluations per column
+        warp_fdjac(sm, M.cfg, st, rm, M.x, fjac, M.ybuf32(), act ? M.fvec[lane] : 0.0, pa, pb, lane);
         nfev += n;
         __syncwarp();
         // qrfac: Householder QR without pivoting; lane k owns column k.  acnorm -> wa2, rdiag -> wa1
@@ -427,7 +401,12 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, int lane, d
             const double pnorm = enorm_w(n, diag_l * p_l, nullptr);
             if (iter == 1) delta = fmin(delta, pnorm);
             __syncwarp();
-            st_residual_w(sm, M, M.wa2, M.wa4, lane);
+            double qa, qb;
+            {
+                const double f1 = warp_residual(sm, M.cfg, M.ybuf0, M.wa2, rm, act, lane, &qa, &qb);
+                if (act) M.wa4[lane] = f1;
+                __syncwarp();
+            }
             nfev++;
             const double fnorm1 = enorm_w(n, act ? M.wa4[lane] : 0.0, M.wa4);
             double actred = -1;
@@ -461,6 +440,8 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, int lane, d
                     M.x[lane] = M.wa2[lane];
                     M.fvec[lane] = M.wa4[lane];
                 }
+                pa = qa;
+                pb = qb;
                 xnorm = enorm_w(n, act ? diag_l * M.wa2[lane] : 0.0, nullptr);
                 fnorm = fnorm1;
                 iter++;
@@ -493,9 +474,9 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, int lane, d
                 if (ratio >= p0001) M.qtf[lane] = sum;
             }
             __syncwarp();
-            r1updt_w(n, M.r, u_l, M.wa2, M.wa3, lane);
-            if (act) st_r1mpyq_row(n, fjac + lane, kNP, M.wa2, M.wa3);
-            if (lane == 31) st_r1mpyq_row(n, M.qtf, 1, M.wa2, M.wa3);
+            r1updt_w(n, M.r, u_l, M.wa2, M.wa1, M.wa2, M.wa3, M.wa4, lane);  // v is read into registers before c1/s1 land
+            // rows of Q on lanes 0..n-1, qtf (one more row under the same rotations) on lane 31
+            if (act || lane == 31) st_r1mpyq_row(n, act ? fjac + lane : M.qtf, act ? kNP : 1, M.wa1, M.wa2, M.wa3, M.wa4);
             __syncwarp();
             jeval = false;
         }
@@ -510,6 +491,9 @@ __global__ void __launch_bounds__(kSWarps * 32, 5)
                         int32_t* __restrict__ info_out, unsigned long long* __restrict__ ticket,
                         const long long* __restrict__ list, const unsigned long long* __restrict__ list_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SlotTable st;
+    if (threadIdx.x == 0) build_slot_table(sm, st);
+    __syncthreads();
     // with a list the kernel solves configurations list[0 .. *list_count): the ones the fast kernel handed back
     const long long work = list ? (long long)*list_count : B;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -527,7 +511,7 @@ __global__ void __launch_bounds__(kSWarps * 32, 5)
         __syncwarp();
         const StCfg& c = M.cfg;
         int nfev = 0;
-        const int info = st_hybrd(sm, M, lane, xtol, 200 * (n + 1), 100.0, &nfev);
+        const int info = st_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, &nfev);
         __syncwarp();
         if (sol_out && lane < n) sol_out[b * n + lane] = M.x[lane];
         if (lane == 0) {

@@ -377,6 +377,143 @@ __device__ __noinline__ double res_assemble(const StModel& sm, const StCfg& c, c
     return val;
 }
 
+constexpr int kJLD = 31;  // leading dimension of the column-major n x n matrices (odd: conflict-free row and column access)
+
+// per-lane description of residual row `lane` (which block of static.py:63 it belongs to)
+struct RowMeta {
+    int blk, k, sec, yo;
+};
+
+__device__ __forceinline__ RowMeta row_meta(const StModel& sm, int comp) {
+    RowMeta r;
+    r.blk = 0;
+#pragma unroll
+    for (int b = 1; b < 6; ++b)
+        if (comp >= sm.qoff[b] && sm.ndof[b] > 0) r.blk = b;
+    r.k = comp - sm.qoff[r.blk];
+    r.sec = r.blk < 3 ? 0 : (r.blk < 5 ? 1 : 2);
+    r.yo = (r.blk == 0 || r.blk == 3 || r.blk == 5) ? 0 : ((r.blk == 1 || r.blk == 4) ? 9 : 12);
+    return r;
+}
+
+// calculate_integral (static.py:456-491) of one integrand component over one section: the four node values are
+// yb[base + 2 a + e][off] (a = Gauss abscissa, e = lower / upper bracketing node)
+__device__ __forceinline__ double asm_part(const StCfg& c, const double (*yb)[16], int base, int sec, int off) {
+    if (!(c.len[sec] > 0.0)) return 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const double ylo = yb[base + a * 2 + 0][off], yhi = yb[base + a * 2 + 1][off];
+        acc += 0.5 * ((yhi - ylo) * c.wq[sec][a] + ylo);
+    }
+    return (c.len[sec] / 2) * acc;
+}
+
+// F(q) by the whole warp: 12 node integrands (3 sections x 2 abscissae x 2 bracketing nodes), then one residual
+// component per lane.  Returns this lane's component; p1 / p2 are its section shares (row block (3,1) is
+// intg_31 - intg_312, static.py:250-252; p2 = 0 elsewhere).
+__device__ __forceinline__ double warp_residual(const StModel& sm, const StCfg& cfg, double (*y)[16], const double* q,
+                                                const RowMeta& rm, bool act, int lane, double* p1, double* p2) {
+    if (lane < 12) res_node(sm, cfg, QV{q, -1, 0.0}, lane, y[lane]);
+    __syncwarp();
+    double a = 0.0, b = 0.0;
+    if (act) {
+        a = asm_part(cfg, y, rm.sec * 4, rm.sec, rm.yo + rm.k);
+        if (rm.blk == 2) b = asm_part(cfg, y, 4, 1, 12 + rm.k);
+    }
+    __syncwarp();
+    *p1 = a;
+    *p2 = b;
+    return rm.blk == 2 ? a - b : a;
+}
+
+// column-slot table of the forward-difference Jacobian: slot = (unknown j, section whose 4 nodes are re-evaluated)
+struct SlotTable {
+    signed char j[48], sec[48], col_blk[32];
+    int nslots;
+};
+
+// thread 0 of the block fills the table (it only depends on the design)
+__device__ __forceinline__ void build_slot_table(const StModel& sm, SlotTable& st) {
+    int ns = 0;
+    for (int b = 0; b < 6; ++b)
+        for (int k = 0; k < sm.ndof[b]; ++k) st.col_blk[sm.qoff[b] + k] = (signed char)b;
+    // the two-slot columns first, so that a pair never straddles a round of 8 slots
+    for (int k = 0; k < sm.ndof[2]; ++k)
+        for (int s = 0; s < 2; ++s) {
+            st.j[ns] = (signed char)(sm.qoff[2] + k);
+            st.sec[ns++] = (signed char)s;
+        }
+    for (int b = 0; b < 6; ++b) {
+        if (b == 2) continue;
+        for (int k = 0; k < sm.ndof[b]; ++k) {
+            st.j[ns] = (signed char)(sm.qoff[b] + k);
+            st.sec[ns++] = (signed char)(b < 3 ? 0 : (b < 5 ? 1 : 2));
+        }
+    }
+    st.nslots = ns;
+}
+
+// forward-difference Jacobian (MINPACK fdjac1, dense band) using the block structure; f_l / p1b / p2b are this
+// lane's residual component at x and its section shares.  Writes J (column-major, leading dimension kJLD); yb is
+// scratch for 32 node vectors; returns this lane's column norm.
+__device__ __noinline__ double warp_fdjac(const StModel& sm, const StCfg& cfg, const SlotTable& st, const RowMeta& rm,
+                                          const double* x, double* J, double (*yb)[16], double f_l, double p1b, double p2b,
+                                          int lane) {
+    const int n = sm.nq;
+    const bool act = lane < n;
+    const double eps = sqrt(DBL_EPSILON);
+    for (int base = 0; base < st.nslots; base += 8) {
+        {
+            const int slot = base + (lane >> 2);
+            if (slot < st.nslots) {
+                const int j = st.j[slot];
+                const double xv = x[j];
+                double h = eps * fabs(xv);
+                if (h == 0.0) h = eps;
+                res_node(sm, cfg, QV{x, j, h}, st.sec[slot] * 4 + (lane & 3), yb[lane]);
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int s8 = 0; s8 < 8; ++s8) {
+            const int slot = base + s8;
+            if (slot >= st.nslots) break;
+            const int j = st.j[slot], sec = st.sec[slot];
+            const bool pair = st.col_blk[j] == 2;  // (3,1) torsion: sections 1 and 2 both move; slots (s, s + 1)
+            if (pair && sec == 1) continue;
+            if (act) {
+                const bool hit1 = rm.sec == sec || (pair && rm.sec == 1);
+                const bool hit2 = rm.blk == 2 && (sec == 1 || pair);
+                double val = 0.0;
+                if (hit1 || hit2) {
+                    const int b1 = (pair && rm.sec == 1) ? (s8 + 1) * 4 : s8 * 4;
+                    const double p1 = hit1 ? asm_part(cfg, yb, b1, rm.sec, rm.yo + rm.k) : p1b;
+                    double Fp = p1;
+                    if (rm.blk == 2) {
+                        const int b2 = pair ? (s8 + 1) * 4 : s8 * 4;
+                        const double p2 = hit2 ? asm_part(cfg, yb, b2, 1, 12 + rm.k) : p2b;
+                        Fp = p1 - p2;
+                    }
+                    const double xv = x[j];
+                    double h = eps * fabs(xv);
+                    if (h == 0.0) h = eps;
+                    val = (Fp - f_l) / h;
+                }
+                J[lane + j * kJLD] = val;
+            }
+        }
+        __syncwarp();
+    }
+    double s2 = 0.0;
+    if (act) {
+        const double* m = J + lane * kJLD;
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) s2 = fma(m[i], m[i], s2);
+    }
+    return sqrt(s2);
+}
+
 // ------------------------------------------------------------------ curve integration (integrate_g)
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }

@@ -30,7 +30,7 @@
 namespace ctrb {
 
 constexpr int kFWarps = 4;   // warps (= configurations in flight) per block
-constexpr int kLD = 31;      // leading dimension, column-major: element (i, j) at i + j * kLD.  Odd, so both
+constexpr int kLD = kJLD;    // leading dimension, column-major: element (i, j) at i + j * kLD.  Odd, so both
                              // "lane = row" (stride 1) and "lane = column" (stride 31) accesses are conflict-free
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -44,36 +44,6 @@ struct FastMem {
     // integrands of 8 column slots x 4 nodes
     __device__ double (*ybuf())[16] { return reinterpret_cast<double(*)[16]>(H); }
 };
-
-// per-lane description of residual row `lane` (which block of static.py:63 it belongs to)
-struct RowMeta {
-    int blk, k, sec, yo;
-};
-
-__device__ __forceinline__ RowMeta row_meta(const StModel& sm, int comp) {
-    RowMeta r;
-    r.blk = 0;
-#pragma unroll
-    for (int b = 1; b < 6; ++b)
-        if (comp >= sm.qoff[b] && sm.ndof[b] > 0) r.blk = b;
-    r.k = comp - sm.qoff[r.blk];
-    r.sec = r.blk < 3 ? 0 : (r.blk < 5 ? 1 : 2);
-    r.yo = (r.blk == 0 || r.blk == 3 || r.blk == 5) ? 0 : ((r.blk == 1 || r.blk == 4) ? 9 : 12);
-    return r;
-}
-
-// calculate_integral (static.py:456-491) of one integrand component over one section: the four node values are
-// yb[base + 2 a + e][off] (a = Gauss abscissa, e = lower / upper bracketing node)
-__device__ __forceinline__ double asm_part(const StCfg& c, const double (*yb)[16], int base, int sec, int off) {
-    if (!(c.len[sec] > 0.0)) return 0.0;
-    double acc = 0.0;
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const double ylo = yb[base + a * 2 + 0][off], yhi = yb[base + a * 2 + 1][off];
-        acc += 0.5 * ((yhi - ylo) * c.wq[sec][a] + ylo);
-    }
-    return (c.len[sec] / 2) * acc;
-}
 
 // y_i = sum_j M[i][j] v[j]: lane = row i, v broadcast from shared memory
 __device__ __noinline__ double matvec_row(const double* M, const double* v, int n, int lane) {
@@ -104,24 +74,6 @@ __device__ __noinline__ double matvec_col(const double* M, const double* v, int 
 }
 
 __device__ __forceinline__ double wnorm(double v) { return sqrt(warp_sum(v * v)); }
-
-// F(q) by the whole warp: 12 node integrands (3 sections x 2 abscissae x 2 bracketing nodes), then one residual
-// component per lane.  Returns this lane's component; p1 / p2 are its section shares (row block (3,1) is
-// intg_31 - intg_312, static.py:250-252; p2 = 0 elsewhere).
-__device__ __forceinline__ double fast_residual(const StModel& sm, FastMem& M, const double* q, const RowMeta& rm, bool act,
-                                                int lane, double* p1, double* p2) {
-    if (lane < 12) res_node(sm, M.cfg, QV{q, -1, 0.0}, lane, M.y[lane]);
-    __syncwarp();
-    double a = 0.0, b = 0.0;
-    if (act) {
-        a = asm_part(M.cfg, M.y, rm.sec * 4, rm.sec, rm.yo + rm.k);
-        if (rm.blk == 2) b = asm_part(M.cfg, M.y, 4, 1, 12 + rm.k);
-    }
-    __syncwarp();
-    *p1 = a;
-    *p2 = b;
-    return rm.blk == 2 ? a - b : a;
-}
 
 // H = J^-1 by Gauss-Jordan exchange steps with implicit partial pivoting; lane = row.  Returns false when a
 // pivot falls below 1e-12 of its column norm (numerically singular Jacobian).
@@ -176,71 +128,6 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n, double acnorm_l, int
     return true;
 }
 
-// column-slot table of the forward-difference Jacobian: slot = (unknown j, section whose 4 nodes are re-evaluated)
-struct SlotTable {
-    signed char j[48], sec[48], col_blk[32];
-    int nslots;
-};
-
-// forward-difference Jacobian (MINPACK fdjac1, dense band) using the block structure; f_l / p1b / p2b are this
-// lane's residual component at x and its section shares.  Writes M.J; returns this lane's column norm.
-__device__ __noinline__ double fast_fdjac(const StModel& sm, FastMem& M, const SlotTable& st, const RowMeta& rm, double f_l,
-                                          double p1b, double p2b, int lane) {
-    const int n = sm.nq;
-    const bool act = lane < n;
-    const double eps = sqrt(DBL_EPSILON);
-    double (*yb)[16] = M.ybuf();
-    for (int base = 0; base < st.nslots; base += 8) {
-        {
-            const int slot = base + (lane >> 2);
-            if (slot < st.nslots) {
-                const int j = st.j[slot];
-                const double xv = M.x[j];
-                double h = eps * fabs(xv);
-                if (h == 0.0) h = eps;
-                res_node(sm, M.cfg, QV{M.x, j, h}, st.sec[slot] * 4 + (lane & 3), yb[lane]);
-            }
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int s8 = 0; s8 < 8; ++s8) {
-            const int slot = base + s8;
-            if (slot >= st.nslots) break;
-            const int j = st.j[slot], sec = st.sec[slot];
-            const bool pair = st.col_blk[j] == 2;  // (3,1) torsion: sections 1 and 2 both move; slots (s, s + 1)
-            if (pair && sec == 1) continue;
-            if (act) {
-                const bool hit1 = rm.sec == sec || (pair && rm.sec == 1);
-                const bool hit2 = rm.blk == 2 && (sec == 1 || pair);
-                double val = 0.0;
-                if (hit1 || hit2) {
-                    const int b1 = (pair && rm.sec == 1) ? (s8 + 1) * 4 : s8 * 4;
-                    const double p1 = hit1 ? asm_part(M.cfg, yb, b1, rm.sec, rm.yo + rm.k) : p1b;
-                    double Fp = p1;
-                    if (rm.blk == 2) {
-                        const int b2 = pair ? (s8 + 1) * 4 : s8 * 4;
-                        const double p2 = hit2 ? asm_part(M.cfg, yb, b2, 1, 12 + rm.k) : p2b;
-                        Fp = p1 - p2;
-                    }
-                    const double xv = M.x[j];
-                    double h = eps * fabs(xv);
-                    if (h == 0.0) h = eps;
-                    val = (Fp - f_l) / h;
-                }
-                M.J[lane + j * kLD] = val;
-            }
-        }
-        __syncwarp();
-    }
-    double s2 = 0.0;
-    if (act) {
-        const double* m = M.J + lane * kLD;
-#pragma unroll 2
-        for (int i = 0; i < n; ++i) s2 = fma(m[i], m[i], s2);
-    }
-    return sqrt(s2);
-}
-
 // returns MINPACK's info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress), or -1 when the
 // configuration has to go through the QR kernel
 __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
@@ -251,7 +138,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
     const double epsmch = DBL_EPSILON, p1c = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double x_l = act ? M.x[lane] : 0.0;
     double pa, pb;
-    double f_l = fast_residual(sm, M, M.x, rm, act, lane, &pa, &pb);
+    double f_l = warp_residual(sm, M.cfg, M.y, M.x, rm, act, lane, &pa, &pb);
     int nfev = 1, info = 0;
     double fnorm = wnorm(f_l);
     if (!(fnorm < 1.7e308)) return -1;
@@ -260,7 +147,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
 #pragma unroll 1
     for (;;) {
         bool jeval = true;
-        const double acnorm_l = fast_fdjac(sm, M, st, rm, f_l, pa, pb, lane);
+        const double acnorm_l = warp_fdjac(sm, M.cfg, st, rm, M.x, M.J, M.ybuf(), f_l, pa, pb, lane);
         nfev += n;
         if (!fast_invert(M, n, acnorm_l, lane)) return -1;
         if (iter == 1) {
@@ -313,7 +200,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
             }
             __syncwarp();
             double qa, qb;
-            const double fn_l = fast_residual(sm, M, M.vb, rm, act, lane, &qa, &qb);
+            const double fn_l = warp_residual(sm, M.cfg, M.y, M.vb, rm, act, lane, &qa, &qb);
             nfev++;
             const double fnorm1 = wnorm(fn_l);
             if (!(fnorm1 < 1.7e308) || !(pnorm < 1.7e308)) return -1;  // non-finite: let the QR kernel decide
@@ -409,25 +296,7 @@ __global__ void __launch_bounds__(kFWarps * 32, 3)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FastMem& M = reinterpret_cast<FastMem*>(smem_raw)[warp];
     const int T = sm.mc.T, n = sm.nq;
-    if (threadIdx.x == 0) {
-        int ns = 0;
-        for (int b = 0; b < 6; ++b)
-            for (int k = 0; k < sm.ndof[b]; ++k) st.col_blk[sm.qoff[b] + k] = (signed char)b;
-        // the two-slot columns first, so that a pair never straddles a round of 8 slots
-        for (int k = 0; k < sm.ndof[2]; ++k)
-            for (int s = 0; s < 2; ++s) {
-                st.j[ns] = (signed char)(sm.qoff[2] + k);
-                st.sec[ns++] = (signed char)s;
-            }
-        for (int b = 0; b < 6; ++b) {
-            if (b == 2) continue;
-            for (int k = 0; k < sm.ndof[b]; ++k) {
-                st.j[ns] = (signed char)(sm.qoff[b] + k);
-                st.sec[ns++] = (signed char)(b < 3 ? 0 : (b < 5 ? 1 : 2));
-            }
-        }
-        st.nslots = ns;
-    }
+    if (threadIdx.x == 0) build_slot_table(sm, st);
     __syncthreads();
     for (;;) {
         unsigned long long tk = 0;
