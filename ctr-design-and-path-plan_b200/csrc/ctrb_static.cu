@@ -485,7 +485,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotT
 
 // ------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(kSWarps * 32, 5)
-    static_solve_kernel(StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
+    static_solve_kernel(const __grid_constant__ StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
                         const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                         double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
                         int32_t* __restrict__ info_out, unsigned long long* __restrict__ ticket,
