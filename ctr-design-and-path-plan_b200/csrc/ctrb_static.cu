@@ -34,7 +34,6 @@ constexpr int kNV = 32;       // padded vector length
 __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, const double* qp, double* F) {
     const int T = sm.mc.T;
     const QV q = {qp, -1, 0.0};
-    double s31e = 0.0, c31e = 1.0, Xe31 = 0.0;
     double F31[3] = {0.0, 0.0, 0.0};
     if (T == 3) {
         double acc[15];
@@ -45,7 +44,7 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
             for (int a = 0; a < 2; ++a) {
                 double y2[2][15];
 #pragma unroll 1
-                for (int e = 0; e < 2; ++e) node_sec1(sm, c, q, e ? c.hi[0][a] : c.lo[0][a], y2[e]);
+                for (int e = 0; e < 2; ++e) node_sec12(sm, c, q, 0, e ? c.hi[0][a] : c.lo[0][a], y2[e]);
 #pragma unroll 1
                 for (int k = 0; k < 15; ++k) acc[k] += 0.5 * ((y2[1][k] - y2[0][k]) * c.wq[0][a] + y2[0][k]);
             }
@@ -54,12 +53,6 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
         for (int k = 0; k < 9; ++k) F[sm.qoff[0] + k] = h * acc[k];
         for (int k = 0; k < 3; ++k) F[sm.qoff[1] + k] = h * acc[9 + k];
         for (int k = 0; k < 3; ++k) F31[k] = h * acc[12 + k];
-        // final relative frame / basis integral of tube 3 over section 1 (equilibrium_three's return)
-        const double Xe = (c.L[0] - 1) * sm.mc.dx;
-        const SinCos r31 = sincos_ni(c.th[2] + ipoly3(qp + sm.qoff[2], Xe));
-        s31e = r31.s;
-        c31e = r31.c;
-        Xe31 = Xe;
     }
     {
         double acc[15];
@@ -70,7 +63,7 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
             for (int a = 0; a < 2; ++a) {
                 double y2[2][15];
 #pragma unroll 1
-                for (int e = 0; e < 2; ++e) node_sec2(sm, c, q, e ? c.hi[1][a] : c.lo[1][a], s31e, c31e, Xe31, y2[e]);
+                for (int e = 0; e < 2; ++e) node_sec12(sm, c, q, 1, e ? c.hi[1][a] : c.lo[1][a], y2[e]);
 #pragma unroll 1
                 for (int k = 0; k < 15; ++k) acc[k] += 0.5 * ((y2[1][k] - y2[0][k]) * c.wq[1][a] + y2[0][k]);
             }

@@ -163,71 +163,56 @@ __device__ __forceinline__ V3 ksi_star_w(const StModel& sm, int n, int node) {
     return ksi_star_cold(sm.mc, n, node * sm.mc.dx);
 }
 
-__device__ __noinline__ void node_sec1(const StModel& sm, const StCfg& c, QV q, int i, double y[15]) {
-    const double dx = sm.mc.dx, X = i * dx;
-    const int q11 = sm.qoff[0], q21 = sm.qoff[1], q31 = sm.qoff[2];
-    V3 w1 = {poly3v(q, q11, X), poly3v(q, q11 + 3, X), poly3v(q, q11 + 6, X)};
-    const double tg21 = poly3v(q, q21, X), tg31 = poly3v(q, q31, X);
-    const SinCos r21 = sincos_ni(c.th[1] + ipoly3v(q, q21, X));  // gg21 = Rx(theta1 + int tau21)
-    const SinCos r31 = sincos_ni(c.th[2] + ipoly3v(q, q31, X));
-    const double s21 = r21.s, c21 = r21.c, s31 = r31.s, c31 = r31.c;
-    V3 w21 = rotxT(s21, c21, w1);
-    w21.x += tg21;
-    V3 w31 = rotxT(s31, c31, w21);
-    w31.x += tg31;
-    V3 ws = ksi_star_w(sm, 0, i + c.i11);
-    V3 m11 = {sm.Kr[0][0] * (w1.x - ws.x), sm.Kr[0][1] * (w1.y - ws.y), sm.Kr[0][2] * (w1.z - ws.z)};
-    ws = ksi_star_w(sm, 1, i + c.i21);
-    V3 m21 = {sm.Kr[1][0] * (w21.x - ws.x), sm.Kr[1][1] * (w21.y - ws.y), sm.Kr[1][2] * (w21.z - ws.z)};
-    ws = ksi_star_w(sm, 2, i + c.i31);
-    V3 m31 = {sm.Kr[2][0] * (w31.x - ws.x), sm.Kr[2][1] * (w31.y - ws.y), sm.Kr[2][2] * (w31.z - ws.z)};
-    V3 r31m = rotx(s31, c31, m31);                 // coAd(gg31) fi_31 (moment part)
-    V3 u = {m21.x + r31m.x, m21.y + r31m.y, m21.z + r31m.z};
-    V3 ru = rotx(s21, c21, u);                      // coAd21 (fi_21 + coAd31 fi_31)
-    V3 wsum = {m11.x + ru.x, m11.y + ru.y, m11.z + ru.z};
-    V3 z21 = cross3(w1, ru);                        // coad(ksi_1) (...)
-    V3 z31 = cross3(w1, rotx(s21, c21, r31m));
-    const double P[3] = {1.0, X, X * X};
-    const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};  // sg (row 0) = int of the basis
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        y[k] = P[k] * wsum.x;
-        y[3 + k] = P[k] * wsum.y;
-        y[6 + k] = P[k] * wsum.z;
-        y[9 + k] = P[k] * (m21.x + m31.x) - S[k] * z21.x;
-        y[12 + k] = P[k] * m31.x - S[k] * z31.x;
-    }
-}
-
-// section 2 (static.py:347-436); y = [intc2 (9), intg32 (3), intg312 (3)]
-__device__ __noinline__ void node_sec2(const StModel& sm, const StCfg& c, QV q, int i, double s31e, double c31e,
-                                       double Xe, double y[15]) {
+// Sections 1 and 2 (static.py:261-345 and 347-436) through ONE routine, so that the lanes holding section-1 and
+// section-2 nodes do not diverge.  Section 1: outer tube with curvature polynomials w, then two nested relative
+// x-rotations Rx(aM), Rx(aI) of the middle and inner tubes, each adding its torsion polynomial.  Section 2 is the
+// same chain without a middle tube (zero stiffness, no torsion) whose rotation is the relative frame gg31 reached
+// at the end of section 1 (equilibrium_three's return value; identity for two tubes).
+//   sec 0: y = [intc1 (9), intg21 (3), intg31 (3)]      sec 1: y = [intc2 (9), intg32 (3), intg312 (3)]
+__device__ __noinline__ void node_sec12(const StModel& sm, const StCfg& c, QV q, int sec, int i, double y[15]) {
     const int T = sm.mc.T;
+    const bool s2 = sec == 1;
     const double dx = sm.mc.dx, X = i * dx;
-    const int q22 = sm.qoff[3], q32 = sm.qoff[4];
-    V3 w2 = {poly3v(q, q22, X), poly3v(q, q22 + 3, X), poly3v(q, q22 + 6, X)};
-    const double t32 = poly3v(q, q32, X);
-    const SinCos r32 = sincos_ni((T == 2 ? c.th[1] : 0.0) + ipoly3v(q, q32, X));
-    const double s32 = r32.s, c32 = r32.c;
-    V3 w32 = rotxT(s32, c32, rotxT(s31e, c31e, w2));
-    w32.x += t32;
-    V3 ws = ksi_star_w(sm, T - 2, i + c.i22);
-    V3 m22 = {sm.Kr[T - 2][0] * (w2.x - ws.x), sm.Kr[T - 2][1] * (w2.y - ws.y), sm.Kr[T - 2][2] * (w2.z - ws.z)};
-    ws = ksi_star_w(sm, T - 1, i + c.i32);
-    V3 m32 = {sm.Kr[T - 1][0] * (w32.x - ws.x), sm.Kr[T - 1][1] * (w32.y - ws.y), sm.Kr[T - 1][2] * (w32.z - ws.z)};
-    V3 a = rotx(s31e, c31e, rotx(s32, c32, m32));   // coAd31 coAd32 fi_32
-    V3 wsum = {m22.x + a.x, m22.y + a.y, m22.z + a.z};
-    V3 z = cross3(w2, a);
+    const double Xe = T == 3 ? (c.L[0] - 1) * dx : 0.0;
+    const int qo = sm.qoff[s2 ? 3 : 0], qm = sm.qoff[s2 ? 2 : 1], qi = sm.qoff[s2 ? 4 : 2];
+    const int nO = s2 ? T - 2 : 0, nI = s2 ? T - 1 : 2;
+    V3 w1 = {poly3v(q, qo, X), poly3v(q, qo + 3, X), poly3v(q, qo + 6, X)};
+    const double tgM = s2 ? 0.0 : poly3v(q, qm, X), tgI = poly3v(q, qi, X);
+    const bool mid_identity = s2 && T == 2;
+    const double aM = mid_identity ? 0.0 : (s2 ? c.th[2] : c.th[1]) + ipoly3v(q, qm, s2 ? Xe : X);
+    const double aI = (s2 ? (T == 2 ? c.th[1] : 0.0) : c.th[2]) + ipoly3v(q, qi, X);
+    const SinCos rM = sincos_ni(aM);  // gg21 = Rx(theta1 + int tau21)   |   gg31 at the end of section 1
+    const SinCos rI = sincos_ni(aI);  // gg31                            |   gg32
+    const double sM = rM.s, cM = rM.c, sI = rI.s, cI = rI.c;
+    V3 wM = rotxT(sM, cM, w1);
+    wM.x += tgM;
+    V3 wI = rotxT(sI, cI, wM);
+    wI.x += tgI;
+    V3 ws = ksi_star_w(sm, nO, i + (s2 ? c.i22 : c.i11));
+    V3 mO = {sm.Kr[nO][0] * (w1.x - ws.x), sm.Kr[nO][1] * (w1.y - ws.y), sm.Kr[nO][2] * (w1.z - ws.z)};
+    V3 mM = {0.0, 0.0, 0.0};
+    if (!s2) {
+        ws = ksi_star_w(sm, 1, i + c.i21);
+        mM = V3{sm.Kr[1][0] * (wM.x - ws.x), sm.Kr[1][1] * (wM.y - ws.y), sm.Kr[1][2] * (wM.z - ws.z)};
+    }
+    ws = ksi_star_w(sm, nI, i + (s2 ? c.i32 : c.i31));
+    V3 mI = {sm.Kr[nI][0] * (wI.x - ws.x), sm.Kr[nI][1] * (wI.y - ws.y), sm.Kr[nI][2] * (wI.z - ws.z)};
+    V3 rIm = rotx(sI, cI, mI);                      // coAd(gg_I) f_I (moment part)
+    V3 u = {mM.x + rIm.x, mM.y + rIm.y, mM.z + rIm.z};
+    V3 ru = rotx(sM, cM, u);                        // coAd(gg_M) (f_M + coAd(gg_I) f_I)
+    V3 wsum = {mO.x + ru.x, mO.y + ru.y, mO.z + ru.z};
+    V3 zM = cross3(w1, ru);                         // coad(ksi_O) (...)
+    V3 zI = cross3(w1, rotx(sM, cM, rIm));
     const double P[3] = {1.0, X, X * X};
-    const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};
-    const double S31e[3] = {Xe, 0.5 * Xe * Xe, Xe * Xe * Xe * (1.0 / 3.0)};  // sg31 at the end of section 1
+    const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};            // sg (row 0) = int of the basis
+    const double Se[3] = {Xe, 0.5 * Xe * Xe, Xe * Xe * Xe * (1.0 / 3.0)};     // sg31 at the end of section 1
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         y[k] = P[k] * wsum.x;
         y[3 + k] = P[k] * wsum.y;
         y[6 + k] = P[k] * wsum.z;
-        y[9 + k] = P[k] * m32.x - S[k] * z.x;
-        y[12 + k] = S31e[k] * z.x;
+        y[9 + k] = P[k] * (mM.x + mI.x) - S[k] * zM.x;
+        y[12 + k] = s2 ? Se[k] * zI.x : P[k] * mI.x - S[k] * zI.x;
     }
 }
 
@@ -325,17 +310,8 @@ __device__ __noinline__ void res_node(const StModel& sm, const StCfg& c, QV q, i
     const int sec = t >> 2, a = (t >> 1) & 1, e = t & 1;
     if (c.len[sec] > 0.0 && (sec != 0 || T == 3)) {
         const int node = e ? c.hi[sec][a] : c.lo[sec][a];
-        if (sec == 0) {
-            node_sec1(sm, c, q, node, y);
-        } else if (sec == 1) {
-            double s31e = 0.0, c31e = 1.0, Xe = 0.0;
-            if (T == 3) {  // final relative frame / basis integral of tube 3 over section 1 (equilibrium_three's return)
-                Xe = (c.L[0] - 1) * sm.mc.dx;
-                const SinCos r = sincos_ni(c.th[2] + ipoly3v(q, sm.qoff[2], Xe));
-                s31e = r.s;
-                c31e = r.c;
-            }
-            node_sec2(sm, c, q, node, s31e, c31e, Xe, y);
+        if (sec < 2) {
+            node_sec12(sm, c, q, sec, node, y);
         } else {
             node_sec3(sm, c, q, node, y);
         }
