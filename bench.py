@@ -44,6 +44,9 @@ WORKLOADS = {  # name -> (model, exposure lo, hi, default configs per step per G
     "c3_kinematic_colon_straight_uniform": ("kinematic", 1, 33, 10_000_000),
 }
 BYTES_PER_CONFIG = 3 * (4 + 8) + (8 + 8 + 8 + 1)  # idx + theta in, obstacle_min + goal_dist + cost + bit out
+# dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (30000 C3 shallow configurations,
+# profiles/r1_ncu_static_fast_qr.json) divided by the configurations each kernel solved
+NCU_DRAM_BYTES_PER_CONFIG = {"static_fast_kernel": 2401.0, "static_solve_kernel": 5416.0}
 
 
 def make_inputs(B, seed, lo, hi):
@@ -249,7 +252,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms, aux_ms = [], []
+    kern_ms, aux_ms, fast_ms, fallbacks = [], [], [], []
     barrier()
     e0.record()
     dom = "static_solve" if kind == "static" else "chain_eval"
@@ -262,6 +265,8 @@ def main():
         kern_ms.append(ctx.last_kernel_ms(dom))  # CUDA events around the dominant kernel, on its stream
         if kind == "static":
             aux_ms.append(ctx.last_kernel_ms("chain_eval"))
+            fast_ms.append(ctx.last_kernel_ms("static_fast"))
+            fallbacks.append(ctx.static_fallbacks())
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -318,14 +323,23 @@ def main():
         bpc = 3 * 12 + 8 + 128.0 * nodes_mean
         achieved = bpc * B / (k_ms * 1e-3) / 1e9
         # FLOP model: 2.6 kFLOP per residual evaluation (12 node integrands, closed forms) +
-        # hybrd's dense algebra per Jacobian (QR + Q: 2 n^3) and per iteration (dogleg, r1updt, r1mpyq: 9 n^2), n = 30
+        # hybrd's dense algebra per Jacobian (inverse or QR + Q: 2 n^3) and per iteration (6 matrix-vector products
+        # + 2 rank-one updates, or dogleg + r1updt + r1mpyq: ~9 n^2), n = 30
         n_jac = max(1.0, nfev_mean / 45.0)
         flop64 = nfev_mean * 2600.0 + n_jac * 2 * 30 ** 3 + max(nfev_mean - 30 * n_jac, 1.0) * 9 * 30 ** 2 + nodes_mean * 260.0
+        # DRAM traffic per configuration from the ncu --set full capture of the same kernels (profiles/): 2.40 KB
+        # (fast kernel) and 5.42 KB (QR kernel) per solved configuration, scaled to this launch
+        fb = float(np.mean(fallbacks)) / B
+        traffic = ((1 - fb) * NCU_DRAM_BYTES_PER_CONFIG["static_fast_kernel"]
+                   + fb * NCU_DRAM_BYTES_PER_CONFIG["static_solve_kernel"]) * B
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "static_solve_kernel", "kernel_ms": k_ms,
+                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_static_fast_qr.json, per configuration x launch size",
+                    "kernel": "static_fast_kernel + static_solve_kernel (one launch sequence = the static solve)",
+                    "kernel_ms": k_ms, "fast_kernel_ms": float(np.mean(fast_ms)),
+                    "qr_fallback_kernel_ms": k_ms - float(np.mean(fast_ms)), "qr_fallback_fraction": fb,
                     "algorithmic_bytes_per_config": bpc, "peak_source": peak_src,
-                    "note": "per-configuration nonlinear solve: bound by fp64 CUDA-core latency/throughput and "
-                            "shared-memory traffic of hybrd's work arrays, not HBM; see compute_roofline"}
+                    "note": "per-configuration nonlinear solve: bound by fp64 CUDA-core latency and instruction fetch "
+                            "(one warp per configuration, serial dependency chains), not HBM; see compute_roofline"}
         compute = {"residual_evaluations_per_config": nfev_mean, "converged_fraction": conv_frac,
                    "fp64_flop_per_config": flop64, "fp64_tflops_achieved": flop64 * B / (k_ms * 1e-3) / 1e12,
                    "fp64_fma_peak_tflops_measured": f64_peak, "fp32_fma_peak_tflops_measured": f32_peak,

@@ -47,6 +47,16 @@ __device__ __noinline__ SinCos sincos_ni(double a) {
     sincos(a, &r.s, &r.c);
     return r;
 }
+// two independent angles in one call: the two dependency chains interleave (the kernels are latency-bound)
+struct SinCos2 {
+    double s0, c0, s1, c1;
+};
+__device__ __noinline__ SinCos2 sincos2_ni(double a, double b) {
+    SinCos2 r;
+    sincos(a, &r.s0, &r.c0);
+    sincos(b, &r.s1, &r.c1);
+    return r;
+}
 
 // one non-zero per column of a strain base (strain_bases.py:7-224): its row (0..2) and its value at x
 __host__ __device__ __forceinline__ void strain_base_col(int kind, int dof, int k, double x, int* row, double* val) {
@@ -181,9 +191,9 @@ __device__ __noinline__ void node_sec12(const StModel& sm, const StCfg& c, QV q,
     const bool mid_identity = s2 && T == 2;
     const double aM = mid_identity ? 0.0 : (s2 ? c.th[2] : c.th[1]) + ipoly3v(q, qm, s2 ? Xe : X);
     const double aI = (s2 ? (T == 2 ? c.th[1] : 0.0) : c.th[2]) + ipoly3v(q, qi, X);
-    const SinCos rM = sincos_ni(aM);  // gg21 = Rx(theta1 + int tau21)   |   gg31 at the end of section 1
-    const SinCos rI = sincos_ni(aI);  // gg31                            |   gg32
-    const double sM = rM.s, cM = rM.c, sI = rI.s, cI = rI.c;
+    // M: gg21 = Rx(theta1 + int tau21) | gg31 at the end of section 1;   I: gg31 | gg32
+    const SinCos2 rr = sincos2_ni(aM, aI);
+    const double sM = rr.s0, cM = rr.c0, sI = rr.s1, cI = rr.c1;
     V3 wM = rotxT(sM, cM, w1);
     wM.x += tgM;
     V3 wI = rotxT(sI, cI, wM);
