@@ -787,6 +787,38 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
     return st.finish(mem);
 }
 
+int ctrb_knn_batch(ctrb_ctx* ctx, int32_t dim, int64_t N, const double* points, int64_t Q, const double* queries,
+                   const double* weight, const int32_t* topology, int32_t k, int32_t* idx_out, double* dist_out, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(dim >= 1 && dim <= 2 * CTRB_MAX_TUBES, "dim must be in [1, %d]", 2 * CTRB_MAX_TUBES);
+    CTRB_REQUIRE(k >= 1 && k <= 32, "k must be in [1, 32]");
+    CTRB_REQUIRE(N >= 0 && Q >= 0 && weight && topology, "bad argument");
+    if (Q == 0) return CTRB_OK;
+    CTRB_REQUIRE(queries && idx_out && dist_out && (N == 0 || points), "NULL buffer");
+    ctrb::KnnParams P;
+    std::memset(&P, 0, sizeof P);
+    P.dim = dim;
+    P.k = k;
+    P.N = N;
+    P.Q = Q;
+    for (int d = 0; d < dim; ++d) {
+        CTRB_REQUIRE(topology[d] == 1 || topology[d] == 2, "topology[%d] = %d (1 = linear, 2 = circular)", d, topology[d]);
+        P.w[d] = weight[d];
+        P.topo[d] = topology[d];
+    }
+    Stage st(ctx);
+    const double* dp = st.in(points, (size_t)std::max<int64_t>(N, 1) * dim, N > 0 ? mem : CTRB_MEM_DEVICE);
+    const double* dq = st.in(queries, (size_t)Q * dim, mem);
+    int32_t* di = st.out(idx_out, (size_t)Q * k, mem);
+    double* dd = st.out(dist_out, (size_t)Q * k, mem);
+    if (st.rc) return st.rc;
+    int rc = ctrb::launch_knn(ctx, P, dp, dq, di, dd);
+    if (rc) return rc;
+    st.back(idx_out, di, (size_t)Q * k, mem);
+    st.back(dist_out, dd, (size_t)Q * k, mem);
+    return st.finish(mem);
+}
+
 int ctrb_argmin_cost(ctrb_ctx* ctx, int64_t B, const double* cost, int64_t index_base, double* best_cost,
                      int64_t* best_index, int mem) {
     CTRB_ENTER(ctx);

@@ -163,6 +163,16 @@ struct ctrb_env {
 };
 
 namespace ctrb {
+// nearest-neighbour query parameters (ctrb_knn.cu)
+constexpr int kKnnMaxDim = 2 * CTRB_MAX_TUBES;
+struct KnnParams {
+    int dim, k;
+    long long N, Q;
+    double w[kKnnMaxDim];
+    int topo[kKnnMaxDim];
+};
+int launch_knn(ctrb_ctx* ctx, const KnnParams& P, const double* pts, const double* qry, int32_t* idx_out, double* dist_out);
+
 // records the bracketing events of one of the four hot kernels on the launching stream
 struct KernelTimer {
     ctrb_ctx* c;

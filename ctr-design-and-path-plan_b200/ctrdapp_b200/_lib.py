@@ -82,6 +82,7 @@ SYMBOLS = {
     "ctrb_check_collision_batch": (C.c_int, [_vp, _vp, _i64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "ctrb_eval_batch": (C.c_int, [_vp, _vp, _vp, C.POINTER(CostDesc), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   C.c_int]),
+    "ctrb_knn_batch": (C.c_int, [_vp, C.c_int32, _i64, _vp, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int]),
     "ctrb_argmin_cost": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(C.c_double), C.POINTER(_i64), C.c_int]),
 }
 

@@ -113,6 +113,26 @@ class Kinematic(Model):
                                            L.ptr(ftl), L.ptr(mag), L.MEM_HOST))
         return eta, ftl, mag
 
+    def solve_integrate_batch(self, delta_theta, delta_insertion, this_theta, this_insertion, prev_g, prev_offsets,
+                              invert_insert=True, need_g_out=True, want_ftl=False):
+        """kinematic.py:53-80 for K stacked candidates (what RRT._single_iteration does K times).
+        All arguments [K, T]; prev_g / prev_offsets are the parents' curves packed like solve_g_batch's output.
+        -> dict(g, offsets, eta [K,T,6], insert_indices [K,T], prev_indices [K,T], true_insertions [K,T],
+                ftl (packed, or None), ftl_mag [K,4])"""
+        T = self.tube_num
+        this_insertion = _f64(this_insertion).reshape(-1, T)
+        delta_insertion = _f64(delta_insertion).reshape(-1, T)
+        lengths = _f64(self.max_tube_length)[None, :]
+        if invert_insert:  # :57-59
+            this_insertion = lengths - this_insertion
+            delta_insertion = -delta_insertion
+        prev_idx, new_idx = self.calculate_indices_batch(this_insertion - delta_insertion, this_insertion)
+        g, off = self.solve_g_batch(new_idx, this_theta, full=False) if need_g_out else (None, None)
+        eta, ftl, mag = self.eta_ftl_batch(prev_idx, new_idx, delta_theta, prev_g, prev_offsets, want_ftl=want_ftl)
+        true_ins = lengths - new_idx * self.delta_x if invert_insert else new_idx * float(self.delta_x)
+        return {"g": g, "offsets": off, "eta": eta, "insert_indices": new_idx, "prev_indices": prev_idx,
+                "true_insertions": true_ins, "ftl": ftl, "ftl_mag": mag}
+
     # ------------------------------------------------------------------ reference-shaped API (B = 1)
     @staticmethod
     def _split(flat, off, T, width):

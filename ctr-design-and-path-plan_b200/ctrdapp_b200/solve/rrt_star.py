@@ -1,0 +1,87 @@
+"""RRT* over the batched hot path (mirror of ctrdapp/solve/rrt_star.py).
+
+Per accepted candidate the reference (rrt_star.py:13-93) (1) collects up to 16 neighbours within step_bound,
+(2) re-evaluates the follow-the-leader twist with each of them as the parent -- one solve_integrate call each --
+and hangs the node under the cheapest, (3) offers the new node as a parent to the remaining neighbours, again one
+solve_integrate each.  Here the expensive part of a round (g-curves + collision of `batch_size` candidates) is one
+batch as in RRT, and steps (2) and (3) are one eta/FTL batch each over all (candidate, neighbour) pairs of the
+node -- or no model call at all when the cost does not depend on the parent (`heuristic_factory.needs_parent`
+False: obstacle/goal costs only need the parent's running statistic).
+"""
+import numpy as np
+
+from .rrt import RRT
+from .step import delta_rotation_batch
+
+
+class RRTStar(RRT):
+    def __init__(self, model, heuristic_factory, collision_detector, configuration):
+        configuration = dict(configuration)
+        configuration["single_tube_control"] = False  # impossible to maintain with the rewire operation (rrt_star.py:11)
+        super().__init__(model, heuristic_factory, collision_detector, configuration)
+        self.single_tube_control = False
+
+    def _ftl_from_parents(self, parents, to_ins, to_rot):
+        """FTL of moving from each node in `parents` to the configuration (to_ins[i], to_rot[i]) -> result dict of
+        _integrate_and_check without g-curves (need_g_out=False, rrt_star.py:49-51,83-85)."""
+        k = len(parents)
+        ins_p = np.array([self.tree.nodes[j].insertion for j in parents], np.float64).reshape(k, self.tube_num)
+        rot_p = np.array([self.tree.nodes[j].rotation for j in parents], np.float64).reshape(k, self.tube_num)
+        cands = {"new_insert": np.asarray(to_ins, np.float64).reshape(k, -1),
+                 "new_rotation": np.asarray(to_rot, np.float64).reshape(k, -1)}
+        cands["delta_insert"] = cands["new_insert"] - ins_p
+        cands["delta_rotation"] = delta_rotation_batch(rot_p, cands["new_rotation"])
+        return self._integrate_and_check(cands, parents=list(parents), need_g_out=False)
+
+    def _consider(self, c, cands, result):
+        obs_min, goal_dist = result["obs"][c], result["goal"][c]
+        if obs_min < 0:
+            return
+        tree, f = self.tree, self.heuristic_factory
+        new_index = len(tree.nodes)
+        if goal_dist < 0:
+            tree.at_goal.append(new_index)
+            self.found_solution = True
+            goal_dist = 0
+        true_insertion = result["true_insertion"][c]
+        new_rotation = cands["new_rotation"][c].tolist()
+        insert_frac = self._insert_fraction(true_insertion)
+        original = int(cands["neighbor"][c])
+        parent_dependent = getattr(f, "needs_parent", True)
+
+        query_pt = np.empty(2 * self.tube_num)
+        query_pt[0::2] = true_insertion
+        query_pt[1::2] = new_rotation
+        neighbor_indices = tree.find_all_nearest_neighbor(query_pt, self.step_bound)
+
+        # ---- choose the parent (rrt_star.py:40-67)
+        others = [j for j in neighbor_indices if j != original] if parent_dependent else []
+        alt = self._ftl_from_parents(others, [true_insertion] * len(others), [new_rotation] * len(others)) if others else None
+        heur_arr, cost_arr = [], []
+        for j in neighbor_indices:
+            if alt is not None and j != original:
+                h = self._make_heuristic(alt, others.index(j), obs_min, goal_dist, insert_frac)
+            else:
+                h = self._make_heuristic(result, c, obs_min, goal_dist, insert_frac)
+            heur_arr.append(h)
+            cost_arr.append(h.test_cost_from_parent(tree.nodes[j].heuristic))
+        index_min = min(range(len(cost_arr)), key=cost_arr.__getitem__)
+        best_parent, best_heuristic = neighbor_indices[index_min], heur_arr[index_min]
+        tree.insert(true_insertion, new_rotation, best_parent, best_heuristic, result["g"][c], result["insert_indices"][c])
+
+        # ---- rewire the remaining neighbours through the new node (rrt_star.py:69-93)
+        rest = [j for j in neighbor_indices if j != best_parent and tree.no_cycle(new_index, j)]
+        if not rest:
+            return
+        re = None
+        if parent_dependent:
+            re = self._ftl_from_parents([new_index] * len(rest), [tree.nodes[j].insertion for j in rest],
+                                        [tree.nodes[j].rotation for j in rest])
+        for n, j in enumerate(rest):
+            current = tree.nodes[j].heuristic
+            if re is not None and re["ftl"][n] is None and hasattr(f, "create_from_magnitude"):
+                candidate = f.create_from_magnitude(re["ftl_mag"][n], insertion_fraction=getattr(current, "insertion_fraction", None))
+            else:
+                candidate = f.create_from_old(current, follow_the_leader=re["ftl"][n] if re is not None else None)
+            if candidate.test_cost_from_parent(best_heuristic) < current.get_cost():
+                tree.swap_parents(j, new_index, candidate)

@@ -249,6 +249,17 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
  * prefilter tests, [2] exact fp64 cylinder-triangle tests, [3] configurations. Synchronises. */
 int ctrb_ctx_work_counters(ctrb_ctx* ctx, uint64_t out[4]);
 
+/* ---- nearest neighbours of the planner's node store: replaces DynamicTree.nearest_neighbor /
+ *      find_all_nearest_neighbor (dynamic_tree.py:66-120), i.e. pympnn.KDTree_topologies.k_nearest_neighbor,
+ *      for Q queries at once.  points [N][dim] and queries [Q][dim] are interleaved
+ *      [insertion_0, rotation_0, insertion_1, ...] (dynamic_tree.py:57-60), dim = 2 * tube_num <= 8;
+ *      topology[d] = 1 (linear) or 2 (circular, period 2 pi) (dynamic_tree.py:53); weight[d] multiplies the
+ *      per-dimension difference.  idx_out / dist_out [Q][k], ascending distance, ties by lower index;
+ *      missing entries (N < k) are -1 / +inf.  k <= 32. ---- */
+int ctrb_knn_batch(ctrb_ctx* ctx, int32_t dim, int64_t N, const double* points, int64_t Q, const double* queries,
+                   const double* weight /*[dim], host*/, const int32_t* topology /*[dim], host*/, int32_t k,
+                   int32_t* idx_out, double* dist_out, int mem);
+
 /* best (lowest finite cost) configuration of a cost vector: packed key reduction on the
  * device; the multi-GPU driver all-reduces (min) the returned key over NCCL.
  * key = monotone fp64 bits of the cost (upper 64 - 24 bits) ... see DESIGN.md. */

@@ -1,0 +1,210 @@
+"""GPU: the planner mirror (ctrdapp_b200.solve) -- device nearest neighbours vs a NumPy scan, the reference's own
+tree literals (test/test_solve.py), and whole RRT / RRT* runs: the sequential (batch_size 1) search driven through
+the CUDA model + collision path must build the SAME tree as the same search driven through the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import FIXTURES
+from util import gpu_model, orc_model
+
+pytestmark = pytest.mark.gpu
+
+
+def brute_knn(pts, q, w, topo, k):
+    d = np.abs(pts[None, :, :] - q[:, None, :])
+    circ = np.asarray(topo) == 2
+    d[:, :, circ] = np.minimum(d[:, :, circ], np.abs(2 * np.pi - d[:, :, circ]))
+    dist = np.sqrt(((d * w) ** 2).sum(-1))
+    order = np.lexsort((np.broadcast_to(np.arange(len(pts)), dist.shape), dist), axis=1)[:, :k]
+    return order, np.take_along_axis(dist, order, 1)
+
+
+@pytest.mark.parametrize("T,N,k", [(1, 1, 1), (2, 3, 4), (3, 500, 16), (2, 4097, 8), (4, 70, 32)])
+def test_knn_vs_numpy(T, N, k):
+    import ctypes as C
+    from ctrdapp_b200 import _lib as L
+    rng = np.random.default_rng(T * 1000 + N)
+    pts = np.empty((N, 2 * T))
+    pts[:, 0::2] = rng.integers(0, 30, (N, T))           # many exact ties, like insertions on the delta_x grid
+    pts[:, 1::2] = rng.uniform(0, 2 * np.pi, (N, T))
+    if N > 10:
+        pts[5] = pts[3]                                  # duplicate point: tie broken by index
+    q = np.empty((64, 2 * T))
+    q[:, 0::2] = rng.uniform(0, 30, (64, T))
+    q[:, 1::2] = rng.uniform(0, 2 * np.pi, (64, T))
+    q[0] = pts[min(3, N - 1)]
+    w = np.ascontiguousarray([1.0, 1 / 7.5] * T)
+    topo = np.ascontiguousarray([1, 2] * T, np.int32)
+    idx = np.empty((64, k), np.int32)
+    dist = np.empty((64, k))
+    ctx = L.default_context()
+    L.check(L.lib().ctrb_knn_batch(ctx.handle, 2 * T, N, L.ptr(pts), 64, L.ptr(q), L.ptr(w), L.ptr(topo), k, L.ptr(idx),
+                                   L.ptr(dist), L.MEM_HOST))
+    want_i, want_d = brute_knn(pts, q, w, topo, min(k, N))
+    kk = min(k, N)
+    # the device accumulates with fma: ties that NumPy sees as exact can differ in the last bit -> compare distances,
+    # and indices wherever the distance gap to the next candidate is not a rounding artefact
+    np.testing.assert_allclose(dist[:, :kk], want_d, rtol=1e-14, atol=1e-14)
+    clear = np.ones_like(want_i, bool)
+    clear[:, :-1] &= np.diff(want_d, axis=1) > 1e-12
+    clear[:, 1:] &= np.diff(want_d, axis=1) > 1e-12
+    assert np.array_equal(idx[:, :kk][clear], want_i[clear])
+    assert np.all(idx[:, kk:] == -1) and np.all(np.isinf(dist[:, kk:]))
+    assert idx[0, 0] == min(3, N - 1)                     # the duplicate at index 5 loses the tie to index 3
+
+
+def test_reference_tree_literals():
+    """test/test_solve.py:16-170 (scaling [1, 6]); the three find_all_nearest_neighbor literals that are consistent
+    with the code (the first and the `[5,5,5,5] -> []` ones predate the "at least one neighbour" rule, :116-117)."""
+    from ctrdapp_b200.heuristic import OnlyGoalDistance
+    from ctrdapp_b200.solve import DynamicTree, Node
+    h = [OnlyGoalDistance(c) for c in (10, 1, 2, 3)]
+    simple_g, other_g = [[np.eye(4)]], [[np.eye(4)]]
+    other_g[0][0][0:2, 3] = [0.5, 0.1]
+    zeros, ones, twos, threes = [0.0, 0.0], [1.0, 1.0], [2.0, 2.0], [3.0, 3.0]
+    tree = DynamicTree(2, zeros, zeros, h[0], simple_g, 10, [1, 6])
+    assert tree.nearest_neighbor([0.0, 0.0, 0.0, 0.0]) == (zeros, zeros, 0, zeros)
+    assert tree.find_all_nearest_neighbor([0.0, 0.0, 0.0, 0.0], 10) == [0]
+    assert tree.find_all_nearest_neighbor([0.0, 0.0, 0.0, 0.0], 0.0001) == [0]
+    tree.insert(ones, ones, 0, h[0], simple_g, [0, 0])
+    tree.insert(twos, twos, 0, h[0], simple_g, [0, 0])
+    tree.insert(threes, threes, 2, h[0], simple_g, [0, 0])
+    assert len(tree.nodes) == 4 and tree.nodes[0].children == [1, 2] and tree.nodes[2].children == [3]
+
+    final = DynamicTree(2, zeros, zeros, h[0], simple_g, 10, [1, 6])
+    final.insert(ones, ones, 0, h[1], simple_g, [0, 0])
+    final.insert(twos, twos, 1, h[2], simple_g, [0, 0])
+    final.insert(threes, threes, 0, h[3], other_g, [1, 1])
+    assert final.nearest_neighbor([0.0, 0.0, 0.0, 0.0]) == (zeros, zeros, 0, zeros)
+    assert final.nearest_neighbor([1.0, 1.0, 1.0, 1.0]) == (ones, ones, 1, zeros)
+    assert final.nearest_neighbor([0.8, 0.8, 0.7, 0.7]) == (ones, ones, 1, zeros)
+    assert final.nearest_neighbor([2.5, 2.5, 2.49, 2.49]) == (twos, twos, 2, ones)
+    assert final.nearest_neighbor([2.5, 2.5, 2.51, 2.51]) == (threes, threes, 3, zeros)
+    assert final.find_all_nearest_neighbor([2.0, 1.0, 1.0, 1.0], 1.0001) == [1]
+    assert sorted(final.find_all_nearest_neighbor([2.0, 2.0, 1.0, 1.0], 2.5)) == [0, 1, 2, 3]
+    assert final.find_all_nearest_neighbor([2.0, 2.0, 1.0, 1.0], 2.5)[:2] == [1, 2]
+    assert final.find_all_nearest_neighbor([2.0, 2.0, 0.0, 0.0], 2.5)[0] == 1
+    assert sorted(final.find_all_nearest_neighbor([2.0, 2.0, 0.0, 0.0], 2.5)) == [0, 1, 2]
+    assert final.get_costs(0) == [10] and final.get_costs(2) == [2, 1, 10] and final.get_costs(3) == [3, 10]
+    assert final.get_tube_data(2) == ([twos, ones, zeros], [twos, ones, zeros], [[0, 0]] * 3)
+    assert final.get_tube_data(3) == ([threes, zeros], [threes, zeros], [[1, 1], [0, 0]])
+    assert final.get_tube_curves(3)[0] is other_g and len(final.get_tube_curves(2)) == 3
+    with pytest.raises(ValueError):
+        Node([0], [0], 2, h[0], simple_g, [0, 0])
+    # test_no_cycle (:139-170)
+    t = DynamicTree(1, [0.0], [0.0], h[0], simple_g, 10, [1, 6])
+    for parent in (0, 1, 2, 0, 4, 4, 2, 7):
+        t.insert([0.0], [0.0], parent, h[0], simple_g, [1])
+    assert t.no_cycle(5, 3) and t.no_cycle(5, 2) and t.no_cycle(5, 1)
+    assert not t.no_cycle(3, 2) and not t.no_cycle(8, 2) and not t.no_cycle(8, 1) and t.no_cycle(8, 4)
+    with pytest.raises(ValueError):
+        t.no_cycle(0, 3)
+
+
+# ---------------------------------------------------------------- whole searches
+CONF = {"tube_number": 3, "tube_radius": {"outer": [1.2, 0.9, 0.6], "inner": [1.0, 0.7, 0.4]}, "tube_lengths": [33, 66, 99],
+        "iteration_number": 300, "step_bound": 7.5, "rotation_max": 0.5, "single_tube_control": False, "seed": 42,
+        "goal_weight": 3.0, "only_tip": True, "insertion_weight": 0.25}
+HDICT = {"square_obstacle_avg_plus_weighted_goal": ["goal_weight"], "only_goal_distance": [],
+         "follow_the_leader": ["only_tip"], "follow_the_leader_w_insertion": ["only_tip", "insertion_weight"],
+         "follow_the_leader_translation": ["only_tip"]}
+
+
+class OracleModel:
+    """The CPU oracle behind the reference's model interface (test infrastructure)."""
+
+    def __init__(self, name):
+        from oracle import oracle as orc
+        from models_def import MODELS
+        self.orc, self.m = orc, orc_model(name)
+        _, dof, q, lengths, dx = MODELS[name]
+        self.q, self.tube_num, self.max_tube_length, self.delta_x = q, len(lengths), lengths, dx
+
+    def solve_integrate(self, delta_theta, delta_insertion, this_theta, this_insertion, prev_g, invert_insert=True,
+                        need_g_out=True):
+        return self.orc.solve_integrate(self.m, delta_theta, delta_insertion, this_theta, this_insertion, prev_g,
+                                        invert_insert, need_g_out)
+
+
+def _factory(name):
+    from ctrdapp_b200.heuristic import create_heuristic_factory
+    return create_heuristic_factory(dict(CONF, heuristic_type=name), HDICT)
+
+
+def _same_tree(a, b):
+    assert len(a.tree.nodes) == len(b.tree.nodes) > 10
+    for x, y in zip(a.tree.nodes, b.tree.nodes):
+        assert x.parent == y.parent and x.insert_indices == y.insert_indices
+        assert x.insertion == y.insertion and x.rotation == y.rotation
+        assert x.get_cost() == pytest.approx(y.get_cost(), rel=1e-9)
+    assert a.tree.at_goal == b.tree.at_goal
+
+
+@pytest.mark.parametrize("solver,heuristic,single", [("rrt", "square_obstacle_avg_plus_weighted_goal", False),
+                                                     ("rrt", "follow_the_leader_w_insertion", True),
+                                                     ("rrt_star", "follow_the_leader", False)])
+def test_sequential_search_equals_oracle_driven_search(solver, heuristic, single):
+    from oracle import oracle as orc
+    from ctrdapp_b200.collision import CollisionChecker
+    from ctrdapp_b200.solve import create_solver
+    env = FIXTURES / "env_c3_colon_straight.json"
+    conf = dict(CONF, solver_type=solver, single_tube_control=single, iteration_number=400)
+    gpu = create_solver(gpu_model("c3_three_tube"), _factory(heuristic), CollisionChecker(env), conf)
+    cpu = create_solver(OracleModel("c3_three_tube"), _factory(heuristic), orc.Env.from_json(env), conf)
+    _same_tree(gpu, cpu)
+    cost, best = gpu.get_best_cost()
+    assert np.isfinite(cost) and 0 <= best < len(gpu.tree.nodes)
+
+
+@pytest.mark.parametrize("solver", ["rrt", "rrt_star"])
+def test_batched_search_invariants(solver, tmp_path):
+    """batch_size 64: every stored node is collision-free according to the oracle, costs follow the parent chain,
+    the saved tree reloads (TreeFromFile) with the same structure."""
+    from oracle import oracle as orc
+    from ctrdapp_b200.collision import CollisionChecker
+    from ctrdapp_b200.solve import create_solver
+    env = FIXTURES / "env_c3_colon_straight.json"
+    conf = dict(CONF, solver_type=solver, batch_size=64, iteration_number=1024)
+    m = gpu_model("c3_three_tube")
+    s = create_solver(m, _factory("square_obstacle_avg_plus_weighted_goal"), CollisionChecker(env), conf)
+    assert s.rounds == 16 and len(s.tree.nodes) > 50
+    oenv = orc.Env.from_json(env)
+    for i in range(1, len(s.tree.nodes), 7):
+        node = s.tree.nodes[i]
+        obs, goal = oenv.check_collision(node.g_curves, CONF["tube_radius"]["outer"])
+        assert obs > 0
+        assert abs(node.heuristic.store_obstacle_min - obs) < 1e-6
+        chain = s.tree.get_index_list(i)
+        own = [(1 / s.tree.nodes[j].heuristic.store_obstacle_min) ** 2 for j in chain[:-1]]
+        h = node.heuristic
+        assert h.generation == len(chain) - 1
+        # running mean over the path; the root enters with generation 0, i.e. weight 0 (obstacles_and_goal.py:67-88)
+        assert h.avg_obstacle_min == pytest.approx(np.mean(own), rel=1e-9)
+    s.save_tree(tmp_path)
+    lines = (tmp_path / "tree.txt").read_text().splitlines()
+    assert len(lines) == len(s.tree.nodes) and lines[0].startswith("0 | 0, 0, 0 | 0, 0, 0 | None | ")
+    s.save_best_solution(tmp_path)
+    assert (tmp_path / "solution_path.txt").read_text().startswith("Q: ")
+
+
+def test_c4_follow_the_leader_goal_mesh():
+    """BASELINE configs[3]: one tube r = 5 (test/configuration/config_ftl.yaml: linear dof 2, delta_x 2.5, step_bound
+    7.5, RRT*, follow_the_leader_translation, only_tip) against the goal MESH follow_the_leader_goal_multiple.STL."""
+    from ctrdapp_b200.collision import CollisionChecker
+    from ctrdapp_b200.model.kinematic import Kinematic
+    from ctrdapp_b200.solve import create_solver
+    conf = {"tube_number": 1, "tube_radius": {"outer": [5.0], "inner": [4.0]}, "tube_lengths": [50], "delta_x": 2.5,
+            "iteration_number": 800, "step_bound": 7.5, "rotation_max": 0.1745, "single_tube_control": True,
+            "solver_type": "rrt_star", "heuristic_type": "follow_the_leader_translation", "only_tip": True,
+            "batch_size": 32, "seed": 3}
+    m = Kinematic(1, [np.array([0.03, 0.0005])], [2], [50], 2.5, ["linear"])
+    from ctrdapp_b200.heuristic import create_heuristic_factory
+    s = create_solver(m, create_heuristic_factory(conf, HDICT), CollisionChecker(FIXTURES / "env_ftl_goal.json"), conf)
+    assert len(s.tree.nodes) == 801                       # no obstacles: every candidate is kept
+    cost, best = s.get_best_cost()
+    assert np.isfinite(cost) and cost >= 0
+    # FTL costs are running sums of non-negative magnitudes along the path
+    for i in range(1, len(s.tree.nodes), 13):
+        node = s.tree.nodes[i]
+        if any(v != 0.0 for v in node.insertion):
+            assert node.get_cost() >= s.tree.nodes[node.parent].get_cost() - 1e-12 or node.heuristic.generation == 0
