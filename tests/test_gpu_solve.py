@@ -208,3 +208,31 @@ def test_c4_follow_the_leader_goal_mesh():
         node = s.tree.nodes[i]
         if any(v != 0.0 for v in node.insertion):
             assert node.get_cost() >= s.tree.nodes[node.parent].get_cost() - 1e-12 or node.heuristic.generation == 0
+
+
+def test_nelder_mead_design_optimisation(tmp_path):
+    """BASELINE configs[4] in miniature: Nelder-Mead over the 5 design parameters of a 2-tube robot, the objective of
+    a design being the best cost of a batched RRT run against it (neldermead.py:101-135)."""
+    from ctrdapp_b200.collision import CollisionChecker
+    from ctrdapp_b200.heuristic import create_heuristic_factory
+    from ctrdapp_b200.optimize import create_optimizer
+    conf = {"optimizer_type": "nelder_mead", "optimizer_precision": 0.1, "optimize_iterations": 14,
+            "solver_type": "rrt", "model_type": "kinematic", "heuristic_type": "square_obstacle_avg_plus_weighted_goal",
+            "goal_weight": 3.0, "tube_number": 2, "tube_radius": {"outer": [0.9, 0.6], "inner": [0.7, 0.4]},
+            "tube_lengths": [60, 120], "delta_x": 1, "strain_bases": ["linear", "linear"], "q_dof": [2, 3],
+            "iteration_number": 256, "batch_size": 64, "step_bound": 7.5, "rotation_max": 0.5,
+            "single_tube_control": False, "seed": 9}
+    cc = CollisionChecker(FIXTURES / "env_boxes_multi.json")
+    opt = create_optimizer(create_heuristic_factory(conf, HDICT), cc, [0.02, 0.001, 0.05, 0.0001, 0.002], conf)
+    res = opt.find_min()
+    assert res.num_function_eval >= 6 and res.best_solver is not None
+    assert len(res.optimize_process) == res.num_function_eval + res.num_speculative_eval
+    costs = [e["cost"] for e in res.optimize_process]
+    assert min(costs) == pytest.approx(res.best_solver.get_best_cost()[0])
+    assert len(res.best_q) == 5
+    res.save_result(tmp_path)
+    for name in ("tree.txt", "solution_path.txt", "optimize_result.txt", "optimize_process.txt"):
+        assert (tmp_path / name).stat().st_size > 0
+    assert (tmp_path / "optimize_result.txt").read_text().startswith("Optimizer Success: ")
+    # the objective is deterministic (seeded planner): re-evaluating the best design gives the same cost
+    assert opt.solver_heuristic(res.optimize_process[int(np.argmin(costs))]["q"]) == pytest.approx(min(costs))
