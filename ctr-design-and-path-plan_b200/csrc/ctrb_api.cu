@@ -162,8 +162,8 @@ int ctrb_ctx_create(int device, ctrb_ctx** out) {
             CTRB_CUDA(cudaEventCreate(&c->kev[k][i]));
             CTRB_CUDA(cudaEventRecord(c->kev[k][i], c->stream));
         }
-    CTRB_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
-    CTRB_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long)));
+    CTRB_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
+    CTRB_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)));
     cudaDeviceProp prop;
     CTRB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -248,7 +248,7 @@ int ctrb_static_last_fallbacks(ctrb_ctx* c, uint64_t* count) {
     CTRB_CUDA(cudaSetDevice(c->device));
     CTRB_CUDA(cudaStreamSynchronize(c->stream));
     unsigned long long h = 0;
-    CTRB_CUDA(cudaMemcpy(&h, c->d_counters + 7, sizeof h, cudaMemcpyDeviceToHost));
+    CTRB_CUDA(cudaMemcpy(&h, c->d_counters + 10, sizeof h, cudaMemcpyDeviceToHost));
     *count = h;
     return CTRB_OK;
 }

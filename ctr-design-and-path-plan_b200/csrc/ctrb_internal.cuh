@@ -83,7 +83,7 @@ struct ctrb_ctx {
     // grow-only device scratch
     void* scratch[16];
     size_t scratch_bytes[16];
-    unsigned long long* d_counters;  // [8] work counters + scheduler tickets
+    unsigned long long* d_counters;  // [16]: [0..7] collision work counters + ticket, [8..10] static-solve tickets + fallback count
     int sm_count;
 };
 

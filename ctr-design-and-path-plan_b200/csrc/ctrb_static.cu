@@ -502,7 +502,6 @@ __global__ void __launch_bounds__(kSWarps * 32, 5)
         if (lane == 0) st_setup(sm, idx + b * T, theta + b * T, M.cfg);
         if (lane < n) M.x[lane] = x0 ? x0[(x0_per_config ? b * n : 0) + lane] : sm.x0[lane];
         __syncwarp();
-        const StCfg& c = M.cfg;
         int nfev = 0;
         const int info = st_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, &nfev);
         __syncwarp();
@@ -511,7 +510,32 @@ __global__ void __launch_bounds__(kSWarps * 32, 5)
             if (nfev_out) nfev_out[b] = nfev;
             if (info_out) info_out[b] = info;
         }
-        if (g_out) st_write_curves(sm, c, M.x, offsets, b, g_out, lane);
+        __syncwarp();
+    }
+}
+
+// Section curves from the solved unknowns (Static.solve_g's integrate_g calls, static.py:110-130): one warp per
+// configuration.  A kernel of its own: integrate_g's code (Magnus exponentials, SE(3) scan) is as large as the
+// solver's inner loop, and running it at the end of every solve evicted that loop from the instruction cache
+// (+46 % on the fast kernel, profiles/README.md).
+constexpr int kCWarps = 8;
+struct CurveMem {
+    StCfg cfg;
+    double q[kNV];
+};
+__global__ void __launch_bounds__(kCWarps * 32)
+    static_curves_kernel(const __grid_constant__ StModel sm, long long B, const int32_t* __restrict__ idx,
+                         const double* __restrict__ theta, const double* __restrict__ sol,
+                         const long long* __restrict__ offsets, double* __restrict__ g_out) {
+    __shared__ CurveMem mem[kCWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    CurveMem& M = mem[warp];
+    const int T = sm.mc.T, n = sm.nq;
+    for (long long b = (long long)blockIdx.x * kCWarps + warp; b < B; b += (long long)gridDim.x * kCWarps) {
+        if (lane == 0) st_setup(sm, idx + b * T, theta + b * T, M.cfg);
+        if (lane < n) M.q[lane] = sol[b * n + lane];
+        __syncwarp();
+        st_write_curves(sm, M.cfg, M.q, offsets, b, g_out, lane);
         __syncwarp();
     }
 }
@@ -643,8 +667,14 @@ int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int
     int per_sm = 1;
     CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, static_solve_kernel, kSWarps * 32, smem));
     int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * std::max(per_sm, 1));
-    // d_counters[5] = QR ticket, [6] = fast ticket, [7] = fallback count
-    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 5, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    // d_counters[8] = QR ticket, [9] = fast ticket, [10] = fallback count ([0..7] belong to the collision kernels)
+    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 8, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    if (g_out && !sol_out) {  // the curves kernel reads the solutions back
+        void* p = nullptr;
+        int rc = ctx_scratch(ctx, 13, (size_t)B * sm.nq * sizeof(double), &p);
+        if (rc) return rc;
+        sol_out = (double*)p;
+    }
     long long* fb_list = nullptr;
     if (!qr_only) {
         void* p = nullptr;
@@ -657,13 +687,19 @@ int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int
         if (!qr_only) {
             KernelTimer kf(ctx, CTRB_KERNEL_STATIC_FAST);
             int rc = launch_static_fast(ctx, sm, B, idx, theta, x0, x0_per_config, xtol > 0 ? xtol : 1.49012e-8, offsets, g_out,
-                                        sol_out, nfev_out, info_out, fb_list, ctx->d_counters + 7, ctx->d_counters + 6);
+                                        sol_out, nfev_out, info_out, fb_list, ctx->d_counters + 10, ctx->d_counters + 9);
             if (rc) return rc;
         }
         static_solve_kernel<<<grid, kSWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config,
                                                                       xtol > 0 ? xtol : 1.49012e-8, offsets, g_out, sol_out,
-                                                                      nfev_out, info_out, ctx->d_counters + 5, fb_list,
-                                                                      ctx->d_counters + 7);
+                                                                      nfev_out, info_out, ctx->d_counters + 8, fb_list,
+                                                                      ctx->d_counters + 10);
+        ctx->launches++;
+        if (g_out) {
+            const long long blocks = (B + kCWarps - 1) / kCWarps;
+            const int cgrid = (int)std::min<long long>(blocks, (long long)ctx->sm_count * 16);
+            static_curves_kernel<<<cgrid, kCWarps * 32, 0, ctx->stream>>>(sm, B, idx, theta, sol_out, offsets, g_out);
+        }
     }
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());

@@ -326,7 +326,6 @@ __global__ void __launch_bounds__(kFWarps * 32, 3)
             if (nfev_out) nfev_out[b] = nfev;
             if (info_out) info_out[b] = info;
         }
-        if (g_out) st_write_curves(sm, c, M.x, offsets, b, g_out, lane);
         __syncwarp();
     }
 }

@@ -9,6 +9,8 @@ sys.path[:0] = [str(ROOT), str(ROOT / "ctr-design-and-path-plan_b200"), str(ROOT
 from util import gpu_static  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
+import os
+WANT_G = bool(int(os.environ.get("WANT_G", "0")))
 cases = [a for a in sys.argv[2:]] or ["c1:1:8", "c1:1:33", "c3:1:8", "c3:2:8", "c3:1:33", "c3:2:33"]
 models = {"c1": gpu_static("c1_two_tube"), "c3": gpu_static("c3_three_tube")}
 for case in cases:
@@ -22,7 +24,7 @@ for case in cases:
     idx = (N[None, :] - 1 - e).astype(np.int32)
     th = rng.uniform(0, 2 * np.pi, (B, T))
     m.solve_g_batch(idx[:2000], th[:2000], want_g=False)
-    res = m.solve_g_batch(idx, th, want_g=False)
+    res = m.solve_g_batch(idx, th, want_g=WANT_G)
     tot, fast, fb = m.ctx.last_kernel_ms("static_solve"), m.ctx.last_kernel_ms("static_fast"), m.ctx.static_fallbacks()
     print(f"{case}: total {tot:.1f} ms = {B / tot / 1e3:.2f} Mcfg/s | fast kernel {fast:.1f} ms "
           f"({(B - fb) / max(fast, 1e-9) / 1e3:.2f} Mcfg/s over {B - fb}) | QR kernel {tot - fast:.1f} ms "
