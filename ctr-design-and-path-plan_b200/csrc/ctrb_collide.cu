@@ -42,11 +42,15 @@ constexpr int kCWarps = CTRB_EVAL_WARPS;      // warps (= configurations in flig
 constexpr int kTopNodes = CTRB_TOP_NODES;     // BVH nodes staged in shared memory (BFS prefix = top levels)
 constexpr int kStack = 48;
 
+constexpr int kQueue = 96;  // deferred exact tests per warp (drained 32 at a time, all lanes in lock-step)
 struct WarpCtl {
     int bound_bits;   // float bits of an upper bound on the config's min distance (>= 0 => int-ordered)
     int collided;
     int ticket;
-    int pad;
+    int qcount;
+    int q_tri[kQueue];    // triangle (leaf order) of a candidate pair
+    int q_item[kQueue];   // its cylinder
+    float q_lb[kQueue];   // fp32 lower bound on their distance
 };
 
 struct EvalParams {
@@ -323,6 +327,7 @@ __global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_
             ctl->bound_bits = __float_as_int(FLT_MAX);
             ctl->collided = 0;
             ctl->ticket = 0;
+            ctl->qcount = 0;
         }
         __syncwarp();
 
@@ -336,31 +341,150 @@ __global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_
         double best = DBL_MAX;
         const bool have_obstacles = env.obs.ntri > 0 || env.nprim > 0;
         if (have_obstacles) {
-            for (;;) {
-                const int item = atomicAdd(&ctl->ticket, 1);
-                if (item >= ncyl || *(volatile int*)&ctl->collided) break;
+            // Every lane walks the BVH for one cylinder at a time (private stack, fp32 culling against the bound all
+            // lanes share).  The decisive fp64 cylinder<->triangle tests are NOT done inside the walk, where each lane
+            // would run the ~1.5 k-instruction routine alone while the others wait (ncu: 3.6 of 32 lanes active): a
+            // surviving (cylinder, triangle) pair goes into a shared-memory queue and the whole warp drains the queue
+            // in lock-step, one pair per lane.
+            volatile int* vbound = &ctl->bound_bits;
+            volatile int* vcoll = &ctl->collided;
+            const DevBvh& bvh = env.obs;
+            const float slack = bvh.slack;
+            auto cylinder_of = [&](int item, d3& c, d3& a, double& h, double& r) {
                 int n = 0;
 #pragma unroll
                 for (int q = 1; q < CTRB_MAX_TUBES; ++q)
                     if (q < T && item >= cyl_first[q]) n = q;
-                const int node = first[n] + (item - cyl_first[n]);
-                const double* pf = s_pos + (size_t)node * 3;
+                const double* pf = s_pos + (size_t)(first[n] + (item - cyl_first[n])) * 3;
                 d3 f = {pf[0], pf[1], pf[2]}, t = {pf[3], pf[4], pf[5]};
                 d3 vec = t - f;
-                double len = sqrt(dot(vec, vec));           // collision_checker.py:130-131
-                d3 c = f + 0.5 * vec;                        // mid_point
-                d3 a = (1.0 / len) * vec;                    // unit_vec -> cylinder axis
-                const double h = 0.5 * len, r = P.rad[n];
-                if (env.obs.ntri > 0) cylinder_vs_mesh(env.obs, s_top, ntop, c, a, h, r, ctl, best, wk);
-                for (int k = 0; k < env.nprim && !*(volatile int*)&ctl->collided; ++k) {
-                    double d = cylinder_vs_prim(env.prims[k], c, a, h, r, best);
-                    if (d <= 0.0) *(volatile int*)&ctl->collided = 1;
-                    else if (d < best) {
-                        best = d;
-                        atomicMin(&ctl->bound_bits, __float_as_int(__double2float_ru(d)));
+                const double len = sqrt(dot(vec, vec));    // collision_checker.py:130-131
+                c = f + 0.5 * vec;                          // mid_point
+                a = (1.0 / len) * vec;                      // unit_vec -> cylinder axis
+                h = 0.5 * len;
+                r = P.rad[n];
+            };
+            auto exact_pair = [&](int item, int t, float bound) {
+                d3 c, a;
+                double h, r;
+                cylinder_of(item, c, a, h, r);
+                const double* tq = bvh.tri64 + (size_t)t * 9;
+                d3 t0 = {__ldg(tq + 0), __ldg(tq + 1), __ldg(tq + 2)};
+                d3 t1 = {__ldg(tq + 3), __ldg(tq + 4), __ldg(tq + 5)};
+                d3 t2 = {__ldg(tq + 6), __ldg(tq + 7), __ldg(tq + 8)};
+                const double d = cyl_tri_dist(c, a, h, r, t0, t1, t2, (double)bound);
+                wk.exact++;
+                if (d <= 0.0) {
+                    *vcoll = 1;
+                } else if (d < best) {
+                    best = d;
+                    atomicMin(&ctl->bound_bits, __float_as_int(__double2float_ru(d)));
+                }
+            };
+            // every decision that guards a __syncwarp is taken on lane 0's view (lanes of a warp do not run in
+            // lock-step: a flag read lane by lane can differ, and lanes would wait at different barriers)
+            auto drain = [&]() {
+                __syncwarp();
+                const int qc = min(__shfl_sync(0xffffffffu, *(volatile int*)&ctl->qcount, 0), kQueue);
+                for (int base = 0; base < qc; base += 32) {
+                    if (__shfl_sync(0xffffffffu, *vcoll, 0)) break;
+                    const int k = base + lane;
+                    const float bound = __int_as_float(*vbound);
+                    if (k < qc && ctl->q_lb[k] <= bound) exact_pair(ctl->q_item[k], ctl->q_tri[k], bound);
+                    __syncwarp();
+                }
+                __syncwarp();
+                if (lane == 0) ctl->qcount = 0;
+                __syncwarp();
+            };
+            int stack[kStack];
+            int sp = 0, item = 0;
+            bool exhausted = false;  // this lane has seen the end of the cylinder ticket
+            f3 cf = {0.f, 0.f, 0.f};
+            float rb = 0.f, rin = 0.f;
+            for (;;) {
+                if (sp == 0 && !exhausted && !*vcoll) {  // next cylinder for this lane
+                    item = atomicAdd(&ctl->ticket, 1);
+                    exhausted = item >= ncyl;
+                    if (!exhausted) {
+                        d3 c, a;
+                        double h, r;
+                        cylinder_of(item, c, a, h, r);
+                        for (int k = 0; k < env.nprim && !*vcoll; ++k) {
+                            const double d = cylinder_vs_prim(env.prims[k], c, a, h, r, best);
+                            if (d <= 0.0) *vcoll = 1;
+                            else if (d < best) {
+                                best = d;
+                                atomicMin(&ctl->bound_bits, __float_as_int(__double2float_ru(d)));
+                            }
+                        }
+                        if (bvh.ntri > 0 && !*vcoll) {
+                            cf = f3{(float)c.x, (float)c.y, (float)c.z};
+                            rb = __fsqrt_ru(__fmaf_ru((float)h, (float)h, (float)r * (float)r)) * 1.000001f;
+                            rin = fminf((float)h, (float)r);
+                            stack[sp++] = 0;
+                        }
                     }
                 }
+                if (!__any_sync(0xffffffffu, sp > 0 || (!exhausted && !*vcoll))) break;
+                if (sp > 0) {
+                    if (*vcoll) {
+                        sp = 0;
+                    } else {
+                        const int ni = stack[--sp];
+                        const BvhNode nd = load_node(bvh, s_top, ntop, ni);
+                        wk.nodes++;
+                        float bound = __int_as_float(*vbound);
+                        const float reach = bound + rb + slack;
+                        const float reach2 = reach * reach * 1.000001f;
+                        float d0 = aabb_dist2(nd.lo0, nd.hi0, cf);
+                        float d1 = aabb_dist2(nd.lo1, nd.hi1, cf);
+                        int l0 = nd.c0, l1 = nd.c1;
+                        if (d1 < d0) {  // near child first
+                            float t = d0; d0 = d1; d1 = t;
+                            int ti = l0; l0 = l1; l1 = ti;
+                        }
+                        if (l1 >= 0 && d1 <= reach2 && sp < kStack) stack[sp++] = l1;
+                        if (l0 >= 0 && d0 <= reach2 && sp < kStack) stack[sp++] = l0;
+#pragma unroll 1
+                        for (int side = 0; side < 2; ++side) {
+                            const int link = side == 0 ? l0 : l1;
+                            const float dd = side == 0 ? d0 : d1;
+                            if (link >= 0 || dd > reach2) continue;
+                            const int code = ~link;
+                            const int tfirst = code >> 3, tcnt = (code & 7) + 1;
+#pragma unroll 1
+                            for (int t = tfirst; t < tfirst + tcnt && !*vcoll; ++t) {
+                                const float4* tp = bvh.tri32 + (size_t)t * 3;
+                                float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                                const float dpt = sqrtf(point_tri_dist2<f3, float>(cf, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z},
+                                                                                    f3{v2.x, v2.y, v2.z}));
+                                wk.pre++;
+                                if (dpt + slack < rin) {  // a ball of radius min(h, r) about the centre lies inside the cylinder
+                                    *vcoll = 1;
+                                    break;
+                                }
+                                // the centre belongs to the cylinder: d(cyl, tri) <= dpt
+                                atomicMin(&ctl->bound_bits, __float_as_int(dpt + slack));
+                                bound = __int_as_float(*vbound);
+                                const float lb = dpt - rb - slack;  // d(cyl, tri) >= dpt - rb
+                                if (lb > bound) continue;
+                                const int slot = atomicAdd(&ctl->qcount, 1);
+                                if (slot < kQueue) {
+                                    ctl->q_tri[slot] = t;
+                                    ctl->q_item[slot] = item;
+                                    ctl->q_lb[slot] = lb;
+                                } else {
+                                    exact_pair(item, t, bound);  // queue full: decide here (rare)
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (__shfl_sync(0xffffffffu, *(volatile int*)&ctl->qcount, 0) >= 32) drain();
             }
+            drain();
         }
         __syncwarp();
 #pragma unroll
