@@ -45,8 +45,9 @@ WORKLOADS = {  # name -> (model, exposure lo, hi, default configs per step per G
 }
 BYTES_PER_CONFIG = 3 * (4 + 8) + (8 + 8 + 8 + 1)  # idx + theta in, obstacle_min + goal_dist + cost + bit out
 # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (30000 C3 shallow configurations,
-# profiles/r1_ncu_static_fast_qr.json) divided by the configurations each kernel solved
-NCU_DRAM_BYTES_PER_CONFIG = {"static_fast_kernel": 2401.0, "static_solve_kernel": 5416.0}
+# profiles/r1_ncu_final_four_kernels.json) divided by the configurations each kernel handled (22942 / 7058 / 30000);
+# the curves kernel's writes were still partly in the 126 MB L2 when the capture ended
+NCU_DRAM_BYTES_PER_CONFIG = {"static_fast_kernel": 51.0, "static_solve_kernel": 153.0, "static_curves_kernel": 853.0}
 
 
 def make_inputs(B, seed, lo, hi):
@@ -327,14 +328,13 @@ def main():
         # + 2 rank-one updates, or dogleg + r1updt + r1mpyq: ~9 n^2), n = 30
         n_jac = max(1.0, nfev_mean / 45.0)
         flop64 = nfev_mean * 2600.0 + n_jac * 2 * 30 ** 3 + max(nfev_mean - 30 * n_jac, 1.0) * 9 * 30 ** 2 + nodes_mean * 260.0
-        # DRAM traffic per configuration from the ncu --set full capture of the same kernels (profiles/): 2.40 KB
-        # (fast kernel) and 5.42 KB (QR kernel) per solved configuration, scaled to this launch
+        # DRAM traffic per configuration from the ncu --set full capture of the same kernels, scaled to this launch
         fb = float(np.mean(fallbacks)) / B
         traffic = ((1 - fb) * NCU_DRAM_BYTES_PER_CONFIG["static_fast_kernel"]
-                   + fb * NCU_DRAM_BYTES_PER_CONFIG["static_solve_kernel"]) * B
+                   + fb * NCU_DRAM_BYTES_PER_CONFIG["static_solve_kernel"] + NCU_DRAM_BYTES_PER_CONFIG["static_curves_kernel"]) * B
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_static_fast_qr.json, per configuration x launch size",
-                    "kernel": "static_fast_kernel + static_solve_kernel (one launch sequence = the static solve)",
+                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_final_four_kernels.json, per configuration x launch size",
+                    "kernel": "static_fast_kernel + static_solve_kernel + static_curves_kernel (one launch sequence = Static.solve_g)",
                     "kernel_ms": k_ms, "fast_kernel_ms": float(np.mean(fast_ms)),
                     "qr_fallback_kernel_ms": k_ms - float(np.mean(fast_ms)), "qr_fallback_fraction": fb,
                     "algorithmic_bytes_per_config": bpc, "peak_source": peak_src,

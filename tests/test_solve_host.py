@@ -96,3 +96,21 @@ def test_reference_heuristic_literals():
     g = OnlyGoalDistance(7.5)
     g.calculate_cost_from_parent(g)
     assert g.get_cost() == 7.5
+
+
+def test_stl_loader_binary_and_ascii():
+    """init_collision.py:59-88 through the mirror's parse_mesh: SURVEY App. C triangle counts and bounding boxes;
+    sphere_100mm.STL is ASCII (CRLF), the colon files are binary although their header starts with 'solid'."""
+    from conftest import FIXTURES
+    from ctrdapp_b200.collision.init_collision import parse_mesh
+    from oracle import oracle as orc
+    expect = {"colon_straight.STL": (11492, [-312.90, -154.22, 214.47], [-234.00, 0.88, 264.35]),
+              "sphere_100mm.STL": (2400, [-60.5, -49.6, -39.4], [17.9, 29.0, 39.4]),
+              "mm_simple.STL": (12, [0, 0, 0], [1, 2, 3]),
+              "follow_the_leader_goal_multiple.STL": (5268, [-7, -34, -34], [46, 34, 34])}
+    for name, (ntri, lo, hi) in expect.items():
+        v, tris = parse_mesh(FIXTURES / name)
+        assert v.dtype == np.float32 and len(tris) == ntri and v.shape == (3 * ntri, 3)
+        np.testing.assert_allclose(v.min(0), lo, atol=0.06)
+        np.testing.assert_allclose(v.max(0), hi, atol=0.06)
+        np.testing.assert_array_equal(orc.read_stl(FIXTURES / name).reshape(-1, 3), v.astype(np.float64))

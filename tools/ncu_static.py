@@ -21,3 +21,10 @@ for _ in range(2):
     res = m.solve_g_batch(idx, th, want_g=True)
 print("converged", res["converged"].mean(), "nfev", res["nfev"].mean(), "ms", m.ctx.last_kernel_ms("static_solve"),
       "fast ms", m.ctx.last_kernel_ms("static_fast"), "fallbacks", m.ctx.static_fallbacks())
+
+# the fused static evaluation (solve -> curves -> collision -> cost): launches static_fast_kernel, static_solve_kernel,
+# static_curves_kernel and chain_eval_kernel<false> once more -- the four launches an ncu capture with -s 6 -c 4 records
+from ctrdapp_b200.collision import CollisionChecker  # noqa: E402
+cc = CollisionChecker(ROOT / "tests/fixtures/env_c3_colon_straight.json", ctx=m.ctx)
+obs, goal, cost, coll = cc.evaluate_batch(m, idx, th, [1.2, 0.9, 0.6], goal_weight=3.0)
+print("collide", (obs < 0).mean(), "chain_eval ms", m.ctx.last_kernel_ms("chain_eval"), "work", m.ctx.work_counters())
