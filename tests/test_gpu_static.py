@@ -109,6 +109,43 @@ def test_random_batch_vs_oracle():
     assert worst_g < 1e-4, worst_g  # both stopped at xtol = 1.49e-8: curves agree to the solver tolerance
 
 
+def test_random_three_tube_batch_vs_oracle():
+    """600 random C3 configurations (BASELINE configs[2]'s model), exposure 2-12 nodes per tube, i.e. the
+    configurations the explicit-inverse kernel solves itself: converged flag, root and evaluation count against the
+    CPU oracle's literal hybrd; then the same batch with one-step sections mixed in, which must come back through the
+    QR kernel with the flag the oracle reports in all but the chaotic cases."""
+    from oracle import oracle as orc
+    name = "c3_three_tube"
+    m, s = gpu_static(name), orc_static(name)
+    N = np.asarray(m.num_discrete_points)
+    rng = np.random.default_rng(2003)
+    B = 600
+    e = rng.integers(2, 13, (B, 3))
+    idx = (N[None, :] - 1 - e).astype(np.int32)
+    th = rng.uniform(0, 2 * np.pi, (B, 3))
+    res = m.solve_g_batch(idx, th)
+    assert m.ctx.static_fallbacks() <= 0.02 * B          # a numerically singular Jacobian is the exception here
+    flag = root = 0
+    nfev_gap = []
+    for b in range(B):
+        _, sol, nfev, info = orc.static_solve_g(s, idx[b], th[b])
+        flag += (info == 1) == bool(res["converged"][b])
+        if info == 1 and res["converged"][b]:
+            root += np.max(np.abs(sol - res["solution"][b])) <= 1e-5 * max(1.0, np.max(np.abs(sol)))
+            nfev_gap.append(abs(int(res["nfev"][b]) - nfev))
+    assert flag >= 0.98 * B, flag
+    assert root >= 0.97 * res["converged"].sum(), (root, res["converged"].sum())
+    assert np.median(nfev_gap) <= 1, np.median(nfev_gap)  # same path: same number of residual evaluations
+    # one-step sections: the fast kernel hands them over, the QR kernel answers
+    e[::3, rng.integers(0, 2)] = 1
+    idx = (N[None, :] - 1 - e).astype(np.int32)
+    res = m.solve_g_batch(idx, th)
+    assert m.ctx.static_fallbacks() >= B // 3
+    assert np.all(res["info"] >= 1) and np.all(res["nfev"] >= 31) and np.all(np.isfinite(res["solution"]))
+    agree = sum((orc.static_solve_g(s, idx[b], th[b])[3] == 1) == bool(res["converged"][b]) for b in range(0, B, 3))
+    assert agree >= 0.9 * (B // 3), agree
+
+
 def test_static_fused_eval():
     """BASELINE configs[0]: 2-tube static model, 1024 random configs vs in_simple.STL (C1, all collide at the
     base) and vs the translated box (C1b, distances exercised): static solve -> collision -> cost."""
