@@ -1,46 +1,40 @@
-"""create_model: mirror of ctrdapp/model/model_factory.py:12-78."""
+"""create_model(configuration, q): same contract as ctrdapp/model/model_factory.py:12-78 -- a flat q (or one array
+per tube), scalar-or-list `q_dof` / `tube_lengths`, ValueError for a q of the wrong size, UserWarning for an unknown
+model type -- returning a model backed by a libctrb200 handle."""
 import numpy as np
 
 from .kinematic import Kinematic
 from .model import Model
 
 
+def _per_tube(value, tube_num, what):
+    """A scalar configuration entry applies to every tube (model_factory.py:33-38, 58-63)."""
+    if isinstance(value, int):
+        print(f'{what}: {value}.')
+        return [value] * tube_num
+    return value
+
+
+def _split_q(q, q_dof, tube_num):
+    if len(q) == sum(q_dof) and not isinstance(q[0], list):      # one flat list over all tubes
+        bounds = np.concatenate([[0], np.cumsum(q_dof)])
+        return [np.asarray(q[bounds[n]:bounds[n + 1]]) for n in range(tube_num)]
+    if len(q) == tube_num:                                       # already one entry per tube
+        return [np.asarray(tube_q) for tube_q in q]
+    raise ValueError(f"Given q of {q} is not the correct size.")
+
+
 def create_model(configuration, q, ctx=None) -> Model:
-    name = configuration.get("model_type")
+    kind = configuration.get("model_type")
     tube_num = configuration.get('tube_number')
-    names = configuration.get('strain_bases')
-
-    config_dof = configuration.get('q_dof')
-    if isinstance(config_dof, int):
-        output_q_dof = [config_dof] * tube_num
-        print(f'Each base has same degrees of freedom: {config_dof}.')
-    else:
-        output_q_dof = config_dof
-
-    if len(q) == sum(output_q_dof) and not isinstance(q[0], list):  # single flat list
-        q_list, dof_sum = [], 0
-        for n in range(tube_num):
-            q_list.append(np.asarray(q[dof_sum:dof_sum + output_q_dof[n]]))
-            dof_sum += output_q_dof[n]
-        output_q = q_list
-    elif len(q) == tube_num:
-        output_q = [np.asarray(this_q) for this_q in q]
-    else:
-        raise ValueError(f"Given q of {q} is not the correct size.")
-
-    config_lengths = configuration.get('tube_lengths')
-    if isinstance(config_lengths, int):
-        lengths = [config_lengths] * tube_num
-        print(f'Each tube length is the same: {config_lengths}.')
-    else:
-        lengths = config_lengths
-    delta_x = configuration.get('delta_x')
-
-    if name == "kinematic":
-        return Kinematic(tube_num, output_q, output_q_dof, lengths, delta_x, names, ctx=ctx)
-    elif name == "static":
-        from .static import Static  # built in a later milestone
-        return Static(tube_num, output_q, output_q_dof, lengths, delta_x, names, configuration.get('tube_radius'),
-                      configuration.get('degree'), configuration.get('basis_type'), ctx=ctx)
-    else:
-        raise UserWarning(f"{name} is not a defined model. Change config file.")
+    q_dof = _per_tube(configuration.get('q_dof'), tube_num, 'Each base has same degrees of freedom')
+    lengths = _per_tube(configuration.get('tube_lengths'), tube_num, 'Each tube length is the same')
+    args = (tube_num, _split_q(q, q_dof, tube_num), q_dof, lengths, configuration.get('delta_x'),
+            configuration.get('strain_bases'))
+    if kind == "kinematic":
+        return Kinematic(*args, ctx=ctx)
+    if kind == "static":
+        from .static import Static
+        return Static(*args, configuration.get('tube_radius'), configuration.get('degree'),
+                      configuration.get('basis_type'), ctx=ctx)
+    raise UserWarning(f"{kind} is not a defined model. Change config file.")
