@@ -231,23 +231,30 @@ __device__ __noinline__ void r1updt_w(int n, double* s, double u_l, const double
     }
     if (act) wl = fma(vn_final, u_l, wl);
     __syncwarp();
+    // Second sweep (upper Hessenberg -> triangular): rotation j needs R[j][j] and w_j, both held by lane j.  Every lane
+    // forms "its" rotation (no divergence), lane j's is broadcast by shuffle, and the row-(j+1) element is fetched
+    // before the rotation is applied so that the shared-memory latency overlaps the dependent arithmetic.
+    {
+        int ro = 0;  // rowoff(n, 0)
+        double sl = act ? s[lane] : 0.0;
 #pragma unroll 1
-    for (int j = 0; j < n - 1; ++j) {
-        const int ro = rowoff(n, j);
-        if (lane == j) {
+        for (int j = 0; j < n - 1; ++j) {
             double c_, s_;
-            rot_of(s[ro], wl, &c_, &s_);
-            c2[j] = c_;
-            s2[j] = s_;
-        }
-        __syncwarp();
-        const double s_ = s2[j];
-        if (s_ != 0.0 && lane >= j && act) {
-            const double c_ = c2[j];
-            const int l = ro + lane - j;
-            const double sl = s[l];
-            s[l] = c_ * sl + s_ * wl;
-            wl = -s_ * sl + c_ * wl;
+            rot_of(sl, wl, &c_, &s_);
+            c_ = __shfl_sync(0xffffffffu, c_, j);
+            s_ = __shfl_sync(0xffffffffu, s_, j);
+            const int ro_next = ro + (n - j);
+            const double sl_next = (lane > j && act) ? s[ro_next + lane - (j + 1)] : 0.0;
+            if (lane == j) {
+                c2[j] = c_;
+                s2[j] = s_;
+            }
+            if (s_ != 0.0 && lane >= j && act) {
+                s[ro + lane - j] = c_ * sl + s_ * wl;
+                wl = -s_ * sl + c_ * wl;
+            }
+            sl = sl_next;
+            ro = ro_next;
         }
     }
     if (lane == n - 1) s[rowoff(n, n - 1)] = wl;
