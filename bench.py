@@ -397,6 +397,27 @@ def main():
             if k2 == "static":
                 extra[name]["converged_fraction"] = float((outs[4] == 1).double().mean().item())
                 extra[name]["residual_evaluations_per_config"] = float(outs[5].double().mean().item())
+        # BASELINE configs[0] (C1): configuration/config.yaml as a STATIC model, 1024 random configurations against the
+        # translated box of SURVEY 8d's C1b variant (against in_simple.STL itself every configuration collides at the base)
+        q1 = [np.array([0.02, 0.001]), np.array([0.05, 0.0001, 0.002])]
+        ms1 = Static(2, q1, [2, 3], [120, 120], 1, ["linear", "linear"], {"outer": [0.9, 0.6], "inner": [0.7, 0.4]}, 2, ctx=ctx)
+        cc1 = CollisionChecker(ROOT / "tests" / "fixtures" / "env_c1b_in_simple.json", ctx=ctx)
+        rng1 = np.random.default_rng(1001)
+        i1 = torch.from_numpy(rng1.integers(0, 120, (1024, 2)).astype(np.int32)).to(dev)
+        t1 = torch.from_numpy(rng1.uniform(0, 2 * np.pi, (1024, 2))).to(dev)
+        o1 = tuple(torch.empty(1024, dtype=t.dtype, device=dev) for t in dev_outs)
+        rad1 = np.ascontiguousarray([0.9, 0.6])
+        for rep in range(3):
+            ctx.mark(0)
+            L.check(lib.ctrb_static_eval_batch(ctx.handle, ms1.handle, cc1.handle, C.byref(cd), 1024, L.ptr(i1), L.ptr(t1),
+                                               L.ptr(rad1), L.ptr(o1[0]), L.ptr(o1[1]), L.ptr(o1[2]), L.ptr(o1[3]),
+                                               L.ptr(o1[4]), L.ptr(o1[5]), L.MEM_DEVICE))
+            ctx.mark(1)
+            ms_c1 = ctx.elapsed_ms()
+        extra["c1_static_two_tube_1024"] = {"configs_per_s": 1024 / (ms_c1 * 1e-3), "ms": ms_c1, "configs": 1024,
+                                            "collide_fraction": float((o1[0] < 0).double().mean().item()),
+                                            "converged_fraction": float((o1[4] == 1).double().mean().item()),
+                                            "note": "one launch sequence over 1024 configurations: latency, not throughput"}
         m2 = Kinematic(2, [np.array([0.02, 0.001]), np.array([0.05, 0.0001, 0.002])], [2, 3], [120, 120], 1,
                        ["linear", "linear"], ctx=ctx)
         rng = np.random.default_rng(1002)

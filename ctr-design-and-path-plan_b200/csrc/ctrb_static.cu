@@ -284,8 +284,11 @@ __device__ __noinline__ void st_r1mpyq_row(int n, double* a, int lda, const doub
 // computed redundantly and identically by all lanes; vectors are one element per lane.
 // returns info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress)
 __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
-                                     double factor, int* nfev_out) {
-    const int n = sm.nq;
+                                     double factor, bool reduced, int* nfev_out) {
+    // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2)
+    const int n = reduced ? sm.nq - sm.ndof[5] : sm.nq;
+    const int nnodes = reduced ? 8 : 12;
+    const double c33 = reduced ? block5_norm2(sm, M.cfg, M.x, M.ybuf32(), lane) : 0.0;
     const bool act = lane < n;
     const double epsmch = DBL_EPSILON, p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double* fjac = M.fjac;
@@ -293,7 +296,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotT
     const RowMeta rm = row_meta(sm, act ? lane : 0);
     double pa, pb;  // section shares of this lane's residual component at the accepted x (for the sparse fdjac)
     {
-        const double f0 = warp_residual(sm, M.cfg, M.ybuf0, M.x, rm, act, lane, &pa, &pb);
+        const double f0 = warp_residual(sm, M.cfg, M.ybuf0, M.x, rm, act, lane, nnodes, &pa, &pb);
         if (act) M.fvec[lane] = f0;
         __syncwarp();
     }
@@ -306,8 +309,8 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotT
     for (;;) {  // outer loop: fresh forward-difference Jacobian
         bool jeval = true;
         // fdjac1 (dense band) through the block structure of the residual: 4 (8) node evaluations per column
-        warp_fdjac(sm, M.cfg, st, rm, M.x, fjac, M.ybuf32(), act ? M.fvec[lane] : 0.0, pa, pb, lane);
-        nfev += n;
+        warp_fdjac(sm, M.cfg, st, rm, M.x, fjac, M.ybuf32(), act ? M.fvec[lane] : 0.0, pa, pb, n, lane);
+        nfev += sm.nq;  // MINPACK's count: one evaluation per unknown
         __syncwarp();
         // qrfac: Householder QR without pivoting; lane k owns column k.  acnorm -> wa2, rdiag -> wa1
         double acnorm_l = 0.0;
@@ -341,7 +344,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotT
         }
         if (iter == 1) {
             diag_l = acnorm_l == 0 ? 1.0 : acnorm_l;
-            xnorm = enorm_w(n, act ? diag_l * M.x[lane] : 0.0, nullptr);
+            xnorm = sqrt(warp_sum(act ? (diag_l * M.x[lane]) * (diag_l * M.x[lane]) : 0.0) + c33);
             delta = factor * xnorm;
             if (delta == 0) delta = factor;
         }
@@ -403,7 +406,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotT
             __syncwarp();
             double qa, qb;
             {
-                const double f1 = warp_residual(sm, M.cfg, M.ybuf0, M.wa2, rm, act, lane, &qa, &qb);
+                const double f1 = warp_residual(sm, M.cfg, M.ybuf0, M.wa2, rm, act, lane, nnodes, &qa, &qb);
                 if (act) M.wa4[lane] = f1;
                 __syncwarp();
             }
@@ -442,7 +445,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotT
                 }
                 pa = qa;
                 pb = qb;
-                xnorm = enorm_w(n, act ? diag_l * M.wa2[lane] : 0.0, nullptr);
+                xnorm = sqrt(warp_sum(act ? (diag_l * M.wa2[lane]) * (diag_l * M.wa2[lane]) : 0.0) + c33);
                 fnorm = fnorm1;
                 iter++;
             }
@@ -492,7 +495,8 @@ __global__ void __launch_bounds__(kSWarps * 32, 5)
                         const long long* __restrict__ list, const unsigned long long* __restrict__ list_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SlotTable st;
-    if (threadIdx.x == 0) build_slot_table(sm, st);
+    const bool reduced = x0 == nullptr;  // default initial guess: q_33 = q*
+    if (threadIdx.x == 0) build_slot_table(sm, st, reduced);
     __syncthreads();
     // with a list the kernel solves configurations list[0 .. *list_count): the ones the fast kernel handed back
     const long long work = list ? (long long)*list_count : B;
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kSWarps * 32, 5)
         if (lane < n) M.x[lane] = x0 ? x0[(x0_per_config ? b * n : 0) + lane] : sm.x0[lane];
         __syncwarp();
         int nfev = 0;
-        const int info = st_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, &nfev);
+        const int info = st_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, &nfev);
         __syncwarp();
         if (sol_out && lane < n) sol_out[b * n + lane] = M.x[lane];
         if (lane == 0) {

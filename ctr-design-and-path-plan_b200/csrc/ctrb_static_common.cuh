@@ -398,9 +398,10 @@ __device__ __forceinline__ double asm_part(const StCfg& c, const double (*yb)[16
 // F(q) by the whole warp: 12 node integrands (3 sections x 2 abscissae x 2 bracketing nodes), then one residual
 // component per lane.  Returns this lane's component; p1 / p2 are its section shares (row block (3,1) is
 // intg_31 - intg_312, static.py:250-252; p2 = 0 elsewhere).
+// `nnodes` = 12, or 8 when the last block is carried implicitly (see block5_norm2): its nodes are not needed then.
 __device__ __forceinline__ double warp_residual(const StModel& sm, const StCfg& cfg, double (*y)[16], const double* q,
-                                                const RowMeta& rm, bool act, int lane, double* p1, double* p2) {
-    if (lane < 12) res_node(sm, cfg, QV{q, -1, 0.0}, lane, y[lane]);
+                                                const RowMeta& rm, bool act, int lane, int nnodes, double* p1, double* p2) {
+    if (lane < nnodes) res_node(sm, cfg, QV{q, -1, 0.0}, lane, y[lane]);
     __syncwarp();
     double a = 0.0, b = 0.0;
     if (act) {
@@ -419,8 +420,8 @@ struct SlotTable {
     int nslots;
 };
 
-// thread 0 of the block fills the table (it only depends on the design)
-__device__ __forceinline__ void build_slot_table(const StModel& sm, SlotTable& st) {
+// thread 0 of the block fills the table (it only depends on the design); `reduced` leaves the last block out
+__device__ __forceinline__ void build_slot_table(const StModel& sm, SlotTable& st, bool reduced) {
     int ns = 0;
     for (int b = 0; b < 6; ++b)
         for (int k = 0; k < sm.ndof[b]; ++k) st.col_blk[sm.qoff[b] + k] = (signed char)b;
@@ -430,7 +431,7 @@ __device__ __forceinline__ void build_slot_table(const StModel& sm, SlotTable& s
             st.j[ns] = (signed char)(sm.qoff[2] + k);
             st.sec[ns++] = (signed char)s;
         }
-    for (int b = 0; b < 6; ++b) {
+    for (int b = 0; b < (reduced ? 5 : 6); ++b) {
         if (b == 2) continue;
         for (int k = 0; k < sm.ndof[b]; ++k) {
             st.j[ns] = (signed char)(sm.qoff[b] + k);
@@ -440,13 +441,46 @@ __device__ __forceinline__ void build_slot_table(const StModel& sm, SlotTable& s
     st.nslots = ns;
 }
 
+// The last block (3,3) of the system is linear and decoupled: F_33 = int B^T K B (q_33 - q*) depends on q_33 only and
+// nothing else depends on q_33 (static.py:438-452).  From the default initial guess q_33 = q* (static_bases.py:164-166)
+// F_33 is exactly zero, the Jacobian is exactly block diagonal, and hybrd never moves q_33: its Gauss-Newton and
+// gradient components vanish, Broyden's update vectors have zeros there, the QR factors stay block diagonal.  The
+// ONLY place the block enters the iteration is the scaled norm |D x| (trust-region start, the xtol test), through the
+// constant  sum_j (D_j q*_j)^2  with D_j = the forward-difference column norms of the block.  So the solvers iterate on
+// the first n - dof_33 unknowns and add this constant to |D x|^2: the same iterates with 27 instead of 30 unknowns.
+// Returns that constant (all lanes); yb is scratch for 32 node vectors.
+__device__ __noinline__ double block5_norm2(const StModel& sm, const StCfg& cfg, const double* x, double (*yb)[16], int lane) {
+    const int dof = sm.ndof[5], q0 = sm.qoff[5];
+    const double eps = sqrt(DBL_EPSILON);
+    const int slot = lane >> 2;
+    if (slot < dof) {
+        const double xv = x[q0 + slot];
+        double h = eps * fabs(xv);
+        if (h == 0.0) h = eps;
+        res_node(sm, cfg, QV{x, q0 + slot, h}, 8 + (lane & 3), yb[lane]);
+    }
+    __syncwarp();
+    double c2 = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < dof; ++k) {
+        const double xv = x[q0 + k];
+        double h = eps * fabs(xv);
+        if (h == 0.0) h = eps;
+        const double col = lane < dof ? asm_part(cfg, yb, k * 4, 2, lane) / h : 0.0;  // (F_33(x + h e_k) - 0) / h, row `lane`
+        double d = sqrt(warp_sum(col * col));
+        if (d == 0.0) d = 1.0;
+        c2 = fma(d * xv, d * xv, c2);
+    }
+    __syncwarp();
+    return c2;
+}
+
 // forward-difference Jacobian (MINPACK fdjac1, dense band) using the block structure; f_l / p1b / p2b are this
 // lane's residual component at x and its section shares.  Writes J (column-major, leading dimension kJLD); yb is
 // scratch for 32 node vectors; returns this lane's column norm.
 __device__ __noinline__ double warp_fdjac(const StModel& sm, const StCfg& cfg, const SlotTable& st, const RowMeta& rm,
                                           const double* x, double* J, double (*yb)[16], double f_l, double p1b, double p2b,
-                                          int lane) {
-    const int n = sm.nq;
+                                          int n, int lane) {
     const bool act = lane < n;
     const double eps = sqrt(DBL_EPSILON);
     for (int base = 0; base < st.nslots; base += 8) {

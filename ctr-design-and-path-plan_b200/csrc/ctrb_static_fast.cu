@@ -131,14 +131,17 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n, double acnorm_l, int
 // returns MINPACK's info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress), or -1 when the
 // configuration has to go through the QR kernel
 __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
-                                       double factor, int* nfev_out) {
-    const int n = sm.nq;
+                                       double factor, bool reduced, int* nfev_out) {
+    // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2)
+    const int n = reduced ? sm.nq - sm.ndof[5] : sm.nq;
+    const int nnodes = reduced ? 8 : 12;
+    const double c33 = reduced ? block5_norm2(sm, M.cfg, M.x, M.ybuf(), lane) : 0.0;
     const bool act = lane < n;
     const RowMeta rm = row_meta(sm, act ? lane : 0);
     const double epsmch = DBL_EPSILON, p1c = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double x_l = act ? M.x[lane] : 0.0;
     double pa, pb;
-    double f_l = warp_residual(sm, M.cfg, M.y, M.x, rm, act, lane, &pa, &pb);
+    double f_l = warp_residual(sm, M.cfg, M.y, M.x, rm, act, lane, nnodes, &pa, &pb);
     int nfev = 1, info = 0;
     double fnorm = wnorm(f_l);
     if (!(fnorm < 1.7e308)) return -1;
@@ -147,12 +150,12 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
 #pragma unroll 1
     for (;;) {
         bool jeval = true;
-        const double acnorm_l = warp_fdjac(sm, M.cfg, st, rm, M.x, M.J, M.ybuf(), f_l, pa, pb, lane);
-        nfev += n;
+        const double acnorm_l = warp_fdjac(sm, M.cfg, st, rm, M.x, M.J, M.ybuf(), f_l, pa, pb, n, lane);
+        nfev += sm.nq;  // MINPACK's count: one evaluation per unknown
         if (!fast_invert(M, n, acnorm_l, lane)) return -1;
         if (iter == 1) {
             diag_l = acnorm_l == 0.0 ? 1.0 : acnorm_l;
-            xnorm = wnorm(act ? diag_l * x_l : 0.0);
+            xnorm = sqrt(warp_sum(act ? (diag_l * x_l) * (diag_l * x_l) : 0.0) + c33);
             delta = factor * xnorm;
             if (delta == 0.0) delta = factor;
         }
@@ -200,7 +203,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
             }
             __syncwarp();
             double qa, qb;
-            const double fn_l = warp_residual(sm, M.cfg, M.y, M.vb, rm, act, lane, &qa, &qb);
+            const double fn_l = warp_residual(sm, M.cfg, M.y, M.vb, rm, act, lane, nnodes, &qa, &qb);
             nfev++;
             const double fnorm1 = wnorm(fn_l);
             if (!(fnorm1 < 1.7e308) || !(pnorm < 1.7e308)) return -1;  // non-finite: let the QR kernel decide
@@ -235,7 +238,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
                     M.x[lane] = x_l;
                     M.f[lane] = f_l;
                 }
-                xnorm = wnorm(act ? diag_l * x_l : 0.0);
+                xnorm = sqrt(warp_sum(act ? (diag_l * x_l) * (diag_l * x_l) : 0.0) + c33);
                 fnorm = fnorm1;
                 iter++;
             }
@@ -296,7 +299,8 @@ __global__ void __launch_bounds__(kFWarps * 32, 3)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FastMem& M = reinterpret_cast<FastMem*>(smem_raw)[warp];
     const int T = sm.mc.T, n = sm.nq;
-    if (threadIdx.x == 0) build_slot_table(sm, st);
+    const bool reduced = x0 == nullptr;  // default initial guess: q_33 = q*
+    if (threadIdx.x == 0) build_slot_table(sm, st, reduced);
     __syncthreads();
     for (;;) {
         unsigned long long tk = 0;
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(kFWarps * 32, 3)
         // and a one-step section 1 or 2 gives the x and x^2 curvature coefficients identical columns
         const bool degenerate = (T == 3 && c.L[0] < 3) || c.L[1] < 3 || c.L[2] < 2;
         int nfev = 0;
-        const int info = degenerate ? -1 : fast_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, &nfev);
+        const int info = degenerate ? -1 : fast_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, &nfev);
         __syncwarp();
         if (info < 0) {
             if (lane == 0) fb_list[atomicAdd(fb_count, 1ULL)] = b;
