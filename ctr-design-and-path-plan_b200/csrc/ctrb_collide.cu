@@ -43,6 +43,10 @@ constexpr int kTopNodes = CTRB_TOP_NODES;     // BVH nodes staged in shared memo
 constexpr int kStack = 48;
 
 constexpr int kQueue = 96;  // deferred exact tests per warp (drained 32 at a time, all lanes in lock-step)
+#ifndef CTRB_STEPS_PER_ROUND
+#define CTRB_STEPS_PER_ROUND 8
+#endif
+constexpr int kStepsPerRound = CTRB_STEPS_PER_ROUND;  // BVH node steps a lane takes between two warp-wide votes
 struct WarpCtl {
     int bound_bits;   // float bits of an upper bound on the config's min distance (>= 0 => int-ordered)
     int collided;
@@ -427,7 +431,8 @@ __global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_
                     }
                 }
                 if (!__any_sync(0xffffffffu, sp > 0 || (!exhausted && !*vcoll))) break;
-                if (sp > 0) {
+#pragma unroll 1
+                for (int rep = 0; rep < kStepsPerRound && sp > 0; ++rep) {  // a few node steps between two warp votes
                     if (*vcoll) {
                         sp = 0;
                     } else {
