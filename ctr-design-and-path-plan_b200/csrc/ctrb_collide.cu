@@ -254,7 +254,7 @@ __device__ __noinline__ double cylinder_vs_prim(const DevPrim& o, d3 c, d3 a, do
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_kernel(EvalParams P) {
+__global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_kernel(const __grid_constant__ EvalParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BvhNode* s_top = reinterpret_cast<BvhNode*>(smem_raw);
     double* s_pos_all = reinterpret_cast<double*>(smem_raw + (size_t)kTopNodes * sizeof(BvhNode));
