@@ -77,6 +77,7 @@ struct EvalParams {
     ctrb_cost_desc cd;
     unsigned long long* counters;  // [0..3] work counters, [4] config ticket
     int max_nodes;                 // shared-memory rows per warp
+    int bvh_depth;                 // of the obstacle mesh's BVH (host-side knowledge: picks the traversal kernel)
 };
 
 __device__ __forceinline__ BvhNode load_node(const DevBvh& bvh, const BvhNode* s_top, int ntop, int ni) {
@@ -95,77 +96,6 @@ __device__ __forceinline__ BvhNode load_node(const DevBvh& bvh, const BvhNode* s
 struct Work {
     unsigned int nodes, pre, exact;
 };
-
-// exact min distance of one solid cylinder against the mesh, sharing bounds through `ctl`
-__device__ __noinline__ void cylinder_vs_mesh(const DevBvh& bvh, const BvhNode* s_top, int ntop, d3 c, d3 a, double h, double r,
-                                 WarpCtl* ctl, double& best_exact, Work& wk) {
-    const f3 cf = {(float)c.x, (float)c.y, (float)c.z};
-    const float slack = bvh.slack;
-    const float rb = __fsqrt_ru(__fmaf_ru((float)h, (float)h, (float)r * (float)r)) * 1.000001f;
-    const float rin = fminf((float)h, (float)r);
-    int stack[kStack];
-    int sp = 0;
-    stack[sp++] = 0;
-    volatile int* vbound = &ctl->bound_bits;
-    volatile int* vcoll = &ctl->collided;
-    while (sp > 0) {
-        if (*vcoll) return;
-        const int ni = stack[--sp];
-        const BvhNode nd = load_node(bvh, s_top, ntop, ni);
-        wk.nodes++;
-        float bound = __int_as_float(*vbound);
-        float reach = bound + rb + slack;
-        float reach2 = reach * reach * 1.000001f;
-        float d0 = aabb_dist2(nd.lo0, nd.hi0, cf);
-        float d1 = aabb_dist2(nd.lo1, nd.hi1, cf);
-        int l0 = nd.c0, l1 = nd.c1;
-        if (d1 < d0) {  // near child first
-            float t = d0; d0 = d1; d1 = t;
-            int ti = l0; l0 = l1; l1 = ti;
-        }
-        // inner children: push far first so that near is popped first
-        if (l1 >= 0 && d1 <= reach2 && sp < kStack) stack[sp++] = l1;
-        if (l0 >= 0 && d0 <= reach2 && sp < kStack) stack[sp++] = l0;
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-            const int link = side == 0 ? l0 : l1;
-            const float dd = side == 0 ? d0 : d1;
-            if (link >= 0 || dd > reach2) continue;
-            const int code = ~link;
-            const int first = code >> 3, cnt = (code & 7) + 1;
-#pragma unroll 1
-            for (int t = first; t < first + cnt; ++t) {
-                const float4* tp = bvh.tri32 + (size_t)t * 3;
-                float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-                float dpt = sqrtf(point_tri_dist2<f3, float>(cf, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z},
-                                                              f3{v2.x, v2.y, v2.z}));
-                wk.pre++;
-                if (dpt + slack < rin) {  // a ball of radius min(h, r) about the centre lies inside the solid cylinder
-                    *vcoll = 1;
-                    return;
-                }
-                // the centre belongs to the cylinder: d(cyl, tri) <= dpt
-                atomicMin(&ctl->bound_bits, __float_as_int(dpt + slack));
-                bound = __int_as_float(*vbound);
-                if (dpt - rb - slack > bound) continue;  // d(cyl, tri) >= dpt - rb
-                const double* tq = bvh.tri64 + (size_t)t * 9;
-                d3 t0 = {__ldg(tq + 0), __ldg(tq + 1), __ldg(tq + 2)};
-                d3 t1 = {__ldg(tq + 3), __ldg(tq + 4), __ldg(tq + 5)};
-                d3 t2 = {__ldg(tq + 6), __ldg(tq + 7), __ldg(tq + 8)};
-                double d = cyl_tri_dist(c, a, h, r, t0, t1, t2, (double)bound);
-                wk.exact++;
-                if (d <= 0.0) {
-                    *vcoll = 1;
-                    return;
-                }
-                if (d < best_exact) {
-                    best_exact = d;
-                    atomicMin(&ctl->bound_bits, __float_as_int(__double2float_ru(d)));
-                }
-            }
-        }
-    }
-}
 
 // exact nearest distance from a point to a mesh (goal mesh): fp32 culling, fp64 leaves
 __device__ __noinline__ double point_vs_mesh(const DevBvh& bvh, d3 x, Work& wk) {
@@ -555,44 +485,116 @@ __global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_
     }
 }
 
-// ------------------------------------------------------------------ packed variant
+// ------------------------------------------------------------------ grouped variant
 // chain_eval_kernel above gives a whole warp to one configuration, which leaves most lanes idle when a
-// configuration has few cylinders (ncu, C3 "shallow": 3.6 of 32 lanes active per instruction).  The packed
-// kernel lets a warp take 32 configurations at a time: lane = configuration for the SE(3) chain, the node
-// positions and the epilogue (no redundant prologue, coalesced result stores), and lane = work item for the
-// BVH walks: the cylinders of as many of those configurations as fit the warp's node pool are flattened into
-// one item list that the lanes drain through a shared-memory ticket.  Bounds / contact flags are per
-// configuration slot.
-constexpr int kPWarps = 8;
-constexpr int kPool = 384;  // node positions (fp64 xyz) per warp
+// configuration has few cylinders (ncu, C3 "shallow": 8 of 32 lanes active in the walk, 1.8 in the leaf tests).
+// chain_eval_group_kernel lets a warp take as many configurations as fit its node pool (up to 32):
+//   lane = configuration for the SE(3) chain, the node positions and the epilogue (coalesced result stores);
+//   lane = work item for the BVH walks: the cylinders of the whole group are one item list behind a shared-memory
+//   ticket; bounds, contact flags and minima are per configuration slot.
+// The walk is "while-while": a lane pops inner nodes until a LEAF link surfaces (leaf links are pushed like inner
+// nodes), then all lanes that hold
+// a leaf run the fp32 point-triangle prefilter together; surviving (cylinder, triangle) pairs go to the warp's queue
+// and are decided by the exact fp64 test 32 at a time.
+constexpr int kGWarps = 8;
+constexpr int kPool = 256;     // node positions (fp64 xyz) per warp
+constexpr int kGQueue = 128;   // deferred exact tests per warp
+constexpr int kGStack = 24;    // traversal stack entries per lane, in SHARED memory (a BVH deeper than kGStack - 2 takes
+                               // chain_eval_kernel): with 32 busy lanes per warp a local-memory stack thrashed the ~40 KB
+                               // of L1 that the shared-memory carve-out leaves (ncu: L1 hit rate 50 %, long-scoreboard 8.4)
+#ifndef CTRB_GROUP_MIN
+#define CTRB_GROUP_MIN 8
+#endif
+// No BVH levels are staged in shared memory here: the staged-or-global branch in load_node diverges between lanes that
+// are at different depths, and the staging takes L1 capacity away from the nodes below (measured: 45.6 -> 63 M configs/s
+// when the 128-node staging was removed).
+constexpr int kGroupMin = CTRB_GROUP_MIN;   // fewer configurations than this in a group: one pass per configuration
+#ifndef CTRB_GROUP_INNER
+#define CTRB_GROUP_INNER 2
+#endif
+#ifndef CTRB_GROUP_REPS
+#define CTRB_GROUP_REPS 8
+#endif
 
-struct PackedWarpMem {
+struct GroupMem {
     double pos[kPool * 3];
     unsigned int items[kPool];       // node (10 bits) | slot (5 bits) << 10 | tube (2 bits) << 15
-    WarpCtl ctl[32];                 // per configuration slot: bound bits, contact flag
     unsigned long long best_bits[32];
+    int bound_bits[32];
+    int collided[32];
+    int q_tri[kGQueue];
+    unsigned int q_item[kGQueue];
+    float q_lb[kGQueue];
+    int stack[kGStack][32];          // [entry][lane]: conflict-free
     int ticket;
-    int pad[3];
+    int qcount;
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kPWarps * 32, 2) chain_eval_packed_kernel(EvalParams P) {
+__global__ void __launch_bounds__(kGWarps * 32, 2) chain_eval_group_kernel(const __grid_constant__ EvalParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BvhNode* s_top = reinterpret_cast<BvhNode*>(smem_raw);
-    PackedWarpMem* s_all = reinterpret_cast<PackedWarpMem*>(smem_raw + (size_t)kTopNodes * sizeof(BvhNode));
-
+    GroupMem* s_all = reinterpret_cast<GroupMem*>(smem_raw);
     const EnvConst& env = *P.env;
-    const int ntop = min(env.obs.nnodes, kTopNodes);
-    for (int i = threadIdx.x; i < ntop * 4; i += blockDim.x)
-        reinterpret_cast<float4*>(s_top)[i] = __ldg(reinterpret_cast<const float4*>(env.obs.nodes) + i);
-    __syncthreads();
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    PackedWarpMem& W = s_all[warp];
+    GroupMem& W = s_all[warp];
+    int* const stk = &W.stack[0][lane];  // entry k of this lane's stack = stk[k * 32]
     const int T = FUSED ? P.mc.T : P.tube_num;
     const bool have_obstacles = env.obs.ntri > 0 || env.nprim > 0;
+    const DevBvh& bvh = env.obs;
+    const float slack = bvh.slack;
+    volatile int* vbound = W.bound_bits;
+    volatile int* vcoll = W.collided;
     Work wk = {0, 0, 0};
     unsigned int nconf = 0;
+
+    // the solid cylinder of an item: nodes `node`, `node + 1` of the pool (collision_checker.py:121-147)
+    auto cylinder_of = [&](unsigned code, d3& c, d3& a, double& h, double& r) {
+        const double* pf = W.pos + (size_t)(code & 1023u) * 3;
+        d3 f = {pf[0], pf[1], pf[2]}, t = {pf[3], pf[4], pf[5]};
+        d3 vec = t - f;
+        const double len = sqrt(dot(vec, vec));
+        c = f + 0.5 * vec;
+        a = (1.0 / len) * vec;
+        h = 0.5 * len;
+        r = P.rad[(code >> 15) & 3u];
+    };
+    auto record = [&](int slot, double d) {
+        if (d <= 0.0) {
+            vcoll[slot] = 1;
+        } else {
+            atomicMin(&W.best_bits[slot], (unsigned long long)__double_as_longlong(d));
+            atomicMin(&W.bound_bits[slot], __float_as_int(__double2float_ru(d)));
+        }
+    };
+    auto exact_pair = [&](unsigned code, int t, float bound) {
+        d3 c, a;
+        double h, r;
+        cylinder_of(code, c, a, h, r);
+        const double* tq = bvh.tri64 + (size_t)t * 9;
+        d3 t0 = {__ldg(tq + 0), __ldg(tq + 1), __ldg(tq + 2)};
+        d3 t1 = {__ldg(tq + 3), __ldg(tq + 4), __ldg(tq + 5)};
+        d3 t2 = {__ldg(tq + 6), __ldg(tq + 7), __ldg(tq + 8)};
+        const double d = cyl_tri_dist(c, a, h, r, t0, t1, t2, (double)bound);
+        wk.exact++;
+        record((code >> 10) & 31u, d);
+    };
+    // every decision that guards a __syncwarp is taken on lane 0's view (see chain_eval_kernel)
+    auto drain = [&]() {
+        __syncwarp();
+        const int qc = min(__shfl_sync(0xffffffffu, *(volatile int*)&W.qcount, 0), kGQueue);
+        for (int base = 0; base < qc; base += 32) {
+            const int k = base + lane;
+            if (k < qc) {
+                const unsigned code = W.q_item[k];
+                const int slot = (code >> 10) & 31u;
+                const float bound = __int_as_float(vbound[slot]);
+                if (!vcoll[slot] && W.q_lb[k] <= bound) exact_pair(code, W.q_tri[k], bound);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) W.qcount = 0;
+        __syncwarp();
+    };
 
     for (;;) {
         long long b0;
@@ -637,88 +639,227 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) chain_eval_packed_kernel(Eval
             const bool mine = valid && lane < m;
             const int nstart = nend - tn, istart = iend - ncyl;
             const int total_items = __shfl_sync(0xffffffffu, iend, m - 1);
-            // ---- positions of my configuration into the pool, cylinder items into the list
-            if (mine) {
-                nconf++;
-                double* dst = W.pos + (size_t)nstart * 3;
-                unsigned int* it = W.items + istart;
-                int node = nstart;
-                if (FUSED) {
-                    const int tot = P.mc.total_nodes;
+            // ---- positions into the pool, cylinder items into the list
+            if (mine) nconf++;
+            if (m >= kGroupMin) {
+                // many short configurations: lane = configuration, nodes one after the other
+                if (mine) {
+                    double* dst = W.pos + (size_t)nstart * 3;
+                    unsigned int* it = W.items + istart;
+                    int node = nstart;
+                    if (FUSED) {
+                        const int tot = P.mc.total_nodes;
+                        SE3 g;
+                        se3_identity(g);
+                        for (int n = 0; n < T; ++n) {
+                            const int id = P.idx[b * T + n];
+                            se3_rot_x(g, P.theta[b * T + n]);
+                            const SE3 a = se3_mul(g, load_tab(P.tb.tab_inv, tot, P.mc.node_base[n] + id));
+                            const int colbase = P.mc.node_base[n] + id;
+#pragma unroll 1
+                            for (int k = 0; k < cnt[n]; ++k) {
+                                const int col = colbase + k;
+                                const double cx = __ldg(P.tb.tab + 9 * tot + col), cy = __ldg(P.tb.tab + 10 * tot + col),
+                                             cz = __ldg(P.tb.tab + 11 * tot + col);
+                                dst[0] = fma(a.r[0], cx, fma(a.r[1], cy, fma(a.r[2], cz, a.p[0])));
+                                dst[1] = fma(a.r[3], cx, fma(a.r[4], cy, fma(a.r[5], cz, a.p[1])));
+                                dst[2] = fma(a.r[6], cx, fma(a.r[7], cy, fma(a.r[8], cz, a.p[2])));
+                                dst += 3;
+                                if (k + 1 < cnt[n]) *it++ = (unsigned)(node + k) | ((unsigned)lane << 10) | ((unsigned)n << 15);
+                            }
+                            node += cnt[n];
+                            g = se3_mul(a, load_tab(P.tb.tab, tot, P.mc.node_base[n] + P.mc.npts[n] - 1));
+                        }
+                    } else {
+                        for (int n = 0; n < T; ++n) {
+                            const double* gg = P.g + P.offsets[b * T + n] * 16;
+#pragma unroll 1
+                            for (int k = 0; k < cnt[n]; ++k) {
+                                dst[0] = __ldg(gg + (size_t)k * 16 + 3);
+                                dst[1] = __ldg(gg + (size_t)k * 16 + 7);
+                                dst[2] = __ldg(gg + (size_t)k * 16 + 11);
+                                dst += 3;
+                                if (k + 1 < cnt[n]) *it++ = (unsigned)(node + k) | ((unsigned)lane << 10) | ((unsigned)n << 15);
+                            }
+                            node += cnt[n];
+                        }
+                    }
+                }
+            } else {
+                // a few long configurations: one after the other, lanes stride over the nodes of each tube
+#pragma unroll 1
+                for (int sl = 0; sl < m; ++sl) {
+                    const long long bs = b0 + done + sl;
+                    int node = __shfl_sync(0xffffffffu, nstart, sl);
+                    int item = __shfl_sync(0xffffffffu, istart, sl);
                     SE3 g;
                     se3_identity(g);
                     for (int n = 0; n < T; ++n) {
-                        const int id = P.idx[b * T + n];
-                        se3_rot_x(g, P.theta[b * T + n]);
-                        const SE3 a = se3_mul(g, load_tab(P.tb.tab_inv, tot, P.mc.node_base[n] + id));
-                        const int colbase = P.mc.node_base[n] + id;
-#pragma unroll 1
-                        for (int k = 0; k < cnt[n]; ++k) {
-                            const int col = colbase + k;
-                            const double cx = __ldg(P.tb.tab + 9 * tot + col), cy = __ldg(P.tb.tab + 10 * tot + col),
-                                         cz = __ldg(P.tb.tab + 11 * tot + col);
-                            dst[0] = fma(a.r[0], cx, fma(a.r[1], cy, fma(a.r[2], cz, a.p[0])));
-                            dst[1] = fma(a.r[3], cx, fma(a.r[4], cy, fma(a.r[5], cz, a.p[1])));
-                            dst[2] = fma(a.r[6], cx, fma(a.r[7], cy, fma(a.r[8], cz, a.p[2])));
-                            dst += 3;
-                            if (k + 1 < cnt[n]) *it++ = (unsigned)(node + k) | ((unsigned)lane << 10) | ((unsigned)n << 15);
+                        const int cn = __shfl_sync(0xffffffffu, cnt[n], sl);
+                        if (FUSED) {
+                            const int tot = P.mc.total_nodes;
+                            const int id = P.idx[bs * T + n];
+                            se3_rot_x(g, P.theta[bs * T + n]);
+                            const SE3 a = se3_mul(g, load_tab(P.tb.tab_inv, tot, P.mc.node_base[n] + id));
+                            const int colbase = P.mc.node_base[n] + id;
+                            for (int k = lane; k < cn; k += 32) {
+                                const int col = colbase + k;
+                                const double cx = __ldg(P.tb.tab + 9 * tot + col), cy = __ldg(P.tb.tab + 10 * tot + col),
+                                             cz = __ldg(P.tb.tab + 11 * tot + col);
+                                double* dst = W.pos + (size_t)(node + k) * 3;
+                                dst[0] = fma(a.r[0], cx, fma(a.r[1], cy, fma(a.r[2], cz, a.p[0])));
+                                dst[1] = fma(a.r[3], cx, fma(a.r[4], cy, fma(a.r[5], cz, a.p[1])));
+                                dst[2] = fma(a.r[6], cx, fma(a.r[7], cy, fma(a.r[8], cz, a.p[2])));
+                            }
+                            g = se3_mul(a, load_tab(P.tb.tab, tot, P.mc.node_base[n] + P.mc.npts[n] - 1));
+                        } else {
+                            const double* gg = P.g + P.offsets[bs * T + n] * 16;
+                            for (int k = lane; k < cn; k += 32) {
+                                double* dst = W.pos + (size_t)(node + k) * 3;
+                                dst[0] = __ldg(gg + (size_t)k * 16 + 3);
+                                dst[1] = __ldg(gg + (size_t)k * 16 + 7);
+                                dst[2] = __ldg(gg + (size_t)k * 16 + 11);
+                            }
                         }
-                        node += cnt[n];
-                        g = se3_mul(a, load_tab(P.tb.tab, tot, P.mc.node_base[n] + P.mc.npts[n] - 1));
-                    }
-                } else {
-                    for (int n = 0; n < T; ++n) {
-                        const double* gg = P.g + P.offsets[b * T + n] * 16;
-#pragma unroll 1
-                        for (int k = 0; k < cnt[n]; ++k) {
-                            dst[0] = __ldg(gg + (size_t)k * 16 + 3);
-                            dst[1] = __ldg(gg + (size_t)k * 16 + 7);
-                            dst[2] = __ldg(gg + (size_t)k * 16 + 11);
-                            dst += 3;
-                            if (k + 1 < cnt[n]) *it++ = (unsigned)(node + k) | ((unsigned)lane << 10) | ((unsigned)n << 15);
-                        }
-                        node += cnt[n];
+                        for (int k = lane; k + 1 < cn; k += 32)
+                            W.items[item + k] = (unsigned)(node + k) | ((unsigned)sl << 10) | ((unsigned)n << 15);
+                        node += cn;
+                        item += max(cn - 1, 0);
                     }
                 }
             }
-            W.ctl[lane].bound_bits = __float_as_int(FLT_MAX);
-            W.ctl[lane].collided = 0;
+            W.bound_bits[lane] = __float_as_int(FLT_MAX);
+            W.collided[lane] = 0;
             W.best_bits[lane] = (unsigned long long)__double_as_longlong(DBL_MAX);
-            if (lane == 0) W.ticket = 0;
+            if (lane == 0) {
+                W.ticket = 0;
+                W.qcount = 0;
+            }
             __syncwarp();
-            // ---- lane = work item: drain the cylinder list
-            if (have_obstacles) {
+            // ---- lane = work item
+            // Many short configurations: one pass over the whole item list.  A few long ones: one pass per configuration,
+            // so that a contact ends that configuration's walks at once and the warp moves on together (python-fcl's
+            // callback stops at the first contact; most long configurations collide).
+            const int npass = !have_obstacles ? 0 : (m >= kGroupMin ? 1 : m);
+#pragma unroll 1
+            for (int pass = 0; pass < npass; ++pass) {
+                int range_end = total_items;
+                if (m < kGroupMin) {
+                    range_end = __shfl_sync(0xffffffffu, iend, pass);
+                    const int range_begin = __shfl_sync(0xffffffffu, istart, pass);
+                    if (lane == 0) W.ticket = range_begin;
+                    __syncwarp();
+                }
+                int sp = 0, slot = 0;
+                unsigned code = 0;
+                bool exhausted = false;
+                f3 cf = {0.f, 0.f, 0.f};
+                float rb = 0.f, rin = 0.f;
                 for (;;) {
-                    const int q = atomicAdd(&W.ticket, 1);
-                    if (q >= total_items) break;
-                    const unsigned code = W.items[q];
-                    const int node = code & 1023, slot = (code >> 10) & 31, n = (code >> 15) & 3;
-                    WarpCtl* ctl = &W.ctl[slot];
-                    if (*(volatile int*)&ctl->collided) continue;
-                    const double* pf = W.pos + (size_t)node * 3;
-                    d3 f = {pf[0], pf[1], pf[2]}, t = {pf[3], pf[4], pf[5]};
-                    d3 vec = t - f;
-                    const double len = sqrt(dot(vec, vec));       // collision_checker.py:130-131
-                    d3 c = f + 0.5 * vec;
-                    d3 a = (1.0 / len) * vec;
-                    const double h = 0.5 * len, r = P.rad[n];
-                    double best = DBL_MAX;
-                    if (env.obs.ntri > 0) cylinder_vs_mesh(env.obs, s_top, ntop, c, a, h, r, ctl, best, wk);
-                    for (int k = 0; k < env.nprim && !*(volatile int*)&ctl->collided; ++k) {
-                        const double d = cylinder_vs_prim(env.prims[k], c, a, h, r, best);
-                        if (d <= 0.0) *(volatile int*)&ctl->collided = 1;
-                        else if (d < best) {
-                            best = d;
-                            atomicMin(&ctl->bound_bits, __float_as_int(__double2float_ru(d)));
+                    if (sp == 0 && !exhausted) {  // next live cylinder for this lane
+#pragma unroll 1
+                        for (int tries = 0; tries < 4; ++tries) {
+                            const int q = atomicAdd(&W.ticket, 1);
+                            if (q >= range_end) {
+                                exhausted = true;
+                                break;
+                            }
+                            code = W.items[q];
+                            slot = (code >> 10) & 31u;
+                            if (vcoll[slot]) {
+                                if (m < kGroupMin) {  // this pass is that configuration's alone: nothing left to do
+                                    exhausted = true;
+                                    break;
+                                }
+                                continue;
+                            }
+                            d3 c, a;
+                            double h, r;
+                            cylinder_of(code, c, a, h, r);
+                            for (int k = 0; k < env.nprim && !vcoll[slot]; ++k)
+                                record(slot, cylinder_vs_prim(env.prims[k], c, a, h, r,
+                                                              __longlong_as_double((long long)W.best_bits[slot])));
+                            if (bvh.ntri > 0 && !vcoll[slot]) {
+                                cf = f3{(float)c.x, (float)c.y, (float)c.z};
+                                rb = __fsqrt_ru(__fmaf_ru((float)h, (float)h, (float)r * (float)r)) * 1.000001f;
+                                rin = fminf((float)h, (float)r);
+                                stk[0] = 0;
+                                sp = 1;
+                                break;
+                            }
                         }
                     }
-                    if (best < DBL_MAX) atomicMin(&W.best_bits[slot], (unsigned long long)__double_as_longlong(best));
+                    if (!__any_sync(0xffffffffu, sp > 0 || !exhausted)) break;
+#pragma unroll 1
+                    for (int rep = 0; rep < CTRB_GROUP_REPS; ++rep) {
+                        int leaf = 0;
+                        bool has_leaf = false;
+#pragma unroll 1
+                        for (int mstep = 0; mstep < CTRB_GROUP_INNER && sp > 0 && !has_leaf; ++mstep) {
+                            if (vcoll[slot]) {
+                                sp = 0;
+                                break;
+                            }
+                            const int e = stk[--sp * 32];
+                            if (e < 0) {
+                                leaf = e;
+                                has_leaf = true;
+                            } else {
+                                const BvhNode nd = load_node(bvh, nullptr, 0, e);
+                                wk.nodes++;
+                                const float reach = __int_as_float(vbound[slot]) + rb + slack;
+                                const float reach2 = reach * reach * 1.000001f;
+                                float d0 = aabb_dist2(nd.lo0, nd.hi0, cf);
+                                float d1 = aabb_dist2(nd.lo1, nd.hi1, cf);
+                                int l0 = nd.c0, l1 = nd.c1;
+                                if (d1 < d0) {  // near child on top of the stack
+                                    float t = d0; d0 = d1; d1 = t;
+                                    int ti = l0; l0 = l1; l1 = ti;
+                                }
+                                if (d1 <= reach2 && sp < kGStack) stk[sp++ * 32] = l1;
+                                if (d0 <= reach2 && sp < kGStack) stk[sp++ * 32] = l0;
+                            }
+                        }
+                        if (has_leaf) {
+                            const int lc = ~leaf;
+                            const int tfirst = lc >> 3, tcnt = (lc & 7) + 1;
+#pragma unroll 1
+                            for (int t = tfirst; t < tfirst + tcnt && !vcoll[slot]; ++t) {
+                                const float4* tp = bvh.tri32 + (size_t)t * 3;
+                                const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                                const float dpt = sqrtf(point_tri_dist2<f3, float>(cf, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z},
+                                                                                    f3{v2.x, v2.y, v2.z}));
+                                wk.pre++;
+                                if (dpt + slack < rin) {  // a ball of radius min(h, r) about the centre lies inside the cylinder
+                                    vcoll[slot] = 1;
+                                    sp = 0;
+                                    break;
+                                }
+                                // the centre belongs to the cylinder: d(cyl, tri) <= dpt
+                                atomicMin(&W.bound_bits[slot], __float_as_int(dpt + slack));
+                                const float bound = __int_as_float(vbound[slot]);
+                                const float lb = dpt - rb - slack;  // d(cyl, tri) >= dpt - rb
+                                if (lb > bound) continue;
+                                const int qs = atomicAdd(&W.qcount, 1);
+                                if (qs < kGQueue) {
+                                    W.q_tri[qs] = t;
+                                    W.q_item[qs] = code;
+                                    W.q_lb[qs] = lb;
+                                } else {
+                                    exact_pair(code, t, bound);  // queue full: decide here (rare)
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (__shfl_sync(0xffffffffu, *(volatile int*)&W.qcount, 0) >= 32) drain();
                 }
+                drain();
             }
             __syncwarp();
             // ---- lane = configuration again: goal distance, cost, results (coalesced across lanes)
             if (mine) {
-                const bool collided = *(volatile int*)&W.ctl[lane].collided != 0;
+                const bool collided = vcoll[lane] != 0;
                 const double best = __longlong_as_double((long long)W.best_bits[lane]);
                 double gd = DBL_MAX;
                 if (tn > 0 && env.goal.shape != CTRB_SHAPE_NONE) {
@@ -739,7 +880,7 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) chain_eval_packed_kernel(Eval
                     }
                     if (gd <= 0.0) gd = -1.0;
                 }
-                const double om = collided ? -1.0 : (have_obstacles && ncyl > 0 ? best : DBL_MAX);
+                const double om = collided ? -1.0 : (have_obstacles ? best : DBL_MAX);
                 P.obstacle_min[b] = om;
                 P.goal_dist[b] = gd;
                 if (P.collide) P.collide[b] = collided ? 1 : 0;
@@ -748,12 +889,12 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) chain_eval_packed_kernel(Eval
                     if (!collided) {
                         const double g0 = gd < 0.0 ? 0.0 : gd;
                         if (P.cd.cost_type == CTRB_COST_SOAPWG) {
-                            const double inv = 1.0 / om;
+                            const double inv = 1.0 / om;  // obstacles_and_goal.py:39-45,87-88
                             cst = g0 * P.cd.goal_weight + inv * inv;
                         } else if (P.cd.cost_type == CTRB_COST_ONLY_GOAL) {
-                            cst = g0;
+                            cst = g0;  // only_goal_distance.py:20-24
                         } else {
-                            cst = 0.0;
+                            cst = 0.0;  // FTL family: the twist term comes from ctrb_eta_ftl_batch
                         }
                     }
                     P.cost[b] = cst;
@@ -784,26 +925,25 @@ size_t eval_smem_bytes(int max_nodes) {
 
 int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
     if (P.B <= 0) return CTRB_OK;
-    // The packed kernel is kept for experiments only (CTRB_EVAL_PACKED=1): measured on a B200 it is 25-30 % SLOWER
-    // than one warp per configuration (18.6 vs 24.5 M configs/s, C3 shallow) although every lane is busy -- the walks
-    // diverge lane by lane and the fp64 exact tests serialise, and with more cylinders in flight per warp the shared
-    // bounds tighten later (exact tests per config 10.6 vs 6.2).  See DESIGN.md section 9.
-    if (P.max_nodes <= kPool && getenv("CTRB_EVAL_PACKED")) {
-        const size_t smem_p = (size_t)kTopNodes * sizeof(BvhNode) + (size_t)kPWarps * sizeof(PackedWarpMem);
+    // grouped kernel (several configurations per warp) whenever a configuration fits the warp's node pool;
+    // CTRB_EVAL_GROUP=0 forces one warp per configuration
+    static const bool group_off = getenv("CTRB_EVAL_GROUP") && atoi(getenv("CTRB_EVAL_GROUP")) == 0;
+    if (P.max_nodes <= kPool && P.bvh_depth + 2 <= kGStack && !group_off) {
+        const size_t smem_p = (size_t)kGWarps * sizeof(GroupMem);
         CTRB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
         int per_sm = 1;
         if (fused) {
-            CTRB_CUDA(cudaFuncSetAttribute(chain_eval_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-            CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_eval_packed_kernel<true>, kPWarps * 32, smem_p));
+            CTRB_CUDA(cudaFuncSetAttribute(chain_eval_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_eval_group_kernel<true>, kGWarps * 32, smem_p));
         } else {
-            CTRB_CUDA(cudaFuncSetAttribute(chain_eval_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-            CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_eval_packed_kernel<false>, kPWarps * 32, smem_p));
+            CTRB_CUDA(cudaFuncSetAttribute(chain_eval_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_eval_group_kernel<false>, kGWarps * 32, smem_p));
         }
         const long long chunks = (P.B + 31) / 32;
-        const int grid_p = (int)std::min<long long>((chunks + kPWarps - 1) / kPWarps, (long long)ctx->sm_count * std::max(per_sm, 1));
+        const int grid_p = (int)std::min<long long>((chunks + kGWarps - 1) / kGWarps, (long long)ctx->sm_count * std::max(per_sm, 1));
         KernelTimer kt(ctx, CTRB_KERNEL_CHAIN_EVAL);
-        if (fused) chain_eval_packed_kernel<true><<<grid_p, kPWarps * 32, smem_p, ctx->stream>>>(P);
-        else chain_eval_packed_kernel<false><<<grid_p, kPWarps * 32, smem_p, ctx->stream>>>(P);
+        if (fused) chain_eval_group_kernel<true><<<grid_p, kGWarps * 32, smem_p, ctx->stream>>>(P);
+        else chain_eval_group_kernel<false><<<grid_p, kGWarps * 32, smem_p, ctx->stream>>>(P);
         ctx->launches++;
         CTRB_CUDA(cudaGetLastError());
         return CTRB_OK;
@@ -851,6 +991,7 @@ int launch_eval_fused(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, c
     P.collide = collide;
     P.cd = *cd;
     P.counters = ctx->d_counters;
+    P.bvh_depth = env->stats[2];
     P.max_nodes = m->mc.total_nodes;
     return launch_eval(ctx, P, true);
 }
@@ -869,6 +1010,7 @@ int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube
     P.obstacle_min = obstacle_min;
     P.goal_dist = goal_dist;
     P.counters = ctx->d_counters;
+    P.bvh_depth = env->stats[2];
     P.max_nodes = max_nodes;
     return launch_eval(ctx, P, false);
 }
@@ -890,6 +1032,7 @@ int launch_eval_curves_cost(ctrb_ctx* ctx, const ctrb_env* env, const ctrb_cost_
     P.collide = collide;
     P.cd = *cd;
     P.counters = ctx->d_counters;
+    P.bvh_depth = env->stats[2];
     P.max_nodes = max_nodes;
     return launch_eval(ctx, P, false);
 }

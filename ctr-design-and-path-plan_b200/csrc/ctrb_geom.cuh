@@ -151,6 +151,8 @@ __device__ __noinline__ double seg_cyl_dist2(d3 p0, d3 p1, d3 c, d3 a, double h,
             side = -1;
         }
         if (hi - lo < 1e-14) break;
+        // F is convex and [lo, hi] brackets its minimiser: F(s) - min F <= |F'(s)| (hi - lo)
+        if (fabs(g) * (hi - lo) <= 1e-14 * F) break;
     }
     return best;
 }
