@@ -753,8 +753,8 @@ __global__ void __launch_bounds__(kGWarps * 32, 2) chain_eval_group_kernel(const
                 int sp = 0, slot = 0;
                 unsigned code = 0;
                 bool exhausted = false;
-                f3 cf = {0.f, 0.f, 0.f};
-                float rb = 0.f, rin = 0.f;
+                f3 cf = {0.f, 0.f, 0.f}, af = {0.f, 0.f, 0.f};
+                float rb = 0.f, hf = 0.f, rf = 0.f;
                 for (;;) {
                     if (sp == 0 && !exhausted) {  // next live cylinder for this lane
 #pragma unroll 1
@@ -781,8 +781,10 @@ __global__ void __launch_bounds__(kGWarps * 32, 2) chain_eval_group_kernel(const
                                                               __longlong_as_double((long long)W.best_bits[slot])));
                             if (bvh.ntri > 0 && !vcoll[slot]) {
                                 cf = f3{(float)c.x, (float)c.y, (float)c.z};
-                                rb = __fsqrt_ru(__fmaf_ru((float)h, (float)h, (float)r * (float)r)) * 1.000001f;
-                                rin = fminf((float)h, (float)r);
+                                af = f3{(float)a.x, (float)a.y, (float)a.z};
+                                hf = (float)h;
+                                rf = (float)r;
+                                rb = __fsqrt_ru(__fmaf_ru(hf, hf, rf * rf)) * 1.000001f;
                                 stk[0] = 0;
                                 sp = 1;
                                 break;
@@ -827,16 +829,20 @@ __global__ void __launch_bounds__(kGWarps * 32, 2) chain_eval_group_kernel(const
                             for (int t = tfirst; t < tfirst + tcnt && !vcoll[slot]; ++t) {
                                 const float4* tp = bvh.tri32 + (size_t)t * 3;
                                 const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-                                const float dpt = sqrtf(point_tri_dist2<f3, float>(cf, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z},
-                                                                                    f3{v2.x, v2.y, v2.z}));
+                                // q = the triangle's closest point to the cylinder's centre, in cylinder coordinates
+                                const f3 w = point_tri_closest(cf, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z}, f3{v2.x, v2.y, v2.z});
                                 wk.pre++;
-                                if (dpt + slack < rin) {  // a ball of radius min(h, r) about the centre lies inside the cylinder
+                                const float dpt2 = dot(w, w), tq = dot(w, af);
+                                const float dpt = sqrtf(dpt2), rho = sqrtf(fmaxf(dpt2 - tq * tq, 0.f));
+                                const float et = fabsf(tq) - hf, er = rho - rf;
+                                if (et + slack < 0.f && er + slack < 0.f) {  // q is inside the solid cylinder for certain
                                     vcoll[slot] = 1;
                                     sp = 0;
                                     break;
                                 }
-                                // the centre belongs to the cylinder: d(cyl, tri) <= dpt
-                                atomicMin(&W.bound_bits[slot], __float_as_int(dpt + slack));
+                                // q belongs to the triangle: d(cyl, tri) <= d(q, cyl)
+                                const float dt_ = fmaxf(et, 0.f), dr_ = fmaxf(er, 0.f);
+                                atomicMin(&W.bound_bits[slot], __float_as_int(sqrtf(fmaf(dt_, dt_, dr_ * dr_)) + slack));
                                 const float bound = __int_as_float(vbound[slot]);
                                 const float lb = dpt - rb - slack;  // d(cyl, tri) >= dpt - rb
                                 if (lb > bound) continue;

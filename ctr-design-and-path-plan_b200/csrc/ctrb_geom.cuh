@@ -76,6 +76,41 @@ __device__ __forceinline__ S point_tri_dist2(V p, V a, V b, V c) {
     return t * t / nn;
 }
 
+// fp32: the vector from p to the closest point of triangle (a, b, c) (same region walk as point_tri_dist2)
+__device__ __forceinline__ f3 point_tri_closest(f3 p, f3 a, f3 b, f3 c) {
+    const f3 ab = b - a, ac = c - a, ap = p - a;
+    const float d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0 && d2 <= 0) return f3{-ap.x, -ap.y, -ap.z};
+    const f3 bp = p - b;
+    const float d3_ = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3_ >= 0 && d4 <= d3_) return f3{-bp.x, -bp.y, -bp.z};
+    const float vc = d1 * d4 - d3_ * d2;
+    if (vc <= 0 && d1 >= 0 && d3_ <= 0) {
+        const float v = d1 / (d1 - d3_);
+        return f3{v * ab.x - ap.x, v * ab.y - ap.y, v * ab.z - ap.z};
+    }
+    const f3 cp = p - c;
+    const float d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0 && d5 <= d6) return f3{-cp.x, -cp.y, -cp.z};
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+        const float w = d2 / (d2 - d6);
+        return f3{w * ac.x - ap.x, w * ac.y - ap.y, w * ac.z - ap.z};
+    }
+    const float va = d3_ * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3_) >= 0 && (d5 - d6) >= 0) {
+        const float w = (d4 - d3_) / ((d4 - d3_) + (d5 - d6));
+        const f3 bc = c - b;
+        return f3{w * bc.x - bp.x, w * bc.y - bp.y, w * bc.z - bp.z};
+    }
+    // interior: foot of the perpendicular
+    const f3 n = {ab.y * ac.z - ab.z * ac.y, ab.z * ac.x - ab.x * ac.z, ab.x * ac.y - ab.y * ac.x};
+    const float nn = dot(n, n);
+    if (nn == 0) return f3{-ap.x, -ap.y, -ap.z};
+    const float t = -dot(ap, n) / nn;
+    return f3{t * n.x, t * n.y, t * n.z};
+}
+
 // distance from a point to the solid cylinder {c + t a + u : |t| <= h, u _|_ a, |u| <= r}
 __device__ __forceinline__ double point_cyl_dist(d3 x, d3 c, d3 a, double h, double r) {
     d3 y = x - c;
