@@ -78,6 +78,7 @@ struct EvalParams {
     unsigned long long* counters;  // [0..3] work counters, [4] config ticket
     int max_nodes;                 // shared-memory rows per warp
     int bvh_depth;                 // of the obstacle mesh's BVH (host-side knowledge: picks the traversal kernel)
+    int chunk;                     // grouped kernel: configurations a warp takes per ticket (<= 32)
 };
 
 __device__ __forceinline__ BvhNode load_node(const DevBvh& bvh, const BvhNode* s_top, int ntop, int ni) {
@@ -600,11 +601,11 @@ __global__ void __launch_bounds__(kGWarps * 32, 2) chain_eval_group_kernel(const
         long long b0;
         {
             unsigned long long t = 0;
-            if (lane == 0) t = atomicAdd(P.counters + 4, 32ULL);
+            if (lane == 0) t = atomicAdd(P.counters + 4, (unsigned long long)P.chunk);
             b0 = (long long)__shfl_sync(0xffffffffu, t, 0);
         }
         if (b0 >= P.B) break;
-        const int nchunk = (int)min((long long)32, P.B - b0);
+        const int nchunk = (int)min((long long)P.chunk, P.B - b0);
         int done = 0;
         while (done < nchunk) {
             // ---- lane = configuration: node counts, how many configurations fit the pool
@@ -945,11 +946,15 @@ int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
             CTRB_CUDA(cudaFuncSetAttribute(chain_eval_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
             CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_eval_group_kernel<false>, kGWarps * 32, smem_p));
         }
-        const long long chunks = (P.B + 31) / 32;
+        // a small batch (an RRT round, a simplex) is spread over all resident warps rather than packed 32 to a warp
+        const long long resident = (long long)ctx->sm_count * std::max(per_sm, 1) * kGWarps;
+        EvalParams Q = P;
+        Q.chunk = (int)std::min<long long>(32, std::max<long long>(1, P.B / resident));
+        const long long chunks = (P.B + Q.chunk - 1) / Q.chunk;
         const int grid_p = (int)std::min<long long>((chunks + kGWarps - 1) / kGWarps, (long long)ctx->sm_count * std::max(per_sm, 1));
         KernelTimer kt(ctx, CTRB_KERNEL_CHAIN_EVAL);
-        if (fused) chain_eval_group_kernel<true><<<grid_p, kGWarps * 32, smem_p, ctx->stream>>>(P);
-        else chain_eval_group_kernel<false><<<grid_p, kGWarps * 32, smem_p, ctx->stream>>>(P);
+        if (fused) chain_eval_group_kernel<true><<<grid_p, kGWarps * 32, smem_p, ctx->stream>>>(Q);
+        else chain_eval_group_kernel<false><<<grid_p, kGWarps * 32, smem_p, ctx->stream>>>(Q);
         ctx->launches++;
         CTRB_CUDA(cudaGetLastError());
         return CTRB_OK;
