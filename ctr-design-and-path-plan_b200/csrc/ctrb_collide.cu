@@ -934,7 +934,8 @@ int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
     if (P.B <= 0) return CTRB_OK;
     // grouped kernel (several configurations per warp) whenever a configuration fits the warp's node pool;
     // CTRB_EVAL_GROUP=0 forces one warp per configuration
-    static const bool group_off = getenv("CTRB_EVAL_GROUP") && atoi(getenv("CTRB_EVAL_GROUP")) == 0;
+    const char* genv = getenv("CTRB_EVAL_GROUP");
+    const bool group_off = genv && atoi(genv) == 0;
     if (P.max_nodes <= kPool && P.bvh_depth + 2 <= kGStack && !group_off) {
         const size_t smem_p = (size_t)kGWarps * sizeof(GroupMem);
         CTRB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), ctx->stream));

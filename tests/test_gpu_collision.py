@@ -215,3 +215,45 @@ def test_large_batch_properties():
     oenv = orc.Env.from_json(FIXTURES / "env_c3_colon_straight.json")
     o_obs, o_goal, _ = oenv.eval_batch(om, idx[sub], theta[sub], RAD3, 3.0)
     _compare(obs[sub], goal[sub], o_obs, o_goal)
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 1000, 2369, 100_003])
+def test_grouped_and_one_warp_per_config_kernels_agree(B, monkeypatch):
+    """chain_eval_group_kernel (several configurations per warp; chunk size chosen from the batch size) and
+    chain_eval_kernel (one warp per configuration; CTRB_EVAL_GROUP=0) are two schedules of the same exact query:
+    identical bits, distances and costs on ragged batch sizes, mixed short and long configurations included."""
+    from ctrdapp_b200.collision import CollisionChecker
+    m = gpu_model("c3_three_tube")
+    cc = CollisionChecker(FIXTURES / "env_c3_colon_straight.json")
+    rng = np.random.default_rng(B)
+    idx, theta = random_configs(m.num_discrete_points, B, rng, 1, 8)
+    long_ones = rng.random(B) < 0.2            # a fifth of the batch fully random (up to 198 cylinders)
+    idx2, _ = random_configs(m.num_discrete_points, B, rng)
+    idx[long_ones] = idx2[long_ones]
+    monkeypatch.delenv("CTRB_EVAL_GROUP", raising=False)
+    a = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
+    monkeypatch.setenv("CTRB_EVAL_GROUP", "0")
+    b = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+
+
+def test_model_larger_than_the_node_pool_takes_the_one_warp_kernel():
+    """A configuration with more nodes than the grouped kernel's per-warp pool (256) falls back to one warp per
+    configuration; results against the oracle as for any other model."""
+    from oracle import oracle as orc
+    from ctrdapp_b200.collision import CollisionChecker
+    from ctrdapp_b200.model.kinematic import Kinematic
+    from util import split_q
+    bases, dof = ["linear"] * 3, [2, 3, 3]
+    q = [0.01, 0.0005, 0.02, 0.0001, 0.001, 0.015, 0.0002, 0.0003]
+    lengths = [60, 120, 180]                   # 61 + 121 + 181 = 363 nodes
+    m = Kinematic(3, split_q(q, dof), dof, lengths, 1, bases)
+    om = orc.make_model(bases, dof, q, lengths, 1)
+    cc = CollisionChecker(FIXTURES / "env_boxes_multi.json")
+    oenv = orc.Env.from_json(FIXTURES / "env_boxes_multi.json")
+    rng = np.random.default_rng(11)
+    idx, theta = random_configs(m.num_discrete_points, 200, rng)
+    obs, goal, cost, coll = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
+    o_obs, o_goal, _ = oenv.eval_batch(om, idx, theta, RAD3, 3.0)
+    _compare(obs, goal, o_obs, o_goal)
