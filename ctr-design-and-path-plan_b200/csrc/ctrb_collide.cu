@@ -79,6 +79,7 @@ struct EvalParams {
     int max_nodes;                 // shared-memory rows per warp
     int bvh_depth;                 // of the obstacle mesh's BVH (host-side knowledge: picks the traversal kernel)
     int chunk;                     // grouped kernel: configurations a warp takes per ticket (<= 32)
+    int pool;                      // grouped kernel: node positions per warp
 };
 
 __device__ __forceinline__ BvhNode load_node(const DevBvh& bvh, const BvhNode* s_top, int ntop, int ni) {
@@ -497,9 +498,22 @@ __global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_
 // nodes), then all lanes that hold
 // a leaf run the fp32 point-triangle prefilter together; surviving (cylinder, triangle) pairs go to the warp's queue
 // and are decided by the exact fp64 test 32 at a time.
-constexpr int kGWarps = 8;
-constexpr int kPool = 256;     // node positions (fp64 xyz) per warp
-constexpr int kGQueue = 128;   // deferred exact tests per warp
+#ifndef CTRB_GROUP_WARPS
+#define CTRB_GROUP_WARPS 8
+#endif
+#ifndef CTRB_GROUP_BLOCKS
+#define CTRB_GROUP_BLOCKS 2
+#endif
+#ifndef CTRB_GROUP_QUEUE
+#define CTRB_GROUP_QUEUE 64
+#endif
+constexpr int kGWarps = CTRB_GROUP_WARPS;
+// Node positions (fp64 xyz) per warp: the pool is sized at launch, kPoolMin or kPoolMax, whichever the longest
+// configuration needs.  Shared memory is taken from the SM's L1, and this kernel lives on L1 hits (BVH nodes,
+// triangles): 2 x 8 warps with 256-node pools and 128-entry queues (197 KB of shared memory) ran at 83 M configs/s,
+// with 208-node pools and 64-entry queues (162 KB) at 92 M; more resident warps (20-24) made it slower (49-58 M).
+constexpr int kPoolMin = 208, kPoolMax = 256;
+constexpr int kGQueue = CTRB_GROUP_QUEUE;  // deferred exact tests per warp
 constexpr int kGStack = 24;    // traversal stack entries per lane, in SHARED memory (a BVH deeper than kGStack - 2 takes
                                // chain_eval_kernel): with 32 busy lanes per warp a local-memory stack thrashed the ~40 KB
                                // of L1 that the shared-memory carve-out leaves (ncu: L1 hit rate 50 %, long-scoreboard 8.4)
@@ -518,8 +532,8 @@ constexpr int kGroupMin = CTRB_GROUP_MIN;   // fewer configurations than this in
 #endif
 
 struct GroupMem {
-    double pos[kPool * 3];
-    unsigned int items[kPool];       // node (10 bits) | slot (5 bits) << 10 | tube (2 bits) << 15
+    double* pos;                     // [pool][3]  (behind the GroupMem array in dynamic shared memory)
+    unsigned int* items;             // [pool]     node (10 bits) | slot (5 bits) << 10 | tube (2 bits) << 15
     unsigned long long best_bits[32];
     int bound_bits[32];
     int collided[32];
@@ -532,12 +546,19 @@ struct GroupMem {
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kGWarps * 32, 2) chain_eval_group_kernel(const __grid_constant__ EvalParams P) {
+__global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_group_kernel(const __grid_constant__ EvalParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GroupMem* s_all = reinterpret_cast<GroupMem*>(smem_raw);
     const EnvConst& env = *P.env;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GroupMem& W = s_all[warp];
+    const int pool = P.pool;
+    if (lane == 0) {
+        double* pos0 = reinterpret_cast<double*>(s_all + kGWarps);
+        W.pos = pos0 + (size_t)warp * pool * 3;
+        W.items = reinterpret_cast<unsigned int*>(pos0 + (size_t)kGWarps * pool * 3) + (size_t)warp * pool;
+    }
+    __syncwarp();
     int* const stk = &W.stack[0][lane];  // entry k of this lane's stack = stk[k * 32]
     const int T = FUSED ? P.mc.T : P.tube_num;
     const bool have_obstacles = env.obs.ntri > 0 || env.nprim > 0;
@@ -633,7 +654,7 @@ __global__ void __launch_bounds__(kGWarps * 32, 2) chain_eval_group_kernel(const
                     iend += c;
                 }
             }
-            const unsigned fit = __ballot_sync(0xffffffffu, valid && nend <= kPool);
+            const unsigned fit = __ballot_sync(0xffffffffu, valid && nend <= pool);
             int m = __ffs(~fit) - 1;  // leading lanes that fit (the host guarantees one configuration always fits)
             if (m < 0) m = 32;
             m = max(m, 1);
@@ -936,8 +957,9 @@ int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
     // CTRB_EVAL_GROUP=0 forces one warp per configuration
     const char* genv = getenv("CTRB_EVAL_GROUP");
     const bool group_off = genv && atoi(genv) == 0;
-    if (P.max_nodes <= kPool && P.bvh_depth + 2 <= kGStack && !group_off) {
-        const size_t smem_p = (size_t)kGWarps * sizeof(GroupMem);
+    if (P.max_nodes <= kPoolMax && P.bvh_depth + 2 <= kGStack && !group_off) {
+        const int pool = P.max_nodes <= kPoolMin ? kPoolMin : kPoolMax;
+        const size_t smem_p = (size_t)kGWarps * (sizeof(GroupMem) + (size_t)pool * (3 * sizeof(double) + sizeof(unsigned int)));
         CTRB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
         int per_sm = 1;
         if (fused) {
@@ -950,6 +972,7 @@ int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
         // a small batch (an RRT round, a simplex) is spread over all resident warps rather than packed 32 to a warp
         const long long resident = (long long)ctx->sm_count * std::max(per_sm, 1) * kGWarps;
         EvalParams Q = P;
+        Q.pool = pool;
         Q.chunk = (int)std::min<long long>(32, std::max<long long>(1, P.B / resident));
         const long long chunks = (P.B + Q.chunk - 1) / Q.chunk;
         const int grid_p = (int)std::min<long long>((chunks + kGWarps - 1) / kGWarps, (long long)ctx->sm_count * std::max(per_sm, 1));
