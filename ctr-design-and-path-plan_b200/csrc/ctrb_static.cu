@@ -26,7 +26,13 @@
 
 namespace ctrb {
 
-constexpr int kSWarps = 3;    // warps (= configurations) per block: 5 blocks (15 warps) per SM by smem and registers
+#ifndef CTRB_QR_WARPS
+#define CTRB_QR_WARPS 3
+#endif
+#ifndef CTRB_QR_BLOCKS
+#define CTRB_QR_BLOCKS 5
+#endif
+constexpr int kSWarps = CTRB_QR_WARPS;    // warps (= configurations) per block: 5 blocks (15 warps) per SM by smem and registers
 constexpr int kNP = 31;       // leading dimension of the n x n work matrices (odd: conflict-free column access)
 constexpr int kNV = 32;       // padded vector length
 
@@ -487,7 +493,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotT
 }
 
 // ------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(kSWarps * 32, 5)
+__global__ void __launch_bounds__(kSWarps * 32, CTRB_QR_BLOCKS)
     static_solve_kernel(const __grid_constant__ StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
                         const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                         double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,

@@ -23,13 +23,20 @@
 // through the relative frame at the end of section 1), so a column needs 4 (or 8) node evaluations, not 12,
 // and the untouched entries are exact zeros either way.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctrb_static_common.cuh"
 
 namespace ctrb {
 
-constexpr int kFWarps = 4;   // warps (= configurations in flight) per block
+#ifndef CTRB_FAST_WARPS
+#define CTRB_FAST_WARPS 4
+#endif
+#ifndef CTRB_FAST_BLOCKS
+#define CTRB_FAST_BLOCKS 3
+#endif
+constexpr int kFWarps = CTRB_FAST_WARPS;   // warps (= configurations in flight) per block
 constexpr int kLD = kJLD;    // leading dimension, column-major: element (i, j) at i + j * kLD.  Odd, so both
                              // "lane = row" (stride 1) and "lane = column" (stride 31) accesses are conflict-free
 constexpr unsigned kFull = 0xffffffffu;
@@ -288,7 +295,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
     }
 }
 
-__global__ void __launch_bounds__(kFWarps * 32, 3)
+__global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
     static_fast_kernel(const __grid_constant__ StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
                        const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                        double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
