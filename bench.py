@@ -290,7 +290,7 @@ def main():
 
     def step_host():
         eval_any(m, B, idx_p, theta_p, (obs_p, goal_p, cost_p, coll_p, info_p, nfev_p), L.MEM_HOST)
-        return float(np.nanmin(cost_p)) if np.isfinite(cost_p).any() else float("inf")
+        return float(np.fmin.reduce(cost_p))  # best node of the step, read on the host (NaN = colliding, ignored)
 
     step_host()
     barrier()

@@ -120,6 +120,77 @@ struct Stage {
         return CTRB_OK;
     }
 };
+
+// idx[b][t] in [0, npts[t]) (ValueError in the reference's mirror); `first` = index of idx[0] in the caller's batch
+int check_idx_host(const ctrb_model* m, int64_t B, const int32_t* idx, int64_t first = 0) {
+    const int T = m->mc.T;
+    int bad = 0;
+    for (int64_t b = 0; b < B; ++b)
+        for (int t = 0; t < T; ++t) bad |= (idx[b * T + t] < 0) | (idx[b * T + t] >= m->mc.npts[t]);
+    if (!bad) return CTRB_OK;
+    for (int64_t b = 0; b < B; ++b)
+        for (int t = 0; t < T; ++t)
+            CTRB_REQUIRE(idx[b * T + t] >= 0 && idx[b * T + t] < m->mc.npts[t], "idx[%lld]=%d outside [0,%d)",
+                         (long long)((first + b) * T + t), idx[b * T + t], m->mc.npts[t]);
+    return CTRB_OK;
+}
+
+// Host-memory calls on large batches run as a pipeline over chunks of the batch: while chunk c computes on ctx->stream,
+// chunk c+1's inputs are validated on the CPU and copied in on ctx->stream2, and chunk c-1's results are copied out
+// behind it.  Two sets of device buffers (scratch slots 1.. and 17..) alternate.  Order on stream2:
+//     in(0) in(1) [k(0)] out(0) in(2) [k(1)] out(1) ...      ([k(c)] = wait for chunk c's kernels)
+// so in(c+2) never overwrites the inputs that the kernels of chunk c still read, and the kernels of chunk c+2 start
+// after in(c+2), i.e. after out(c) has read the outputs they overwrite.
+// Chunks stay large (an eighth of the batch, at least 2^17 configurations): a launch over fewer configurations loses
+// more to its tail than the overlap gains.
+constexpr int64_t kPipeMinBatch = 1 << 19;
+inline int64_t pipe_chunk(int64_t B) {
+    if (B < kPipeMinBatch) return B;
+    int64_t ch = (B + 7) / 8;
+    ch = std::min<int64_t>(std::max<int64_t>(ch, 1 << 17), 1 << 22);
+    return (ch + 31) / 32 * 32;
+}
+template <class In, class Launch, class Out>
+int host_pipeline(ctrb_ctx* ctx, int64_t B, int64_t CH, In copy_in, Launch launch, Out copy_out) {
+    int rc = CTRB_OK;
+    int64_t prev0 = 0, prevn = 0;
+    int c = 0;
+    for (int64_t b0 = 0; b0 < B && rc == CTRB_OK; b0 += CH, ++c) {
+        const int64_t nb = std::min(CH, B - b0);
+        const int p = c & 1;
+        rc = copy_in(b0, nb, p, ctx->stream2);
+        if (rc) break;
+        if (cudaEventRecord(ctx->ev_chunk[p], ctx->stream2) != cudaSuccess ||
+            cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[p], 0) != cudaSuccess) { rc = CTRB_ERR_CUDA; break; }
+        rc = launch(b0, nb, p);
+        if (rc) break;
+        if (cudaEventRecord(ctx->ev_done[p], ctx->stream) != cudaSuccess) { rc = CTRB_ERR_CUDA; break; }
+        if (c > 0) {
+            if (cudaStreamWaitEvent(ctx->stream2, ctx->ev_done[p ^ 1], 0) != cudaSuccess) { rc = CTRB_ERR_CUDA; break; }
+            rc = copy_out(prev0, prevn, p ^ 1, ctx->stream2);
+        }
+        prev0 = b0;
+        prevn = nb;
+    }
+    if (rc == CTRB_OK && c > 0) {
+        const int p = (c - 1) & 1;
+        if (cudaStreamWaitEvent(ctx->stream2, ctx->ev_done[p], 0) != cudaSuccess) rc = CTRB_ERR_CUDA;
+        else rc = copy_out(prev0, prevn, p, ctx->stream2);
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = cudaStreamSynchronize(ctx->stream2);
+    if (rc == CTRB_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        set_error("host pipeline: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        rc = CTRB_ERR_CUDA;
+    }
+    return rc;
+}
+#define CTRB_COPY(dst, src, bytes, kind, stream)                                                           \
+    do {                                                                                                   \
+        if ((bytes) && cudaMemcpyAsync(dst, src, bytes, kind, stream) != cudaSuccess) {                    \
+            set_error("copy failed: %s", cudaGetErrorString(cudaGetLastError()));                          \
+            return (int)CTRB_ERR_CUDA;                                                                     \
+        }                                                                                                  \
+    } while (0)
 }  // namespace
 
 extern "C" {
@@ -156,6 +227,7 @@ int ctrb_ctx_create(int device, ctrb_ctx** out) {
     for (int i = 0; i < 2; ++i) {
         CTRB_CUDA(cudaEventCreate(&c->ev[i]));
         CTRB_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+        CTRB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
     for (int k = 0; k < 5; ++k)
         for (int i = 0; i < 2; ++i) {
@@ -181,12 +253,13 @@ void ctrb_ctx_destroy(ctrb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2);
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < 32; ++i)
         if (c->scratch[i]) cudaFree(c->scratch[i]);
     cudaFree(c->d_counters);
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(c->ev[i]);
         cudaEventDestroy(c->ev_chunk[i]);
+        cudaEventDestroy(c->ev_done[i]);
     }
     for (int k = 0; k < 5; ++k)
         for (int i = 0; i < 2; ++i) cudaEventDestroy(c->kev[k][i]);
@@ -626,9 +699,41 @@ int ctrb_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* env, con
         return launch_eval_fused(ctx, m, env, cd, B, idx, theta, rad, obstacle_min, goal_dist, cost, collide);
     }
     const size_t n = (size_t)B * T;
-    for (size_t i = 0; i < n; ++i) {
-        int t = (int)(i % T);
-        CTRB_REQUIRE(idx[i] >= 0 && idx[i] < m->mc.npts[t], "idx[%zu]=%d outside [0,%d)", i, idx[i], m->mc.npts[t]);
+    const int64_t CH = pipe_chunk(B);
+    if (CH < B) {  // large batch: chunked copy / compute pipeline
+        void* d[2][6];
+        const size_t sz[6] = {(size_t)CH * T * sizeof(int32_t), (size_t)CH * T * sizeof(double), (size_t)CH * sizeof(double),
+                              (size_t)CH * sizeof(double), (size_t)CH * sizeof(double), (size_t)CH};
+        for (int p = 0; p < 2; ++p)
+            for (int k = 0; k < 6; ++k) {
+                int rc = ctx_scratch(ctx, (p ? 17 : 1) + k, sz[k], &d[p][k]);
+                if (rc) return rc;
+            }
+        return host_pipeline(
+            ctx, B, CH,
+            [&](int64_t b0, int64_t nb, int p, cudaStream_t s) -> int {
+                int rc = check_idx_host(m, nb, idx + b0 * T, b0);
+                if (rc) return rc;
+                CTRB_COPY(d[p][0], idx + b0 * T, (size_t)nb * T * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+                CTRB_COPY(d[p][1], theta + b0 * T, (size_t)nb * T * sizeof(double), cudaMemcpyHostToDevice, s);
+                return (int)CTRB_OK;
+            },
+            [&](int64_t, int64_t nb, int p) -> int {
+                return launch_eval_fused(ctx, m, env, cd, nb, (const int32_t*)d[p][0], (const double*)d[p][1], rad,
+                                         (double*)d[p][2], (double*)d[p][3], cost ? (double*)d[p][4] : nullptr,
+                                         collide ? (uint8_t*)d[p][5] : nullptr);
+            },
+            [&](int64_t b0, int64_t nb, int p, cudaStream_t s) -> int {
+                CTRB_COPY(obstacle_min + b0, d[p][2], (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, s);
+                CTRB_COPY(goal_dist + b0, d[p][3], (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, s);
+                if (cost) CTRB_COPY(cost + b0, d[p][4], (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, s);
+                if (collide) CTRB_COPY(collide + b0, d[p][5], (size_t)nb, cudaMemcpyDeviceToHost, s);
+                return (int)CTRB_OK;
+            });
+    }
+    {
+        int rc = check_idx_host(m, B, idx);
+        if (rc) return rc;
     }
     Stage st(ctx);
     const int32_t* di = st.in(idx, n, mem);
@@ -662,14 +767,6 @@ int ctrb_static_initial_guess(const ctrb_model* m, double* x0) {
     return CTRB_OK;
 }
 
-static int check_idx_host(const ctrb_model* m, int64_t B, const int32_t* idx) {
-    const size_t n = (size_t)B * m->mc.T;
-    for (size_t i = 0; i < n; ++i) {
-        int t = (int)(i % m->mc.T);
-        CTRB_REQUIRE(idx[i] >= 0 && idx[i] < m->mc.npts[t], "idx[%zu]=%d outside [0,%d)", i, idx[i], m->mc.npts[t]);
-    }
-    return CTRB_OK;
-}
 
 int ctrb_static_residual_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx, const double* theta,
                                const double* q, double* F, int mem) {
@@ -747,6 +844,9 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
     CTRB_REQUIRE(idx && theta && rad && obstacle_min && goal_dist, "NULL buffer");
     const int T = m->mc.T;
     const size_t n = (size_t)B * T;
+    // (no chunk pipeline here: the solve is ~200 ns per configuration against ~1 ns of copies, and launches over
+    // fewer configurations lose more to the tails of the fast / QR / curves / collision kernels than the overlap gains;
+    // measured 3.2 M instead of 4.7 M configs/s end to end with eight chunks)
     if (mem == CTRB_MEM_HOST) {
         int rc = check_idx_host(m, B, idx);
         if (rc) return rc;

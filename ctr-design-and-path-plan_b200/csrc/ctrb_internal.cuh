@@ -77,12 +77,13 @@ struct ctrb_ctx {
     cudaStream_t own_stream;
     cudaStream_t stream2;  // second stream for host-memory chunk pipelining
     cudaEvent_t ev[2];
-    cudaEvent_t ev_chunk[2];
+    cudaEvent_t ev_chunk[2];  // host-memory pipeline: chunk inputs have landed (recorded on stream2)
+    cudaEvent_t ev_done[2];   //                       chunk kernels have finished (recorded on stream)
     cudaEvent_t kev[5][2];  // per-kernel start/stop of the most recent launch (ctrb_kernel_id)
     int64_t launches;
     // grow-only device scratch
-    void* scratch[16];
-    size_t scratch_bytes[16];
+    void* scratch[32];        // [1..8] Stage buffers, [9..15] per-call scratch, [17..24] second set of Stage buffers
+    size_t scratch_bytes[32];
     unsigned long long* d_counters;  // [16]: [0..7] collision work counters + ticket, [8..10] static-solve tickets + fallback count
     int sm_count;
 };

@@ -257,3 +257,26 @@ def test_model_larger_than_the_node_pool_takes_the_one_warp_kernel():
     obs, goal, cost, coll = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
     o_obs, o_goal, _ = oenv.eval_batch(om, idx, theta, RAD3, 3.0)
     _compare(obs, goal, o_obs, o_goal)
+
+
+def test_host_memory_pipeline_equals_single_shot():
+    """Host-memory calls on >= 2^19 configurations run as a chunked copy / compute pipeline (two device buffer sets,
+    two streams): the results are those of the same configurations evaluated in pieces small enough to go in one
+    shot; a bad index in a late chunk is still a ValueError and leaves the context usable."""
+    from ctrdapp_b200.collision import CollisionChecker
+    m = gpu_model("c3_three_tube")
+    cc = CollisionChecker(FIXTURES / "env_c3_colon_straight.json")
+    rng = np.random.default_rng(77)
+    B = 600_017                              # 5 chunks of 131 072 (the last one ragged)
+    idx, theta = random_configs(m.num_discrete_points, B, rng, 1, 8)
+    whole = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
+    cut = [0, 200_000, 400_000, B]
+    parts = [cc.evaluate_batch(m, idx[a:b], theta[a:b], RAD3, goal_weight=3.0) for a, b in zip(cut[:-1], cut[1:])]
+    for k in range(4):
+        np.testing.assert_array_equal(whole[k], np.concatenate([p[k] for p in parts]))
+    bad = idx.copy()
+    bad[B - 5, 2] = 100                      # npts[2] = 100: out of range, last chunk
+    with pytest.raises(ValueError):
+        cc.evaluate_batch(m, bad, theta, RAD3, goal_weight=3.0)
+    again = cc.evaluate_batch(m, idx[:1000], theta[:1000], RAD3, goal_weight=3.0)
+    np.testing.assert_array_equal(again[0], whole[0][:1000])

@@ -179,3 +179,4 @@ def test_static_fused_eval():
             assert cost[b] == pytest.approx(3.0 * max(o_goal, 0.0) + 1.0 / o_obs ** 2, rel=1e-9)
         checked += 1
     assert checked > 100
+
