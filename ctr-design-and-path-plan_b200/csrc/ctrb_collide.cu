@@ -531,6 +531,124 @@ constexpr int kGroupMin = CTRB_GROUP_MIN;   // fewer configurations than this in
 #define CTRB_GROUP_REPS 8
 #endif
 
+// ---- long cylinders.  Non-physical equilibria of the static model (one-step sections) put up to tens
+// of metres between two consecutive nodes.  A ball about the centre of such a cylinder covers the whole mesh: every
+// triangle became a candidate pair and 0.9 % of a static batch took as long as the other 99.1 %.  Cylinders with a
+// half-length above kLongHalf are therefore set aside during the group's walk and handled afterwards, when the
+// configuration's bound is known, by their AXIS: the axis is clipped to the mesh's bounding box grown by bound + r (points
+// beyond it cannot beat the bound), boxes are culled by a slab test against the grown box, and the prefilter is the
+// fp32 segment-triangle distance d: d - r <= d(cylinder, triangle) <= d.  The decisive test stays the exact fp64 one on
+// the whole cylinder.
+constexpr float kLongHalf = 1.5f;
+constexpr int kLongMax = 32;  // long cylinders set aside per group; any beyond that go the ordinary (slow) way
+
+// does the segment c +- h a pass through the box [lo - grow, hi + grow]?  (slab test, fp32, conservative through `grow`)
+__device__ __forceinline__ bool axis_hits_box(const float lo[3], const float hi[3], f3 c, f3 a, float h, float grow) {
+    const float o[3] = {c.x - h * a.x, c.y - h * a.y, c.z - h * a.z};
+    const float d[3] = {2.f * h * a.x, 2.f * h * a.y, 2.f * h * a.z};
+    float tmin = 0.f, tmax = 1.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float dk = copysignf(fmaxf(fabsf(d[k]), 1e-20f), d[k]);
+        const float inv = 1.f / dk;
+        const float t0 = (lo[k] - grow - o[k]) * inv, t1 = (hi[k] + grow - o[k]) * inv;
+        tmin = fmaxf(tmin, fminf(t0, t1));
+        tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    return tmin <= tmax * 1.00001f + 1e-6f;
+}
+
+// squared distance between segments p1 + s d1 (s in [0,1]) and p2..q2; *s_out = the parameter on the first one
+__device__ __forceinline__ float seg_seg_dist2_f(f3 p1, f3 d1, f3 p2, f3 q2, float* s_out) {
+    const f3 d2 = q2 - p2, r = p1 - p2;
+    const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r);
+    float s = 0.f, t = 0.f;
+    if (a > 1e-20f && e > 1e-20f) {
+        const float b = dot(d1, d2), den = a * e - b * b;
+        s = den > 0.f ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
+        t = (b * s + f) / e;
+        if (t < 0.f) {
+            t = 0.f;
+            s = fminf(fmaxf(-c / a, 0.f), 1.f);
+        } else if (t > 1.f) {
+            t = 1.f;
+            s = fminf(fmaxf((b - c) / a, 0.f), 1.f);
+        }
+    } else if (a > 1e-20f) {
+        s = fminf(fmaxf(-c / a, 0.f), 1.f);
+    } else if (e > 1e-20f) {
+        t = fminf(fmaxf(f / e, 0.f), 1.f);
+    }
+    const f3 w = {r.x + s * d1.x - t * d2.x, r.y + s * d1.y - t * d2.y, r.z + s * d1.z - t * d2.z};
+    *s_out = s;
+    return dot(w, w);
+}
+
+// fp32 distance between the segment c +- h a and triangle (v0, v1, v2), everything taken relative to c;
+// *s_out = where on the segment (0 .. 1) the closest point lies
+__device__ __noinline__ float seg_tri_dist_f(f3 c, f3 a, float h, f3 v0, f3 v1, f3 v2, float* s_out) {
+    const f3 A = v0 - c, B = v1 - c, C = v2 - c;
+    const f3 p = {-h * a.x, -h * a.y, -h * a.z}, q = {h * a.x, h * a.y, h * a.z};
+    const f3 d = {2.f * h * a.x, 2.f * h * a.y, 2.f * h * a.z};
+    float s = 0.f, sb;
+    float best = point_tri_dist2<f3, float>(p, A, B, C);
+    float t = point_tri_dist2<f3, float>(q, A, B, C);
+    if (t < best) { best = t; s = 1.f; }
+    t = seg_seg_dist2_f(p, d, A, B, &sb);
+    if (t < best) { best = t; s = sb; }
+    t = seg_seg_dist2_f(p, d, B, C, &sb);
+    if (t < best) { best = t; s = sb; }
+    t = seg_seg_dist2_f(p, d, C, A, &sb);
+    if (t < best) { best = t; s = sb; }
+    // the segment may pierce the triangle
+    const f3 ab = B - A, ac = C - A;
+    const f3 n = {ab.y * ac.z - ab.z * ac.y, ab.z * ac.x - ab.x * ac.z, ab.x * ac.y - ab.y * ac.x};
+    const float dp = dot(n, p - A), dq = dot(n, q - A);
+    if ((dp < 0.f) != (dq < 0.f) && dp != dq) {
+        const float u = dp / (dp - dq);
+        const f3 x = {p.x + u * d.x, p.y + u * d.y, p.z + u * d.z};
+        if (point_tri_dist2<f3, float>(x, A, B, C) <= 1e-12f * fmaxf(dot(x, x), 1.f)) {
+            best = 0.f;
+            s = u;
+        }
+    }
+    *s_out = s;
+    return sqrtf(best);
+}
+
+struct LongItem {
+    f3 c, a;       // clipped axis segment: centre, unit direction
+    float h, r;    // its half-length; the cylinder's radius
+    int active;
+};
+// Clip the axis of cylinder (c, a, h) to the mesh's bounding box grown by `grow` (fp64: the cylinder may be kilometres
+// long).  Points of the axis outside that box are farther than `grow` from every triangle.
+__device__ __noinline__ LongItem clip_long(const DevBvh& bvh, d3 c, d3 a, double h, double r, double grow) {
+    LongItem L;
+    L.active = 0;
+    L.r = (float)r;
+    const BvhNode root = bvh.nodes[0];
+    double t0 = -h, t1 = h;
+    const double cc[3] = {c.x, c.y, c.z}, aa[3] = {a.x, a.y, a.z};
+    for (int k = 0; k < 3; ++k) {
+        const double lo = (double)fminf(root.lo0[k], root.lo1[k]) - grow, hi = (double)fmaxf(root.hi0[k], root.hi1[k]) + grow;
+        if (fabs(aa[k]) < 1e-300) {
+            if (cc[k] < lo || cc[k] > hi) return L;
+        } else {
+            const double u0 = (lo - cc[k]) / aa[k], u1 = (hi - cc[k]) / aa[k];
+            t0 = fmax(t0, fmin(u0, u1));
+            t1 = fmin(t1, fmax(u0, u1));
+        }
+    }
+    if (!(t0 <= t1)) return L;
+    const double mid = 0.5 * (t0 + t1);
+    L.c = f3{(float)(c.x + mid * a.x), (float)(c.y + mid * a.y), (float)(c.z + mid * a.z)};
+    L.a = f3{(float)a.x, (float)a.y, (float)a.z};
+    L.h = (float)(0.5 * (t1 - t0)) * 1.000001f + 1e-6f;
+    L.active = 1;
+    return L;
+}
+
 struct GroupMem {
     double* pos;                     // [pool][3]  (behind the GroupMem array in dynamic shared memory)
     unsigned int* items;             // [pool]     node (10 bits) | slot (5 bits) << 10 | tube (2 bits) << 15
@@ -541,8 +659,11 @@ struct GroupMem {
     unsigned int q_item[kGQueue];
     float q_lb[kGQueue];
     int stack[kGStack][32];          // [entry][lane]: conflict-free
+    unsigned int long_items[kLongMax];  // long cylinders set aside during the walk
+    int nlong;
     int ticket;
     int qcount;
+    int pad_;
 };
 
 template <bool FUSED>
@@ -756,6 +877,7 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
             if (lane == 0) {
                 W.ticket = 0;
                 W.qcount = 0;
+                W.nlong = 0;
             }
             __syncwarp();
             // ---- lane = work item
@@ -802,6 +924,13 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                                 record(slot, cylinder_vs_prim(env.prims[k], c, a, h, r,
                                                               __longlong_as_double((long long)W.best_bits[slot])));
                             if (bvh.ntri > 0 && !vcoll[slot]) {
+                                if (h > (double)kLongHalf) {  // set aside: handled by its axis once the bounds are known
+                                    const int kl = atomicAdd(&W.nlong, 1);
+                                    if (kl < kLongMax) {
+                                        W.long_items[kl] = code;
+                                        continue;
+                                    }
+                                }
                                 cf = f3{(float)c.x, (float)c.y, (float)c.z};
                                 af = f3{(float)a.x, (float)a.y, (float)a.z};
                                 hf = (float)h;
@@ -876,6 +1005,107 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                                 } else {
                                     exact_pair(code, t, bound);  // queue full: decide here (rare)
                                 }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (__shfl_sync(0xffffffffu, *(volatile int*)&W.qcount, 0) >= 32) drain();
+                }
+                drain();
+            }
+            __syncwarp();
+            // ---- the long cylinders that were set aside: lane = cylinder
+            const int nl = min(__shfl_sync(0xffffffffu, *(volatile int*)&W.nlong, 0), kLongMax);
+            if (nl > 0) {
+                unsigned code = 0;
+                int slot = 0, sp = 0;
+                LongItem li;
+                li.active = 0;
+                li.h = 0.f;
+                li.r = 0.f;
+                li.c = li.a = f3{0.f, 0.f, 0.f};
+                if (lane < nl) {
+                    code = W.long_items[lane];
+                    slot = (code >> 10) & 31u;
+                    if (!vcoll[slot]) {
+                        d3 c, a;
+                        double h, r;
+                        cylinder_of(code, c, a, h, r);
+                        if (__int_as_float(vbound[slot]) > 1e30f) {
+                            // no bound yet: the cylinder's centre to any one vertex of the mesh is an upper bound
+                            const d3 v = {__ldg(bvh.tri64 + 0), __ldg(bvh.tri64 + 1), __ldg(bvh.tri64 + 2)};
+                            const d3 dv = v - c;
+                            atomicMin(&W.bound_bits[slot], __float_as_int(__double2float_ru(sqrt(dot(dv, dv)))));
+                        }
+                        const float bound = __int_as_float(vbound[slot]);
+                        li = clip_long(bvh, c, a, h, r, (double)bound * 1.000001 + r + 4.0 * (double)slack);
+                        if (li.active) {
+                            stk[0] = 0;
+                            sp = 1;
+                        }
+                    }
+                }
+                const float lslack = slack * 4.f + li.h * 4e-6f;  // fp32 error of a point far out on the clipped axis
+                // The tree is walked with a tube about the axis that starts thin (2 r) and is widened fourfold, from the
+                // root again, until it reaches bound + r: the boxes the axis itself runs through come first, so a
+                // cylinder that pierces the wall finds its contact in the first pass, and one that does not has a tight
+                // bound (from the triangles next to it) before the wide passes.
+                float gcap = 2.f * li.r;
+                for (;;) {
+                    if (sp == 0 && li.active) {
+                        if (!vcoll[slot] && gcap < __int_as_float(vbound[slot]) + li.r) {
+                            gcap *= 4.f;
+                            stk[0] = 0;
+                            sp = 1;
+                        } else {
+                            li.active = 0;
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, sp > 0)) break;
+#pragma unroll 1
+                    for (int rep = 0; rep < 8 && sp > 0; ++rep) {
+                        if (vcoll[slot]) {
+                            sp = 0;
+                            break;
+                        }
+                        const int e = stk[--sp * 32];
+                        if (e >= 0) {
+                            const BvhNode nd = load_node(bvh, nullptr, 0, e);
+                            wk.nodes++;
+                            const float grow = fminf(__int_as_float(vbound[slot]) + li.r, gcap) * 1.00001f + lslack;
+                            if (axis_hits_box(nd.lo1, nd.hi1, li.c, li.a, li.h, grow) && sp < kGStack) stk[sp++ * 32] = nd.c1;
+                            if (axis_hits_box(nd.lo0, nd.hi0, li.c, li.a, li.h, grow) && sp < kGStack) stk[sp++ * 32] = nd.c0;
+                            continue;
+                        }
+                        const int lc = ~e;
+                        const int tfirst = lc >> 3, tcnt = (lc & 7) + 1;
+#pragma unroll 1
+                        for (int t = tfirst; t < tfirst + tcnt && !vcoll[slot]; ++t) {
+                            const float4* tp = bvh.tri32 + (size_t)t * 3;
+                            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                            float sq;
+                            const float dst = seg_tri_dist_f(li.c, li.a, li.h, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z},
+                                                             f3{v2.x, v2.y, v2.z}, &sq);
+                            wk.pre++;
+                            // a triangle point within r of an interior point of the axis is inside the solid cylinder
+                            if (dst + lslack < li.r && sq > 0.001f && sq < 0.999f) {
+                                vcoll[slot] = 1;
+                                sp = 0;
+                                break;
+                            }
+                            // the axis belongs to the cylinder: d(cyl, tri) <= d(axis, tri); and the cylinder lies inside
+                            // the capsule of radius r about its axis: d(cyl, tri) >= d(axis, tri) - r
+                            atomicMin(&W.bound_bits[slot], __float_as_int(dst + lslack));
+                            const float bound = __int_as_float(vbound[slot]);
+                            const float lb = dst - li.r - lslack;
+                            if (lb > bound) continue;
+                            const int qs = atomicAdd(&W.qcount, 1);
+                            if (qs < kGQueue) {
+                                W.q_tri[qs] = t;
+                                W.q_item[qs] = code;
+                                W.q_lb[qs] = lb;
+                            } else {
+                                exact_pair(code, t, bound);
                             }
                         }
                     }

@@ -280,3 +280,41 @@ def test_host_memory_pipeline_equals_single_shot():
         cc.evaluate_batch(m, bad, theta, RAD3, goal_weight=3.0)
     again = cc.evaluate_batch(m, idx[:1000], theta[:1000], RAD3, goal_weight=3.0)
     np.testing.assert_array_equal(again[0], whole[0][:1000])
+
+
+def test_long_cylinders_vs_oracle():
+    """Curves with very long segments (the static model's one-step sections produce them: metres between two nodes).
+    The grouped kernel sets such cylinders aside and culls them by their axis (clip to the mesh box, slab test,
+    segment-triangle prefilter); the answer must stay the exact one: piercing, grazing, free and far-away cases."""
+    from oracle import oracle as orc
+    from ctrdapp_b200.collision import CollisionChecker
+    rng = np.random.default_rng(5)
+    for env_name in ("env_c3_colon_straight.json", "env_colon_angled.json", "env_boxes_multi.json"):
+        cc = CollisionChecker(FIXTURES / env_name)
+        oenv = orc.Env.from_json(FIXTURES / env_name)
+        curves, flat, off = [], [], [0]
+        for b in range(160):
+            n_nodes = int(rng.integers(2, 7))
+            p = rng.uniform(-1.0, 1.0, 3)
+            nodes = [se3(p)]
+            for k in range(n_nodes - 1):
+                d = rng.normal(size=3)
+                d /= np.linalg.norm(d)
+                step = rng.choice([1.0, 2.5, 4.0, 9.0, 30.0, 150.0, 4000.0, 3.0e6])
+                if b % 4 == 0:
+                    step = 1.0 if k else rng.choice([6.0, 12.0])      # short-ish, mostly free inside the lumen
+                p = p + step * d
+                nodes.append(se3(p))
+            curves.append([nodes])
+            flat.extend(nodes)
+            off.append(off[-1] + n_nodes)
+        g = np.ascontiguousarray(np.stack(flat))
+        obs, goal = cc.check_collision_batch(g, np.asarray(off, np.int64), [0.8])
+        o = np.array([oenv.check_collision(c, [0.8]) for c in curves])
+        # distances to far-away geometry: relative 1e-9 instead of the absolute micrometre band
+        bit, o_bit = obs < 0, o[:, 0] < 0
+        band = (np.abs(o[:, 0]) < BAND) & (o[:, 0] > 0)
+        assert np.array_equal(bit[~band], o_bit[~band]), env_name
+        free = ~bit & ~o_bit
+        assert free.sum() >= 10 and (bit.sum() >= 3 or "boxes" in env_name), (env_name, free.sum(), bit.sum())
+        assert np.all(np.abs(obs[free] - o[free, 0]) <= np.maximum(BAND, 1e-9 * o[free, 0])), env_name
