@@ -47,7 +47,8 @@ BYTES_PER_CONFIG = 3 * (4 + 8) + (8 + 8 + 8 + 1)  # idx + theta in, obstacle_min
 # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (30000 C3 shallow configurations,
 # profiles/r1_ncu_final_four_kernels.json) divided by the configurations each kernel handled (22942 / 7058 / 30000);
 # the curves kernel's writes were still partly in the 126 MB L2 when the capture ended
-NCU_DRAM_BYTES_PER_CONFIG = {"static_fast_kernel": 51.0, "static_solve_kernel": 153.0, "static_curves_kernel": 853.0}
+NCU_DRAM_BYTES_PER_CONFIG = {"static_fast_kernel": 51.0, "static_solve_kernel": 154.0, "static_curves_kernel": 887.0,
+                             "chain_eval_group_kernel<true>": 72.5}
 
 
 def make_inputs(B, seed, lo, hi):
@@ -350,7 +351,9 @@ def main():
     else:
         achieved = BYTES_PER_CONFIG * B / (k_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "chain_eval_kernel<true>", "kernel_ms": k_ms,
+                    "traffic": NCU_DRAM_BYTES_PER_CONFIG["chain_eval_group_kernel<true>"] * B,
+                    "traffic_source": "profiles/r1_ncu_final_four_kernels.json (200000 configurations), per configuration x launch size",
+                    "kernel": "chain_eval_group_kernel<true>", "kernel_ms": k_ms,
                     "algorithmic_bytes_per_config": BYTES_PER_CONFIG, "peak_source": peak_src,
                     "note": "latency/compute-bound tree traversal: HBM traffic is ~61 B/config by construction; "
                             "see compute_roofline for the binding resource"}
@@ -454,7 +457,9 @@ def main():
                        "parallelism": f"dp{world} (configs sharded, best node gathered over NCCL)" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": B * 3 * 12, "d2h_bytes_per_step": B * 25,
-                    "steps": n_e2e, "path": "ctrb_eval_batch(CTRB_MEM_HOST) on pinned numpy buffers"},
+                    "steps": n_e2e,
+                    "path": ("ctrb_static_eval_batch" if kind == "static" else "ctrb_eval_batch (chunked copy/compute pipeline)")
+                            + "(CTRB_MEM_HOST) on pinned numpy buffers, best node read on the host"},
             "gpu_launches": int(launches), "roofline": roofline, "compute_roofline": compute,
             "best_node": {"cost": best[0], "index": best[1]}, "bvh": cc.stats()}
     if cpu:

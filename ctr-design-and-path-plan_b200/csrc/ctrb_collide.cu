@@ -1,18 +1,21 @@
 // ctrb_collide.cu -- tube-vs-environment distance / collision and the fused
-// g-curve + collision + cost kernel (sm_100a).
+// g-curve + collision + cost kernels (sm_100a).
 //
 // Replaces CollisionChecker.check_collision (collision_checker.py:35-95) and, in the fused
 // variant, the solve_g -> check_collision -> heuristic chain of rrt.py:110-129.
 //
-// One warp per configuration.  The warp first lays the configuration's node positions into
-// shared memory (fused: p_j = A_n C_n[j].p straight from the model table -- the g-curve
-// never touches HBM).  Every pair of consecutive nodes is a solid flat-capped cylinder
-// (collision_checker.py:121-147); lanes pull cylinders from a warp-local ticket and walk
-// a BVH over the triangle soup with a private stack.  All lanes of the warp share one
-// upper bound on the configuration's minimum distance (shared-memory atomicMin on the
-// float bits), so a cylinder far from the wall prunes against the distance another lane
-// already found, and one contact flag that ends the whole query (python-fcl's
-// defaultDistanceCallback stops at the first contact).
+// Every pair of consecutive nodes is a solid flat-capped cylinder (collision_checker.py:121-147).
+// Two schedules of the same exact query:
+//   chain_eval_group_kernel  a warp takes a group of configurations (lane = configuration for the
+//                            positions and results, lane = cylinder for the BVH walks); the default
+//   chain_eval_kernel        one warp per configuration; for configurations that do not fit the
+//                            grouped kernel's node pool / stack, and as its cross-check
+// In both, lanes walk a BVH over the triangle soup for one cylinder at a time and share, per
+// configuration, one upper bound on the minimum distance (shared-memory atomicMin on the float
+// bits) and one contact flag that ends the whole query (python-fcl's defaultDistanceCallback
+// stops at the first contact); surviving (cylinder, triangle) pairs are queued and decided by the
+// warp in lock-step.  In the fused variants p_j = A_n C_n[j].p comes straight from the model
+// table: the g-curve never touches HBM.
 //
 // Culling is fp32 (boxes rounded outward, `slack` absorbs every fp32 rounding), the
 // decisive cylinder<->triangle distance is fp64 and exact (ctrb_geom.cuh).  No tensor
