@@ -902,6 +902,7 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                 bool exhausted = false;
                 f3 cf = {0.f, 0.f, 0.f}, af = {0.f, 0.f, 0.f};
                 float rb = 0.f, hf = 0.f, rf = 0.f;
+                float slk = slack;  // `slack` is sized for the mesh's coordinates; a cylinder far outside them needs its own
                 for (;;) {
                     if (sp == 0 && !exhausted) {  // next live cylinder for this lane
 #pragma unroll 1
@@ -939,6 +940,7 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                                 hf = (float)h;
                                 rf = (float)r;
                                 rb = __fsqrt_ru(__fmaf_ru(hf, hf, rf * rf)) * 1.000001f;
+                                slk = fmaxf(slack, 1.6e-5f * fmaxf(fmaxf(fabsf(cf.x), fabsf(cf.y)), fabsf(cf.z)));  // 64 ulp of 2 |c|
                                 stk[0] = 0;
                                 sp = 1;
                                 break;
@@ -963,7 +965,7 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                             } else {
                                 const BvhNode nd = load_node(bvh, nullptr, 0, e);
                                 wk.nodes++;
-                                const float reach = __int_as_float(vbound[slot]) + rb + slack;
+                                const float reach = __int_as_float(vbound[slot]) + rb + slk;
                                 const float reach2 = reach * reach * 1.000001f;
                                 float d0 = aabb_dist2(nd.lo0, nd.hi0, cf);
                                 float d1 = aabb_dist2(nd.lo1, nd.hi1, cf);
@@ -989,16 +991,16 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                                 const float dpt2 = dot(w, w), tq = dot(w, af);
                                 const float dpt = sqrtf(dpt2), rho = sqrtf(fmaxf(dpt2 - tq * tq, 0.f));
                                 const float et = fabsf(tq) - hf, er = rho - rf;
-                                if (et + slack < 0.f && er + slack < 0.f) {  // q is inside the solid cylinder for certain
+                                if (et + slk < 0.f && er + slk < 0.f) {  // q is inside the solid cylinder for certain
                                     vcoll[slot] = 1;
                                     sp = 0;
                                     break;
                                 }
                                 // q belongs to the triangle: d(cyl, tri) <= d(q, cyl)
                                 const float dt_ = fmaxf(et, 0.f), dr_ = fmaxf(er, 0.f);
-                                atomicMin(&W.bound_bits[slot], __float_as_int(sqrtf(fmaf(dt_, dt_, dr_ * dr_)) + slack));
+                                atomicMin(&W.bound_bits[slot], __float_as_int(sqrtf(fmaf(dt_, dt_, dr_ * dr_)) + slk));
                                 const float bound = __int_as_float(vbound[slot]);
-                                const float lb = dpt - rb - slack;  // d(cyl, tri) >= dpt - rb
+                                const float lb = dpt - rb - slk;  // d(cyl, tri) >= dpt - rb
                                 if (lb > bound) continue;
                                 const int qs = atomicAdd(&W.qcount, 1);
                                 if (qs < kGQueue) {
@@ -1048,7 +1050,8 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                         }
                     }
                 }
-                const float lslack = slack * 4.f + li.h * 4e-6f;  // fp32 error of a point far out on the clipped axis
+                const float lslack = fmaxf(slack, 1.6e-5f * fmaxf(fmaxf(fabsf(li.c.x), fabsf(li.c.y)), fabsf(li.c.z))) * 4.f +
+                                     li.h * 4e-6f;  // fp32 error of a point far out on the clipped axis
                 // The tree is walked with a tube about the axis that starts thin (2 r) and is widened fourfold, from the
                 // root again, until it reaches bound + r: the boxes the axis itself runs through come first, so a
                 // cylinder that pierces the wall finds its contact in the first pass, and one that does not has a tight
