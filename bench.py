@@ -279,6 +279,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = world * B / (ms_per_step * 1e-3)
+    per_rank = None
+    if world > 1:  # every rank's own step time, dominant-kernel time and SM clock: shows which GPU sets the maximum
+        mine = torch.tensor([ms_total / args.steps, float(np.mean(kern_ms)), float(clocks.get("sm_mhz") or 0.0)],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(a[0]), 2) for a in allr], "dominant_kernel_ms": [round(float(a[1]), 2) for a in allr],
+                    "sm_mhz": [float(a[2]) for a in allr]}
     work = ctx.work_counters()
     collide_frac = float((obs_d < 0).double().mean().item())
 
@@ -462,6 +470,8 @@ def main():
                             + "(CTRB_MEM_HOST) on pinned numpy buffers, best node read on the host"},
             "gpu_launches": int(launches), "roofline": roofline, "compute_roofline": compute,
             "best_node": {"cost": best[0], "index": best[1]}, "bvh": cc.stats()}
+    if per_rank:
+        line["per_rank"] = per_rank
     if cpu:
         line["cpu_baseline"] = cpu
     if extra:

@@ -543,6 +543,8 @@ constexpr int kGroupMin = CTRB_GROUP_MIN;   // fewer configurations than this in
 // fp32 segment-triangle distance d: d - r <= d(cylinder, triangle) <= d.  The decisive test stays the exact fp64 one on
 // the whole cylinder.
 constexpr float kLongHalf = 1.5f;
+constexpr float kFarHalf = 25.f;  // ... and above this one they also get a first look BEFORE the other cylinders
+constexpr unsigned int kLongFlag = 0x80000000u;  // item code bit: this cylinder is in the long list
 constexpr int kLongMax = 32;  // long cylinders set aside per group; any beyond that go the ordinary (slow) way
 
 // does the segment c +- h a pass through the box [lo - grow, hi + grow]?  (slab test, fp32, conservative through `grow`)
@@ -883,6 +885,133 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                 W.nlong = 0;
             }
             __syncwarp();
+            // ---- long cylinders are taken out of the item list
+            if (have_obstacles && bvh.ntri > 0) {
+                for (int i = lane; i < total_items; i += 32) {
+                    const unsigned code = W.items[i];
+                    const double* pf = W.pos + (size_t)(code & 1023u) * 3;
+                    const double dx = pf[3] - pf[0], dy = pf[4] - pf[1], dz = pf[5] - pf[2];
+                    if (fma(dx, dx, fma(dy, dy, dz * dz)) > 4.0 * (double)kLongHalf * (double)kLongHalf) {
+                        const int kl = atomicAdd(&W.nlong, 1);
+                        if (kl < kLongMax) {  // (any beyond that stay in the list and go the ordinary way)
+                            W.long_items[kl] = code;
+                            W.items[i] = code | kLongFlag;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            const int nl = min(__shfl_sync(0xffffffffu, *(volatile int*)&W.nlong, 0), kLongMax);
+            // phase 0: the long cylinders with a thin tube about their axis only (does it pierce the wall? what is near
+            //          it?) -- a contact ends the configuration before anything else is walked, and otherwise the
+            //          configuration has a finite bound before its far-away cylinders are looked at;
+            //          then the walk of all ordinary cylinders;
+            // phase 1: the long cylinders again, tube widened up to the (now tight) bound.
+#pragma unroll 1
+            for (int phase = 0; phase < 2; ++phase) {
+            if (nl > 0) {
+                unsigned code = 0;
+                int slot = 0, sp = 0;
+                LongItem li;
+                li.active = 0;
+                li.h = 0.f;
+                li.r = 0.f;
+                li.c = li.a = f3{0.f, 0.f, 0.f};
+                if (lane < nl) {
+                    code = W.long_items[lane];
+                    slot = (code >> 10) & 31u;
+                    if (!vcoll[slot]) {
+                        d3 c, a;
+                        double h, r;
+                        cylinder_of(code, c, a, h, r);
+                        // phase 0 is for the cylinders long enough to carry the rest of the chain out of the scene
+                        if (phase == 0 && h < (double)kFarHalf) h = -1.0;
+                        if (h > 0.0 && __int_as_float(vbound[slot]) > 1e30f) {
+                            // no bound yet: the cylinder's centre to any one vertex of the mesh is an upper bound
+                            const d3 v = {__ldg(bvh.tri64 + 0), __ldg(bvh.tri64 + 1), __ldg(bvh.tri64 + 2)};
+                            const d3 dv = v - c;
+                            atomicMin(&W.bound_bits[slot], __float_as_int(__double2float_ru(sqrt(dot(dv, dv)))));
+                        }
+                        // phase 0 looks no farther than 32 r from the axis (tubes of 2 r, 8 r, 32 r); phase 1 as far as the bound requires
+                        const double reach = phase == 0 ? 32.0 * r : (double)__int_as_float(vbound[slot]) * 1.000001 + r;
+                        if (h > 0.0) li = clip_long(bvh, c, a, h, r, reach + 4.0 * (double)slack);
+                        if (li.active) {
+                            stk[0] = 0;
+                            sp = 1;
+                        }
+                    }
+                }
+                const float lslack = fmaxf(slack, 1.6e-5f * fmaxf(fmaxf(fabsf(li.c.x), fabsf(li.c.y)), fabsf(li.c.z))) * 4.f +
+                                     li.h * 4e-6f;  // fp32 error of a point far out on the clipped axis
+                // The tree is walked with a tube about the axis that starts thin (2 r) and is widened fourfold, from the
+                // root again, until it reaches bound + r: the boxes the axis itself runs through come first, so a
+                // cylinder that pierces the wall finds its contact in the first pass, and one that does not has a tight
+                // bound (from the triangles next to it) before the wide passes.
+                float gcap = 2.f * li.r;
+                for (;;) {
+                    if (sp == 0 && li.active) {
+                        if (!vcoll[slot] && gcap < __int_as_float(vbound[slot]) + li.r && (phase == 1 || gcap < 32.f * li.r)) {
+                            gcap *= 4.f;
+                            stk[0] = 0;
+                            sp = 1;
+                        } else {
+                            li.active = 0;
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, sp > 0)) break;
+#pragma unroll 1
+                    for (int rep = 0; rep < 8 && sp > 0; ++rep) {
+                        if (vcoll[slot]) {
+                            sp = 0;
+                            break;
+                        }
+                        const int e = stk[--sp * 32];
+                        if (e >= 0) {
+                            const BvhNode nd = load_node(bvh, nullptr, 0, e);
+                            wk.nodes++;
+                            const float grow = fminf(__int_as_float(vbound[slot]) + li.r, gcap) * 1.00001f + lslack;
+                            if (axis_hits_box(nd.lo1, nd.hi1, li.c, li.a, li.h, grow) && sp < kGStack) stk[sp++ * 32] = nd.c1;
+                            if (axis_hits_box(nd.lo0, nd.hi0, li.c, li.a, li.h, grow) && sp < kGStack) stk[sp++ * 32] = nd.c0;
+                            continue;
+                        }
+                        const int lc = ~e;
+                        const int tfirst = lc >> 3, tcnt = (lc & 7) + 1;
+#pragma unroll 1
+                        for (int t = tfirst; t < tfirst + tcnt && !vcoll[slot]; ++t) {
+                            const float4* tp = bvh.tri32 + (size_t)t * 3;
+                            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+                            float sq;
+                            const float dst = seg_tri_dist_f(li.c, li.a, li.h, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z},
+                                                             f3{v2.x, v2.y, v2.z}, &sq);
+                            wk.pre++;
+                            // a triangle point within r of an interior point of the axis is inside the solid cylinder
+                            if (dst + lslack < li.r && sq > 0.001f && sq < 0.999f) {
+                                vcoll[slot] = 1;
+                                sp = 0;
+                                break;
+                            }
+                            // the axis belongs to the cylinder: d(cyl, tri) <= d(axis, tri); and the cylinder lies inside
+                            // the capsule of radius r about its axis: d(cyl, tri) >= d(axis, tri) - r
+                            atomicMin(&W.bound_bits[slot], __float_as_int(dst + lslack));
+                            const float bound = __int_as_float(vbound[slot]);
+                            const float lb = dst - li.r - lslack;
+                            if (lb > bound) continue;
+                            const int qs = atomicAdd(&W.qcount, 1);
+                            if (qs < kGQueue) {
+                                W.q_tri[qs] = t;
+                                W.q_item[qs] = code;
+                                W.q_lb[qs] = lb;
+                            } else {
+                                exact_pair(code, t, bound);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (__shfl_sync(0xffffffffu, *(volatile int*)&W.qcount, 0) >= 32) drain();
+                }
+                drain();
+            }
+            if (phase == 1) break;
             // ---- lane = work item
             // Many short configurations: one pass over the whole item list.  A few long ones: one pass per configuration,
             // so that a contact ends that configuration's walks at once and the warp moves on together (python-fcl's
@@ -913,6 +1042,7 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                                 break;
                             }
                             code = W.items[q];
+                            if (code & kLongFlag) continue;  // a long cylinder: handled by its axis, before and after this walk
                             slot = (code >> 10) & 31u;
                             if (vcoll[slot]) {
                                 if (m < kGroupMin) {  // this pass is that configuration's alone: nothing left to do
@@ -928,13 +1058,6 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                                 record(slot, cylinder_vs_prim(env.prims[k], c, a, h, r,
                                                               __longlong_as_double((long long)W.best_bits[slot])));
                             if (bvh.ntri > 0 && !vcoll[slot]) {
-                                if (h > (double)kLongHalf) {  // set aside: handled by its axis once the bounds are known
-                                    const int kl = atomicAdd(&W.nlong, 1);
-                                    if (kl < kLongMax) {
-                                        W.long_items[kl] = code;
-                                        continue;
-                                    }
-                                }
                                 cf = f3{(float)c.x, (float)c.y, (float)c.z};
                                 af = f3{(float)a.x, (float)a.y, (float)a.z};
                                 hf = (float)h;
@@ -1019,107 +1142,7 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                 drain();
             }
             __syncwarp();
-            // ---- the long cylinders that were set aside: lane = cylinder
-            const int nl = min(__shfl_sync(0xffffffffu, *(volatile int*)&W.nlong, 0), kLongMax);
-            if (nl > 0) {
-                unsigned code = 0;
-                int slot = 0, sp = 0;
-                LongItem li;
-                li.active = 0;
-                li.h = 0.f;
-                li.r = 0.f;
-                li.c = li.a = f3{0.f, 0.f, 0.f};
-                if (lane < nl) {
-                    code = W.long_items[lane];
-                    slot = (code >> 10) & 31u;
-                    if (!vcoll[slot]) {
-                        d3 c, a;
-                        double h, r;
-                        cylinder_of(code, c, a, h, r);
-                        if (__int_as_float(vbound[slot]) > 1e30f) {
-                            // no bound yet: the cylinder's centre to any one vertex of the mesh is an upper bound
-                            const d3 v = {__ldg(bvh.tri64 + 0), __ldg(bvh.tri64 + 1), __ldg(bvh.tri64 + 2)};
-                            const d3 dv = v - c;
-                            atomicMin(&W.bound_bits[slot], __float_as_int(__double2float_ru(sqrt(dot(dv, dv)))));
-                        }
-                        const float bound = __int_as_float(vbound[slot]);
-                        li = clip_long(bvh, c, a, h, r, (double)bound * 1.000001 + r + 4.0 * (double)slack);
-                        if (li.active) {
-                            stk[0] = 0;
-                            sp = 1;
-                        }
-                    }
-                }
-                const float lslack = fmaxf(slack, 1.6e-5f * fmaxf(fmaxf(fabsf(li.c.x), fabsf(li.c.y)), fabsf(li.c.z))) * 4.f +
-                                     li.h * 4e-6f;  // fp32 error of a point far out on the clipped axis
-                // The tree is walked with a tube about the axis that starts thin (2 r) and is widened fourfold, from the
-                // root again, until it reaches bound + r: the boxes the axis itself runs through come first, so a
-                // cylinder that pierces the wall finds its contact in the first pass, and one that does not has a tight
-                // bound (from the triangles next to it) before the wide passes.
-                float gcap = 2.f * li.r;
-                for (;;) {
-                    if (sp == 0 && li.active) {
-                        if (!vcoll[slot] && gcap < __int_as_float(vbound[slot]) + li.r) {
-                            gcap *= 4.f;
-                            stk[0] = 0;
-                            sp = 1;
-                        } else {
-                            li.active = 0;
-                        }
-                    }
-                    if (!__any_sync(0xffffffffu, sp > 0)) break;
-#pragma unroll 1
-                    for (int rep = 0; rep < 8 && sp > 0; ++rep) {
-                        if (vcoll[slot]) {
-                            sp = 0;
-                            break;
-                        }
-                        const int e = stk[--sp * 32];
-                        if (e >= 0) {
-                            const BvhNode nd = load_node(bvh, nullptr, 0, e);
-                            wk.nodes++;
-                            const float grow = fminf(__int_as_float(vbound[slot]) + li.r, gcap) * 1.00001f + lslack;
-                            if (axis_hits_box(nd.lo1, nd.hi1, li.c, li.a, li.h, grow) && sp < kGStack) stk[sp++ * 32] = nd.c1;
-                            if (axis_hits_box(nd.lo0, nd.hi0, li.c, li.a, li.h, grow) && sp < kGStack) stk[sp++ * 32] = nd.c0;
-                            continue;
-                        }
-                        const int lc = ~e;
-                        const int tfirst = lc >> 3, tcnt = (lc & 7) + 1;
-#pragma unroll 1
-                        for (int t = tfirst; t < tfirst + tcnt && !vcoll[slot]; ++t) {
-                            const float4* tp = bvh.tri32 + (size_t)t * 3;
-                            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-                            float sq;
-                            const float dst = seg_tri_dist_f(li.c, li.a, li.h, f3{v0.x, v0.y, v0.z}, f3{v1.x, v1.y, v1.z},
-                                                             f3{v2.x, v2.y, v2.z}, &sq);
-                            wk.pre++;
-                            // a triangle point within r of an interior point of the axis is inside the solid cylinder
-                            if (dst + lslack < li.r && sq > 0.001f && sq < 0.999f) {
-                                vcoll[slot] = 1;
-                                sp = 0;
-                                break;
-                            }
-                            // the axis belongs to the cylinder: d(cyl, tri) <= d(axis, tri); and the cylinder lies inside
-                            // the capsule of radius r about its axis: d(cyl, tri) >= d(axis, tri) - r
-                            atomicMin(&W.bound_bits[slot], __float_as_int(dst + lslack));
-                            const float bound = __int_as_float(vbound[slot]);
-                            const float lb = dst - li.r - lslack;
-                            if (lb > bound) continue;
-                            const int qs = atomicAdd(&W.qcount, 1);
-                            if (qs < kGQueue) {
-                                W.q_tri[qs] = t;
-                                W.q_item[qs] = code;
-                                W.q_lb[qs] = lb;
-                            } else {
-                                exact_pair(code, t, bound);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (__shfl_sync(0xffffffffu, *(volatile int*)&W.qcount, 0) >= 32) drain();
-                }
-                drain();
-            }
+            }  // phase
             __syncwarp();
             // ---- lane = configuration again: goal distance, cost, results (coalesced across lanes)
             if (mine) {

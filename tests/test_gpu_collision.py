@@ -300,7 +300,7 @@ def test_long_cylinders_vs_oracle():
             for k in range(n_nodes - 1):
                 d = rng.normal(size=3)
                 d /= np.linalg.norm(d)
-                step = rng.choice([1.0, 2.5, 4.0, 9.0, 30.0, 150.0, 4000.0, 3.0e6])
+                step = rng.choice([1.0, 2.5, 4.0, 9.0, 30.0, 150.0, 4000.0, 3.0e6, 1.6e7])  # up to 16 000 km (seen in C3 batches)
                 if b % 4 == 0:
                     step = 1.0 if k else rng.choice([6.0, 12.0])      # short-ish, mostly free inside the lumen
                 p = p + step * d
