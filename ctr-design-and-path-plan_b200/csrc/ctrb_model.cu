@@ -13,6 +13,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "ctrb_se3.cuh"
 
@@ -80,17 +81,23 @@ __global__ void __launch_bounds__(kGWarps * 32)
                       OutT* __restrict__ out, int tab_in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = mc.T, tot = mc.total_nodes;
-    // layout: [A: kGWarps*32*T*12 doubles][start idx: kGWarps*32*T ints][table 12*tot doubles (optional)]
+    // layout: [A: kGWarps*32*T*12 doubles][output offsets: kGWarps*32*T int64][start idx: kGWarps*32*T ints]
+    //         [table (optional): fp64 12*tot doubles | fp32 position rows 3*tot doubles + rotation 9*tot floats]
     double* sA = reinterpret_cast<double*>(smem_raw);
-    int* sIdx = reinterpret_cast<int*>(sA + kGWarps * 32 * T * 12);
+    long long* sOff = reinterpret_cast<long long*>(sA + kGWarps * 32 * T * 12);
+    int* sIdx = reinterpret_cast<int*>(sOff + kGWarps * 32 * T);
     const double* tab = tb.tab;
     const float* tabR = tb.tabR32;
+    const double* tabP = tb.tab + 9 * tot;  // position rows, the only fp64 part the fp32 path reads
     if (tab_in_smem) {
-        double* st = reinterpret_cast<double*>(smem_raw) + kGWarps * 32 * T * 12 + (kGWarps * 32 * T + 1) / 2;
-        for (int i = threadIdx.x; i < 12 * tot; i += blockDim.x) st[i] = tb.tab[i];
-        tab = st;
-        if (sizeof(OutT) == 4) {
-            float* sf = reinterpret_cast<float*>(st + 12 * tot);
+        double* st = reinterpret_cast<double*>(sOff + kGWarps * 32 * T) + (kGWarps * 32 * T + 1) / 2;
+        if (sizeof(OutT) == 8) {
+            for (int i = threadIdx.x; i < 12 * tot; i += blockDim.x) st[i] = tb.tab[i];
+            tab = st;
+        } else {  // the fp32 path reads the position rows (9..11) in fp64 and the rotation rows in fp32
+            for (int i = threadIdx.x; i < 3 * tot; i += blockDim.x) st[i] = tb.tab[9 * tot + i];
+            tabP = st;
+            float* sf = reinterpret_cast<float*>(st + 3 * tot);
             for (int i = threadIdx.x; i < 9 * tot; i += blockDim.x) sf[i] = tb.tabR32[i];
             tabR = sf;
         }
@@ -98,6 +105,7 @@ __global__ void __launch_bounds__(kGWarps * 32)
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* wA = sA + (size_t)warp * 32 * T * 12;
+    long long* wOff = sOff + warp * 32 * T;
     int* wIdx = sIdx + warp * 32 * T;
     const long long ngroups = (B + 31) / 32;
     const int slot = lane >> 2, row = lane & 3;
@@ -123,6 +131,7 @@ __global__ void __launch_bounds__(kGWarps * 32)
                         dst[k * 4 + 3] = a.p[k];
                     }
                     wIdx[lane * T + n] = id;
+                    wOff[lane * T + n] = offsets[b * T + n];
                     g = se3_mul(a, load_tab(tb.tab, tot, mc.node_base[n] + mc.npts[n] - 1));  // tube tip
                 }
             }
@@ -133,12 +142,11 @@ __global__ void __launch_bounds__(kGWarps * 32)
         if (sizeof(OutT) == 8) {
             // fp64: lane = (8 node slots, 4 matrix rows); one 256-bit store per lane, 1 KiB per warp instruction
             for (int c = 0; c < ncfg; ++c) {
-                const long long b = b0 + c;
                 for (int n = 0; n < T; ++n) {
                     const int id = wIdx[c * T + n];
                     const int start = full ? 0 : id;                               // kinematic.py:100-103
                     const int cnt = mc.npts[n] - start;
-                    const long long obase = offsets[b * T + n];
+                    const long long obase = wOff[c * T + n];
                     double a0 = 0, a1 = 0, a2 = 0, ap = 0;
                     if (row < 3) {
                         const double* ar = wA + (c * T + n) * 12 + row * 4;
@@ -168,12 +176,11 @@ __global__ void __launch_bounds__(kGWarps * 32)
             // Rotation in fp32, the position entry in fp64 (its two ~L-sized terms cancel).
             const int slot16 = lane >> 1, half = lane & 1;
             for (int c = 0; c < ncfg; ++c) {
-                const long long b = b0 + c;
                 for (int n = 0; n < T; ++n) {
                     const int id = wIdx[c * T + n];
                     const int start = full ? 0 : id;
                     const int cnt = mc.npts[n] - start;
-                    const long long obase = offsets[b * T + n];
+                    const long long obase = wOff[c * T + n];
                     const double* ar = wA + (c * T + n) * 12 + (half ? 8 : 0);   // row 0 or row 2
                     const double a0 = ar[0], a1 = ar[1], a2 = ar[2], ap = ar[3];
                     const double b0_ = half ? 0.0 : ar[4], b1_ = half ? 0.0 : ar[5], b2_ = half ? 0.0 : ar[6], bp = half ? 0.0 : ar[7];
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(kGWarps * 32)
                         const float r0 = tabR[0 * tot + col], r1 = tabR[1 * tot + col], r2 = tabR[2 * tot + col];
                         const float r3 = tabR[3 * tot + col], r4 = tabR[4 * tot + col], r5 = tabR[5 * tot + col];
                         const float r6 = tabR[6 * tot + col], r7 = tabR[7 * tot + col], r8 = tabR[8 * tot + col];
-                        const double px = tab[9 * tot + col], py = tab[10 * tot + col], pz = tab[11 * tot + col];
+                        const double px = tabP[col], py = tabP[tot + col], pz = tabP[2 * tot + col];
                         float o[8];
                         o[0] = fmaf(f0, r0, fmaf(f1, r3, f2 * r6));
                         o[1] = fmaf(f0, r1, fmaf(f1, r4, f2 * r7));
@@ -478,20 +485,34 @@ int launch_gcurve(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_t
                   int precision, const long long* offsets, void* out) {
     if (B <= 0) return CTRB_OK;
     const int T = m->mc.T, tot = m->mc.total_nodes;
-    size_t base = (size_t)kGWarps * 32 * T * 12 * sizeof(double) + (((size_t)kGWarps * 32 * T + 1) / 2) * sizeof(double);
-    size_t with_tab = base + (size_t)12 * tot * sizeof(double) + (precision == CTRB_F32 ? (size_t)9 * tot * sizeof(float) : 0);
+    size_t base = (size_t)kGWarps * 32 * T * (12 * sizeof(double) + sizeof(long long)) +
+                  (((size_t)kGWarps * 32 * T + 1) / 2) * sizeof(double);
+    size_t with_tab = base + (precision == CTRB_F32 ? (size_t)3 * tot * sizeof(double) + (size_t)9 * tot * sizeof(float)
+                                                    : (size_t)12 * tot * sizeof(double));
     int tab_in_smem = with_tab <= 100 * 1024;
     size_t smem = tab_in_smem ? with_tab : base;
     long long ngroups = (B + 31) / 32;
     long long blocks_needed = (ngroups + kGWarps - 1) / kGWarps;
-    int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * 4);
-    KernelTimer kt(ctx, CTRB_KERNEL_GCURVE);
+    // persistent grid of resident blocks only (a fixed 4 per SM left the fp32 kernel, whose shared memory then allowed 3,
+    // with a quarter of its blocks in a second wave: 4.28 TB/s).  Measured on C2 (10^6 configurations), blocks per SM ->
+    // TB/s fp64 / fp32: 2 -> 5.76 / 5.55, 3 -> 5.91 / 6.12, 4 -> 5.71 / 5.63, 5+ (fp32) -> 5.63: twelve write streams
+    // per SM are enough to cover the store latency and more only scatter the DRAM pages.  CTRB_GCURVE_BLOCKS overrides.
+    int per_sm = 1;
     if (precision == CTRB_F64) {
         CTRB_CUDA(cudaFuncSetAttribute(kin_gcurve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kin_gcurve_kernel<double>, kGWarps * 32, smem));
+    } else {
+        CTRB_CUDA(cudaFuncSetAttribute(kin_gcurve_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kin_gcurve_kernel<float>, kGWarps * 32, smem));
+    }
+    static const int max_blocks = getenv("CTRB_GCURVE_BLOCKS") ? atoi(getenv("CTRB_GCURVE_BLOCKS")) : 3;
+    per_sm = std::max(1, std::min(per_sm, max_blocks));
+    int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * per_sm);
+    KernelTimer kt(ctx, CTRB_KERNEL_GCURVE);
+    if (precision == CTRB_F64) {
         kin_gcurve_kernel<double><<<grid, kGWarps * 32, smem, ctx->stream>>>(m->mc, m->tables(), B, idx, theta, full, offsets,
                                                                             (double*)out, tab_in_smem);
     } else {
-        CTRB_CUDA(cudaFuncSetAttribute(kin_gcurve_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kin_gcurve_kernel<float><<<grid, kGWarps * 32, smem, ctx->stream>>>(m->mc, m->tables(), B, idx, theta, full, offsets,
                                                                            (float*)out, tab_in_smem);
     }
