@@ -37,7 +37,8 @@ constexpr int kNP = 31;       // leading dimension of the n x n work matrices (o
 constexpr int kNV = 32;       // padded vector length
 
 // static_equilibrium (static.py:228-259): F(q), n = sm.nq
-__device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, const double* qp, double* F) {
+__device__ __noinline__ void st_residual(const StModel& sm_, const StCfg& c, const double* qp, double* F) {
+    CTRB_USE_SM;
     const int T = sm.mc.T;
     const QV q = {qp, -1, 0.0};
     double F31[3] = {0.0, 0.0, 0.0};
@@ -50,7 +51,7 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
             for (int a = 0; a < 2; ++a) {
                 double y2[2][15];
 #pragma unroll 1
-                for (int e = 0; e < 2; ++e) node_sec12(sm, c, q, 0, e ? c.hi[0][a] : c.lo[0][a], y2[e]);
+                for (int e = 0; e < 2; ++e) node_sec12<false>(sm, c, q, 0, e ? c.hi[0][a] : c.lo[0][a], y2[e]);
 #pragma unroll 1
                 for (int k = 0; k < 15; ++k) acc[k] += 0.5 * ((y2[1][k] - y2[0][k]) * c.wq[0][a] + y2[0][k]);
             }
@@ -69,7 +70,7 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
             for (int a = 0; a < 2; ++a) {
                 double y2[2][15];
 #pragma unroll 1
-                for (int e = 0; e < 2; ++e) node_sec12(sm, c, q, 1, e ? c.hi[1][a] : c.lo[1][a], y2[e]);
+                for (int e = 0; e < 2; ++e) node_sec12<false>(sm, c, q, 1, e ? c.hi[1][a] : c.lo[1][a], y2[e]);
 #pragma unroll 1
                 for (int k = 0; k < 15; ++k) acc[k] += 0.5 * ((y2[1][k] - y2[0][k]) * c.wq[1][a] + y2[0][k]);
             }
@@ -89,7 +90,7 @@ __device__ __noinline__ void st_residual(const StModel& sm, const StCfg& c, cons
             for (int a = 0; a < 2; ++a) {
                 double y2[2][CTRB_MAX_DOF];
 #pragma unroll 1
-                for (int e = 0; e < 2; ++e) node_sec3(sm, c, q, e ? c.hi[2][a] : c.lo[2][a], y2[e]);
+                for (int e = 0; e < 2; ++e) node_sec3<false>(sm, c, q, e ? c.hi[2][a] : c.lo[2][a], y2[e]);
 #pragma unroll 1
                 for (int k = 0; k < dof; ++k) acc[k] += 0.5 * ((y2[1][k] - y2[0][k]) * c.wq[2][a] + y2[0][k]);
             }
@@ -289,8 +290,9 @@ __device__ __noinline__ void st_r1mpyq_row(int n, double* a, int lda, const doub
 // MINPACK hybrd, warp-cooperative.  Every scalar of the iteration (delta, norms, counters, ratio) is
 // computed redundantly and identically by all lanes; vectors are one element per lane.
 // returns info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress)
-__device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
+__device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
                                      double factor, bool reduced, int* nfev_out) {
+    CTRB_USE_SM;
     // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2)
     const int n = reduced ? sm.nq - sm.ndof[5] : sm.nq;
     const int nnodes = reduced ? 8 : 12;
@@ -494,11 +496,13 @@ __device__ __noinline__ int st_hybrd(const StModel& sm, HybrdMem& M, const SlotT
 
 // ------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(kSWarps * 32, CTRB_QR_BLOCKS)
-    static_solve_kernel(const __grid_constant__ StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
+    static_solve_kernel(const __grid_constant__ StModel sm_, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
                         const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                         double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
                         int32_t* __restrict__ info_out, unsigned long long* __restrict__ ticket,
                         const long long* __restrict__ list, const unsigned long long* __restrict__ list_count) {
+    load_model(sm_);
+    const StModel& sm = g_sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SlotTable st;
     const bool reduced = x0 == nullptr;  // default initial guess: q_33 = q*
@@ -541,9 +545,11 @@ struct CurveMem {
     double q[kNV];
 };
 __global__ void __launch_bounds__(kCWarps * 32)
-    static_curves_kernel(const __grid_constant__ StModel sm, long long B, const int32_t* __restrict__ idx,
+    static_curves_kernel(const __grid_constant__ StModel sm_, long long B, const int32_t* __restrict__ idx,
                          const double* __restrict__ theta, const double* __restrict__ sol,
                          const long long* __restrict__ offsets, double* __restrict__ g_out) {
+    load_model(sm_);
+    const StModel& sm = g_sm;
     __shared__ CurveMem mem[kCWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     CurveMem& M = mem[warp];
@@ -558,9 +564,11 @@ __global__ void __launch_bounds__(kCWarps * 32)
 }
 
 // residual only (parity tests): one thread per (config) evaluates F(q)
-__global__ void static_residual_kernel(StModel sm, long long B, const int32_t* __restrict__ idx,
+__global__ void static_residual_kernel(StModel sm_, long long B, const int32_t* __restrict__ idx,
                                        const double* __restrict__ theta, const double* __restrict__ q,
                                        double* __restrict__ F) {
+    load_model(sm_);
+    const StModel& sm = g_sm;
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     StCfg c;

@@ -15,6 +15,23 @@ namespace {  // internal linkage: two translation units include this header
 
 constexpr int kMaxNq = kStaticMaxNq;
 
+// The model constants as every device function below reads them: a block-wide shared-memory copy that each kernel
+// fills first (load_model).  Through the kernel parameter (a generic pointer once it crosses an out-of-line call)
+// every field access was a generic LD behind two R2UR descriptor moves: 22 % of node_sec12's instructions.
+__shared__ StModel g_sm;
+#define CTRB_USE_SM      \
+    (void)sm_;           \
+    const StModel& sm = g_sm
+// Pointers into the warp's shared-memory workspace lose their address space when they cross an out-of-line call
+// inside a struct; the hint turns the generic LD / ST (+ descriptor moves) back into LDS / STS.
+#define CTRB_IN_SHARED(p) __builtin_assume(__isShared(p))
+__device__ __forceinline__ void load_model(const StModel& src) {
+    const int* s = reinterpret_cast<const int*>(&src);
+    int* d = reinterpret_cast<int*>(&g_sm);
+    for (int i = threadIdx.x; i < (int)(sizeof(StModel) / sizeof(int)); i += blockDim.x) d[i] = s[i];
+    __syncthreads();
+}
+
 struct StCfg {
     int i11, i21, i31, i22, i32, i33;
     int L[3];  // nodes of sections 1..3
@@ -103,7 +120,8 @@ __host__ __device__ __forceinline__ void strain_base_col(int kind, int dof, int 
 
 // ------------------------------------------------------------------ per-configuration setup
 // static.py:81-95 section indices; :456-491 quadrature brackets
-__device__ __noinline__ void st_setup(const StModel& sm, const int* idx, const double* theta, StCfg& c) {
+__device__ __noinline__ void st_setup(const StModel& sm_, const int* idx, const double* theta, StCfg& c) {
+    CTRB_USE_SM;
     const int T = sm.mc.T;
     const int* N = sm.mc.npts;
     int i11 = idx[0], i22 = idx[T - 2], i33 = idx[T - 1];
@@ -165,7 +183,8 @@ __device__ __noinline__ V3 ksi_star_cold(const ModelConst& mc, int n, double x) 
     strain_omega(mc, n, x, w);
     return V3{w[0], w[1], w[2]};
 }
-__device__ __forceinline__ V3 ksi_star_w(const StModel& sm, int n, int node) {
+__device__ __forceinline__ V3 ksi_star_w(const StModel& sm_, int n, int node) {
+    CTRB_USE_SM;
     if (node >= 0 && node < sm.mc.npts[n]) {
         const double* ws = sm.ws_tab + 3 * (sm.mc.node_base[n] + node);
         return V3{ws[0], ws[1], ws[2]};
@@ -179,7 +198,14 @@ __device__ __forceinline__ V3 ksi_star_w(const StModel& sm, int n, int node) {
 // same chain without a middle tube (zero stiffness, no torsion) whose rotation is the relative frame gg31 reached
 // at the end of section 1 (equilibrium_three's return value; identity for two tubes).
 //   sec 0: y = [intc1 (9), intg21 (3), intg31 (3)]      sec 1: y = [intc2 (9), intg32 (3), intg312 (3)]
-__device__ __noinline__ void node_sec12(const StModel& sm, const StCfg& c, QV q, int sec, int i, double y[15]) {
+template <bool kShared = true>  // kShared: c, q and y live in shared memory (all callers but the scalar parity kernel)
+__device__ __noinline__ void node_sec12(const StModel& sm_, const StCfg& c, QV q, int sec, int i, double y[15]) {
+    CTRB_USE_SM;
+    if (kShared) {
+        CTRB_IN_SHARED(&c);
+        CTRB_IN_SHARED(q.q);
+        CTRB_IN_SHARED(y);
+    }
     const int T = sm.mc.T;
     const bool s2 = sec == 1;
     const double dx = sm.mc.dx, X = i * dx;
@@ -228,7 +254,14 @@ __device__ __noinline__ void node_sec12(const StModel& sm, const StCfg& c, QV q,
 
 // section 3 (static.py:438-452); y = intc3 (dof of the last tube): B^T K (B q33 - B q*) with the base's single
 // non-zero per column taken from the per-design table
-__device__ __noinline__ void node_sec3(const StModel& sm, const StCfg& c, QV q, int i, double y[CTRB_MAX_DOF]) {
+template <bool kShared = true>
+__device__ __noinline__ void node_sec3(const StModel& sm_, const StCfg& c, QV q, int i, double y[CTRB_MAX_DOF]) {
+    CTRB_USE_SM;
+    if (kShared) {
+        CTRB_IN_SHARED(&c);
+        CTRB_IN_SHARED(q.q);
+        CTRB_IN_SHARED(y);
+    }
     const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
     const int q33 = sm.qoff[5];
     const double* bt = sm.b3_tab + (CTRB_MAX_DOF + 3) * (i + c.i33);
@@ -315,7 +348,11 @@ __device__ __noinline__ double enorm_w(int n, double v, const double* x_smem_or_
 
 // Cooperative residual, phase 1: work item t in 0..11 = (section, abscissa, bracket end) evaluates one node
 // integrand vector into y (shared memory).  q is a shared-memory vector of the unknowns.
-__device__ __noinline__ void res_node(const StModel& sm, const StCfg& c, QV q, int t, double* y) {
+__device__ __noinline__ void res_node(const StModel& sm_, const StCfg& c, QV q, int t, double* y) {
+    CTRB_USE_SM;
+    CTRB_IN_SHARED(&c);
+    CTRB_IN_SHARED(q.q);
+    CTRB_IN_SHARED(y);
     const int T = sm.mc.T;
     const int sec = t >> 2, a = (t >> 1) & 1, e = t & 1;
     if (c.len[sec] > 0.0 && (sec != 0 || T == 3)) {
@@ -332,7 +369,8 @@ __device__ __noinline__ void res_node(const StModel& sm, const StCfg& c, QV q, i
 }
 
 // phase 2: component k of F from the 12 node vectors (calculate_integral, static.py:456-491)
-__device__ __noinline__ double res_assemble(const StModel& sm, const StCfg& c, const double (*yb)[16], int comp) {
+__device__ __noinline__ double res_assemble(const StModel& sm_, const StCfg& c, const double (*yb)[16], int comp) {
+    CTRB_USE_SM;
     int blk = 0;  // order (1,1),(2,1),(3,1),(2,2),(3,2),(3,3)
 #pragma unroll
     for (int b = 1; b < 6; ++b)
@@ -370,7 +408,8 @@ struct RowMeta {
     int blk, k, sec, yo;
 };
 
-__device__ __forceinline__ RowMeta row_meta(const StModel& sm, int comp) {
+__device__ __forceinline__ RowMeta row_meta(const StModel& sm_, int comp) {
+    CTRB_USE_SM;
     RowMeta r;
     r.blk = 0;
 #pragma unroll
@@ -399,8 +438,9 @@ __device__ __forceinline__ double asm_part(const StCfg& c, const double (*yb)[16
 // component per lane.  Returns this lane's component; p1 / p2 are its section shares (row block (3,1) is
 // intg_31 - intg_312, static.py:250-252; p2 = 0 elsewhere).
 // `nnodes` = 12, or 8 when the last block is carried implicitly (see block5_norm2): its nodes are not needed then.
-__device__ __forceinline__ double warp_residual(const StModel& sm, const StCfg& cfg, double (*y)[16], const double* q,
+__device__ __forceinline__ double warp_residual(const StModel& sm_, const StCfg& cfg, double (*y)[16], const double* q,
                                                 const RowMeta& rm, bool act, int lane, int nnodes, double* p1, double* p2) {
+    CTRB_USE_SM;
     if (lane < nnodes) res_node(sm, cfg, QV{q, -1, 0.0}, lane, y[lane]);
     __syncwarp();
     double a = 0.0, b = 0.0;
@@ -421,7 +461,8 @@ struct SlotTable {
 };
 
 // thread 0 of the block fills the table (it only depends on the design); `reduced` leaves the last block out
-__device__ __forceinline__ void build_slot_table(const StModel& sm, SlotTable& st, bool reduced) {
+__device__ __forceinline__ void build_slot_table(const StModel& sm_, SlotTable& st, bool reduced) {
+    CTRB_USE_SM;
     int ns = 0;
     for (int b = 0; b < 6; ++b)
         for (int k = 0; k < sm.ndof[b]; ++k) st.col_blk[sm.qoff[b] + k] = (signed char)b;
@@ -449,7 +490,8 @@ __device__ __forceinline__ void build_slot_table(const StModel& sm, SlotTable& s
 // constant  sum_j (D_j q*_j)^2  with D_j = the forward-difference column norms of the block.  So the solvers iterate on
 // the first n - dof_33 unknowns and add this constant to |D x|^2: the same iterates with 27 instead of 30 unknowns.
 // Returns that constant (all lanes); yb is scratch for 32 node vectors.
-__device__ __noinline__ double block5_norm2(const StModel& sm, const StCfg& cfg, const double* x, double (*yb)[16], int lane) {
+__device__ __noinline__ double block5_norm2(const StModel& sm_, const StCfg& cfg, const double* x, double (*yb)[16], int lane) {
+    CTRB_USE_SM;
     const int dof = sm.ndof[5], q0 = sm.qoff[5];
     const double eps = sqrt(DBL_EPSILON);
     const int slot = lane >> 2;
@@ -478,9 +520,10 @@ __device__ __noinline__ double block5_norm2(const StModel& sm, const StCfg& cfg,
 // forward-difference Jacobian (MINPACK fdjac1, dense band) using the block structure; f_l / p1b / p2b are this
 // lane's residual component at x and its section shares.  Writes J (column-major, leading dimension kJLD); yb is
 // scratch for 32 node vectors; returns this lane's column norm.
-__device__ __noinline__ double warp_fdjac(const StModel& sm, const StCfg& cfg, const SlotTable& st, const RowMeta& rm,
+__device__ __noinline__ double warp_fdjac(const StModel& sm_, const StCfg& cfg, const SlotTable& st, const RowMeta& rm,
                                           const double* x, double* J, double (*yb)[16], double f_l, double p1b, double p2b,
                                           int n, int lane) {
+    CTRB_USE_SM;
     const bool act = lane < n;
     const double eps = sqrt(DBL_EPSILON);
     for (int base = 0; base < st.nslots; base += 8) {
@@ -553,8 +596,9 @@ __device__ __noinline__ SE3 magnus_step(const double wA[3], const double wB[3], 
 }
 
 // omega of the (tube==section) basis at absolute section coordinate `sidx` (static_bases.py:61-81)
-__device__ __noinline__ void sect_omega(const StModel& sm, const StCfg& c, const double* qs, int sect, double sidx,
+__device__ __noinline__ void sect_omega(const StModel& sm_, const StCfg& c, const double* qs, int sect, double sidx,
                                            double w[3]) {
+    CTRB_USE_SM;
     const double dx = sm.mc.dx;
     if (sect == 3) {
         const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
@@ -580,8 +624,9 @@ __device__ __noinline__ void sect_omega(const StModel& sm, const StCfg& c, const
 
 // Writes `count` nodes of one section curve: node 0 = g0, node k = g0 * E_1 ... E_k with
 // E_k the Magnus step at absolute index start + k.  Returns the last node (all lanes).
-__device__ __noinline__ SE3 integrate_section(const StModel& sm, const StCfg& c, const double* qs, int sect, int start, int count,
+__device__ __noinline__ SE3 integrate_section(const StModel& sm_, const StCfg& c, const double* qs, int sect, int start, int count,
                                  SE3 g0, double* out, int lane) {
+    CTRB_USE_SM;
     const double dx = sm.mc.dx;
     const double cg1 = 0.5 - sqrt(3.0) / 6, cg2 = 0.5 + sqrt(3.0) / 6;  // static.py:597-599
     if (lane == 0 && out) {
@@ -651,8 +696,9 @@ __device__ __forceinline__ double ipoly3_abs(const double* q, double a, double b
 
 // Static.solve_g's curve assembly (static.py:110-130) from a solved q (shared-memory vector): the whole warp
 // writes the T section curves of configuration b into the packed g_out.
-__device__ __noinline__ void st_write_curves(const StModel& sm, const StCfg& c, const double* q, const long long* offsets,
+__device__ __noinline__ void st_write_curves(const StModel& sm_, const StCfg& c, const double* q, const long long* offsets,
                                              long long b, double* g_out, int lane) {
+    CTRB_USE_SM;
     const int T = sm.mc.T;
     const double dx = sm.mc.dx;
     SE3 g11_last, g21_last, g31_last;

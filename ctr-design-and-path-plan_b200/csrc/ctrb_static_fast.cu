@@ -137,8 +137,9 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n, double acnorm_l, int
 
 // returns MINPACK's info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress), or -1 when the
 // configuration has to go through the QR kernel
-__device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
+__device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
                                        double factor, bool reduced, int* nfev_out) {
+    CTRB_USE_SM;
     // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2)
     const int n = reduced ? sm.nq - sm.ndof[5] : sm.nq;
     const int nnodes = reduced ? 8 : 12;
@@ -296,11 +297,13 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm, FastMem& M, const Slot
 }
 
 __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
-    static_fast_kernel(const __grid_constant__ StModel sm, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
+    static_fast_kernel(const __grid_constant__ StModel sm_, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
                        const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                        double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
                        int32_t* __restrict__ info_out, long long* __restrict__ fb_list,
                        unsigned long long* __restrict__ fb_count, unsigned long long* __restrict__ ticket) {
+    load_model(sm_);
+    const StModel& sm = g_sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SlotTable st;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
