@@ -32,6 +32,13 @@ namespace ctrb {
 #ifndef CTRB_QR_BLOCKS
 #define CTRB_QR_BLOCKS 5
 #endif
+#ifndef CTRB_QR_UNROLL
+// unroll factor of the dot-product / update loops of qrfac, qform, dogleg and the Broyden vectors (one multiply-add per
+// 10 instructions when rolled).  Measured on C3 shallow, QR kernel M cfg/s: 1 -> 2.55, 2 -> 2.69, 4 -> 2.55, 8 -> 2.28:
+// beyond 2 the larger code costs more instruction-cache misses than the saved loop overhead buys.
+#define CTRB_QR_UNROLL 2
+#endif
+constexpr int kQrUnroll = CTRB_QR_UNROLL;
 constexpr int kSWarps = CTRB_QR_WARPS;    // warps (= configurations) per block: 5 blocks (15 warps) per SM by smem and registers
 constexpr int kNP = 31;       // leading dimension of the n x n work matrices (odd: conflict-free column access)
 constexpr int kNV = 32;       // padded vector length
@@ -151,7 +158,7 @@ __device__ __noinline__ double dogleg_w(int n, const double* r, double diag_l, c
     // scaled gradient direction: wa1_i = (sum_{j<=i} r(j,i) qtb_j) / diag_i
     double g = 0.0;
     if (act) {
-#pragma unroll 1
+#pragma unroll kQrUnroll
         for (int j = 0; j <= lane; ++j) g += r[rowoff(n, j) + lane - j] * qtb[j];
         g = g / diag_l;
     }
@@ -164,7 +171,7 @@ __device__ __noinline__ double dogleg_w(int n, const double* r, double diag_l, c
         double w2 = 0.0;
         if (act) {
             const int ro = rowoff(n, lane);
-#pragma unroll 1
+#pragma unroll kQrUnroll
             for (int i = lane; i < n; ++i) w2 += r[ro + i - lane] * tmp[i];
         }
         double temp = enorm_w(n, w2, nullptr);
@@ -324,7 +331,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
         double acnorm_l = 0.0;
         if (act) {
             double s2 = 0.0;
-#pragma unroll 1
+#pragma unroll kQrUnroll
             for (int i = 0; i < n; ++i) s2 += fjac[i + lane * kNP] * fjac[i + lane * kNP];
             acnorm_l = sqrt(s2);
         }
@@ -340,10 +347,10 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
                 __syncwarp();
                 if (lane > j && act) {  // lane = column k
                     double sum = 0;
-#pragma unroll 1
+#pragma unroll kQrUnroll
                     for (int i = j; i < n; ++i) sum += fjac[i + j * kNP] * fjac[i + lane * kNP];
                     const double temp = sum / fjac[j + j * kNP];
-#pragma unroll 1
+#pragma unroll kQrUnroll
                     for (int i = j; i < n; ++i) fjac[i + lane * kNP] -= temp * fjac[i + j * kNP];
                 }
             }
@@ -390,10 +397,10 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
             if (M.wa3[k] != 0) {
                 if (lane >= k && act) {
                     double sum = 0;
-#pragma unroll 1
+#pragma unroll kQrUnroll
                     for (int i = k; i < n; ++i) sum += fjac[i + lane * kNP] * M.wa3[i];
                     const double temp = sum / M.wa3[k];
-#pragma unroll 1
+#pragma unroll kQrUnroll
                     for (int i = k; i < n; ++i) fjac[i + lane * kNP] -= temp * M.wa3[i];
                 }
             }
@@ -427,7 +434,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
             if (act) {
                 const int ro = rowoff(n, lane);
                 double sum = 0;
-#pragma unroll 1
+#pragma unroll kQrUnroll
                 for (int j = lane; j < n; ++j) sum += M.r[ro + j - lane] * M.wa1[j];
                 w3 = M.qtf[lane] + sum;
             }
@@ -478,7 +485,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
             double u_l = 0.0;
             if (act) {
                 double sum = 0;
-#pragma unroll 1
+#pragma unroll kQrUnroll
                 for (int i = 0; i < n; ++i) sum += fjac[i + lane * kNP] * M.wa4[i];
                 M.wa2[lane] = (sum - w3) / pnorm;                 // v
                 u_l = diag_l * ((diag_l * p_l) / pnorm);          // u

@@ -41,7 +41,7 @@ constexpr int kLD = kJLD;    // leading dimension, column-major: element (i, j) 
                              // "lane = row" (stride 1) and "lane = column" (stride 31) accesses are conflict-free
 constexpr unsigned kFull = 0xffffffffu;
 
-struct FastMem {
+struct alignas(16) FastMem {
     double J[kLD * kMaxNq];
     double H[kLD * kMaxNq + 34];  // + slack: lanes 30, 31 read (and discard) one column past the end
     double x[32], f[32], va[32], vb[32], vc[32];
@@ -52,29 +52,43 @@ struct FastMem {
     __device__ double (*ybuf())[16] { return reinterpret_cast<double(*)[16]>(H); }
 };
 
-// y_i = sum_j M[i][j] v[j]: lane = row i, v broadcast from shared memory
-__device__ __noinline__ double matvec_row(const double* M, const double* v, int n, int lane) {
+// y_i = sum_j M[i][j] v[j]: lane = row i, v broadcast from shared memory (two elements per 128-bit load; every
+// vector of FastMem is 16-byte aligned)
+// N = the system size when the kernel is instantiated for it (loops unroll completely), 0 = run-time n
+template <int N>
+__device__ __noinline__ double matvec_row(const double* M, const double* v, int n_rt, int lane) {
+    const int n = N ? N : n_rt;
+    CTRB_IN_SHARED(M);
+    CTRB_IN_SHARED(v);
     const double* m = M + lane;
+    const double2* v2 = reinterpret_cast<const double2*>(v);
     double a0 = 0.0, a1 = 0.0;
     int j = 0;
-#pragma unroll 2
+#pragma unroll(N ? 16 : 3)
     for (; j + 1 < n; j += 2) {
-        a0 = fma(m[j * kLD], v[j], a0);
-        a1 = fma(m[(j + 1) * kLD], v[j + 1], a1);
+        const double2 vv = v2[j >> 1];
+        a0 = fma(m[j * kLD], vv.x, a0);
+        a1 = fma(m[(j + 1) * kLD], vv.y, a1);
     }
     if (j < n) a0 = fma(m[j * kLD], v[j], a0);
     return a0 + a1;
 }
 
 // y_j = sum_i M[i][j] v[i]: lane = column j
-__device__ __noinline__ double matvec_col(const double* M, const double* v, int n, int lane) {
+template <int N>
+__device__ __noinline__ double matvec_col(const double* M, const double* v, int n_rt, int lane) {
+    const int n = N ? N : n_rt;
+    CTRB_IN_SHARED(M);
+    CTRB_IN_SHARED(v);
     const double* m = M + lane * kLD;
+    const double2* v2 = reinterpret_cast<const double2*>(v);
     double a0 = 0.0, a1 = 0.0;
     int i = 0;
-#pragma unroll 2
+#pragma unroll(N ? 16 : 3)
     for (; i + 1 < n; i += 2) {
-        a0 = fma(m[i], v[i], a0);
-        a1 = fma(m[i + 1], v[i + 1], a1);
+        const double2 vv = v2[i >> 1];
+        a0 = fma(m[i], vv.x, a0);
+        a1 = fma(m[i + 1], vv.y, a1);
     }
     if (i < n) a0 = fma(m[i], v[i], a0);
     return a0 + a1;
@@ -84,7 +98,10 @@ __device__ __forceinline__ double wnorm(double v) { return sqrt(warp_sum(v * v))
 
 // H = J^-1 by Gauss-Jordan exchange steps with implicit partial pivoting; lane = row.  Returns false when a
 // pivot falls below 1e-12 of its column norm (numerically singular Jacobian).
-__device__ __noinline__ bool fast_invert(FastMem& M, int n, double acnorm_l, int lane) {
+template <int N>
+__device__ __noinline__ bool fast_invert(FastMem& M, int n_rt, double acnorm_l, int lane) {
+    const int n = N ? N : n_rt;
+    CTRB_IN_SHARED(&M);
     const bool act = lane < n;
     double* Tm = M.H;
     for (int e = lane; e < kLD * n; e += 32) Tm[e] = M.J[e];
@@ -107,7 +124,7 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n, double acnorm_l, int
         if (act && lane != r) {
             const double* pr = Tm + r;
             double* tr = Tm + lane;
-#pragma unroll 2
+#pragma unroll(N ? 32 : 3)
             for (int j = 0; j < n; ++j) tr[j * kLD] = fma(-m, pr[j * kLD], tr[j * kLD]);
         }
         __syncwarp();
@@ -137,11 +154,14 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n, double acnorm_l, int
 
 // returns MINPACK's info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress), or -1 when the
 // configuration has to go through the QR kernel
+template <int N>
 __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
                                        double factor, bool reduced, int* nfev_out) {
     CTRB_USE_SM;
+    CTRB_IN_SHARED(&M);
+    CTRB_IN_SHARED(&st);
     // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2)
-    const int n = reduced ? sm.nq - sm.ndof[5] : sm.nq;
+    const int n = N ? N : (reduced ? sm.nq - sm.ndof[5] : sm.nq);
     const int nnodes = reduced ? 8 : 12;
     const double c33 = reduced ? block5_norm2(sm, M.cfg, M.x, M.ybuf(), lane) : 0.0;
     const bool act = lane < n;
@@ -160,7 +180,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
         bool jeval = true;
         const double acnorm_l = warp_fdjac(sm, M.cfg, st, rm, M.x, M.J, M.ybuf(), f_l, pa, pb, n, lane);
         nfev += sm.nq;  // MINPACK's count: one evaluation per unknown
-        if (!fast_invert(M, n, acnorm_l, lane)) return -1;
+        if (!fast_invert<N>(M, n, acnorm_l, lane)) return -1;
         if (iter == 1) {
             diag_l = acnorm_l == 0.0 ? 1.0 : acnorm_l;
             xnorm = sqrt(warp_sum(act ? (diag_l * x_l) * (diag_l * x_l) : 0.0) + c33);
@@ -174,18 +194,18 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
 #pragma unroll 1
         for (;;) {
             // ---- dogleg (MINPACK): Gauss-Newton step H f, scaled gradient J^T f / D, their trust-region blend
-            const double xg = act ? matvec_row(M.H, M.f, n, lane) : 0.0;
+            const double xg = act ? matvec_row<N>(M.H, M.f, n, lane) : 0.0;
             const double qnorm = wnorm(diag_l * xg);
             double step = xg;
             if (!(qnorm <= delta)) {
-                double g = act ? matvec_col(M.J, M.f, n, lane) * rdiag_l : 0.0;
+                double g = act ? matvec_col<N>(M.J, M.f, n, lane) * rdiag_l : 0.0;
                 const double gnorm = wnorm(g);
                 double sgnorm = 0.0, alpha = delta / qnorm;
                 if (gnorm != 0.0) {
                     g = act ? (g * (1.0 / gnorm)) * rdiag_l : 0.0;
                     if (act) M.va[lane] = g;
                     __syncwarp();
-                    const double w2 = act ? matvec_row(M.J, M.va, n, lane) : 0.0;
+                    const double w2 = act ? matvec_row<N>(M.J, M.va, n, lane) : 0.0;
                     double temp = wnorm(w2);
                     sgnorm = (gnorm / temp) / temp;
                     alpha = 0.0;
@@ -217,7 +237,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
             if (!(fnorm1 < 1.7e308) || !(pnorm < 1.7e308)) return -1;  // non-finite: let the QR kernel decide
             double actred = -1.0;
             if (fnorm1 < fnorm) actred = 1 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
-            const double w3 = act ? f_l + matvec_row(M.J, M.va, n, lane) : 0.0;  // f + J p
+            const double w3 = act ? f_l + matvec_row<N>(M.J, M.va, n, lane) : 0.0;  // f + J p
             const double temp = wnorm(w3);
             double prered = 0.0;
             if (temp < fnorm) prered = 1 - (temp / fnorm) * (temp / fnorm);
@@ -273,8 +293,8 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
                 M.vc[lane] = v_l;
             }
             __syncwarp();
-            const double Hu = act ? matvec_row(M.H, M.vb, n, lane) : 0.0;
-            const double vH = act ? matvec_col(M.H, M.vc, n, lane) : 0.0;
+            const double Hu = act ? matvec_row<N>(M.H, M.vb, n, lane) : 0.0;
+            const double vH = act ? matvec_col<N>(M.H, M.vc, n, lane) : 0.0;
             const double den = 1.0 + warp_sum(v_l * Hu);
             if (!(fabs(den) > 1e-8) || !(fabs(den) < 1e100)) return -1;  // J+ is (numerically) singular
             __syncwarp();
@@ -284,8 +304,18 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
                 const double hs = -Hu * (1.0 / den);
                 double* jr = M.J + lane;
                 double* hr = M.H + lane;
-#pragma unroll 2
-                for (int j = 0; j < n; ++j) {
+                const double2* vc2 = reinterpret_cast<const double2*>(M.vc);
+                const double2* vb2 = reinterpret_cast<const double2*>(M.vb);
+                int j = 0;
+#pragma unroll(N ? 16 : 3)
+                for (; j + 1 < n; j += 2) {
+                    const double2 c2 = vc2[j >> 1], b2 = vb2[j >> 1];
+                    jr[j * kLD] = fma(u_l, c2.x, jr[j * kLD]);
+                    hr[j * kLD] = fma(hs, b2.x, hr[j * kLD]);
+                    jr[(j + 1) * kLD] = fma(u_l, c2.y, jr[(j + 1) * kLD]);
+                    hr[(j + 1) * kLD] = fma(hs, b2.y, hr[(j + 1) * kLD]);
+                }
+                if (j < n) {
                     jr[j * kLD] = fma(u_l, M.vc[j], jr[j * kLD]);
                     hr[j * kLD] = fma(hs, M.vb[j], hr[j * kLD]);
                 }
@@ -296,6 +326,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
     }
 }
 
+template <int N>
 __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
     static_fast_kernel(const __grid_constant__ StModel sm_, long long B, const int32_t* __restrict__ idx, const double* __restrict__ theta,
                        const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
@@ -329,7 +360,7 @@ __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
         // and a one-step section 1 or 2 gives the x and x^2 curvature coefficients identical columns
         const bool degenerate = (T == 3 && c.L[0] < 3) || c.L[1] < 3 || c.L[2] < 2;
         int nfev = 0;
-        const int info = degenerate ? -1 : fast_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, &nfev);
+        const int info = degenerate ? -1 : fast_hybrd<N>(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, &nfev);
         __syncwarp();
         if (info < 0) {
             if (lane == 0) fb_list[atomicAdd(fb_count, 1ULL)] = b;
@@ -344,21 +375,45 @@ __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
     }
 }
 
+template <int N>
+static int launch_static_fast_n(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
+                                const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
+                                double* sol_out, int32_t* nfev_out, int32_t* info_out, long long* fb_list,
+                                unsigned long long* fb_count, unsigned long long* ticket) {
+    const size_t smem = sizeof(FastMem) * kFWarps;
+    CTRB_CUDA(cudaFuncSetAttribute(static_fast_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, static_fast_kernel<N>, kFWarps * 32, smem));
+    const long long blocks_needed = (B + kFWarps - 1) / kFWarps;
+    const int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * std::max(per_sm, 1));
+    static_fast_kernel<N><<<grid, kFWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out,
+                                                                    sol_out, nfev_out, info_out, fb_list, fb_count, ticket);
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
+    return CTRB_OK;
+}
+
+// The kernel is instantiated for the system sizes of the reference's configurations (three tubes: 30 unknowns, 27 from
+// the default initial guess; two tubes: 15 / 12) so that its n-long loops unroll completely; any other size takes the
+// run-time-n instantiation.
 int launch_static_fast(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
                        const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
                        double* sol_out, int32_t* nfev_out, int32_t* info_out, long long* fb_list,
                        unsigned long long* fb_count, unsigned long long* ticket) {
-    const size_t smem = sizeof(FastMem) * kFWarps;
-    CTRB_CUDA(cudaFuncSetAttribute(static_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, static_fast_kernel, kFWarps * 32, smem));
-    const long long blocks_needed = (B + kFWarps - 1) / kFWarps;
-    const int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * std::max(per_sm, 1));
-    static_fast_kernel<<<grid, kFWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out,
-                                                                 sol_out, nfev_out, info_out, fb_list, fb_count, ticket);
-    ctx->launches++;
-    CTRB_CUDA(cudaGetLastError());
-    return CTRB_OK;
+    const int n = x0 == nullptr ? sm.nq - sm.ndof[5] : sm.nq;  // as fast_hybrd derives it
+    static const bool generic = getenv("CTRB_FAST_GENERIC_N") != nullptr;
+#define CTRB_FAST_ARGS ctx, sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out, sol_out, nfev_out, info_out, fb_list, fb_count, ticket
+    if (!generic) {
+        switch (n) {
+            case 27: return launch_static_fast_n<27>(CTRB_FAST_ARGS);
+            case 30: return launch_static_fast_n<30>(CTRB_FAST_ARGS);
+            case 12: return launch_static_fast_n<12>(CTRB_FAST_ARGS);
+            case 15: return launch_static_fast_n<15>(CTRB_FAST_ARGS);
+            default: break;
+        }
+    }
+    return launch_static_fast_n<0>(CTRB_FAST_ARGS);
+#undef CTRB_FAST_ARGS
 }
 
 }  // namespace ctrb
