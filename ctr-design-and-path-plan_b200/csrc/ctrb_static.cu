@@ -38,7 +38,10 @@ namespace ctrb {
 // beyond 2 the larger code costs more instruction-cache misses than the saved loop overhead buys.
 #define CTRB_QR_UNROLL 2
 #endif
-constexpr int kQrUnroll = CTRB_QR_UNROLL;
+#ifndef CTRB_QR_ITER_UNROLL
+#define CTRB_QR_ITER_UNROLL 2   // the same for the loops inside hybrd's iteration (dogleg, predicted reduction, Broyden vectors)
+#endif
+constexpr int kQrUnroll = CTRB_QR_UNROLL, kQrIterUnroll = CTRB_QR_ITER_UNROLL;
 constexpr int kSWarps = CTRB_QR_WARPS;    // warps (= configurations) per block: 5 blocks (15 warps) per SM by smem and registers
 constexpr int kNP = 31;       // leading dimension of the n x n work matrices (odd: conflict-free column access)
 constexpr int kNV = 32;       // padded vector length
@@ -158,7 +161,7 @@ __device__ __noinline__ double dogleg_w(int n, const double* r, double diag_l, c
     // scaled gradient direction: wa1_i = (sum_{j<=i} r(j,i) qtb_j) / diag_i
     double g = 0.0;
     if (act) {
-#pragma unroll kQrUnroll
+#pragma unroll kQrIterUnroll
         for (int j = 0; j <= lane; ++j) g += r[rowoff(n, j) + lane - j] * qtb[j];
         g = g / diag_l;
     }
@@ -171,7 +174,7 @@ __device__ __noinline__ double dogleg_w(int n, const double* r, double diag_l, c
         double w2 = 0.0;
         if (act) {
             const int ro = rowoff(n, lane);
-#pragma unroll kQrUnroll
+#pragma unroll kQrIterUnroll
             for (int i = lane; i < n; ++i) w2 += r[ro + i - lane] * tmp[i];
         }
         double temp = enorm_w(n, w2, nullptr);
@@ -434,7 +437,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
             if (act) {
                 const int ro = rowoff(n, lane);
                 double sum = 0;
-#pragma unroll kQrUnroll
+#pragma unroll kQrIterUnroll
                 for (int j = lane; j < n; ++j) sum += M.r[ro + j - lane] * M.wa1[j];
                 w3 = M.qtf[lane] + sum;
             }
@@ -485,7 +488,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
             double u_l = 0.0;
             if (act) {
                 double sum = 0;
-#pragma unroll kQrUnroll
+#pragma unroll kQrIterUnroll
                 for (int i = 0; i < n; ++i) sum += fjac[i + lane * kNP] * M.wa4[i];
                 M.wa2[lane] = (sum - w3) / pnorm;                 // v
                 u_l = diag_l * ((diag_l * p_l) / pnorm);          // u

@@ -40,6 +40,21 @@ constexpr int kFWarps = CTRB_FAST_WARPS;   // warps (= configurations in flight)
 constexpr int kLD = kJLD;    // leading dimension, column-major: element (i, j) at i + j * kLD.  Odd, so both
                              // "lane = row" (stride 1) and "lane = column" (stride 31) accesses are conflict-free
 constexpr unsigned kFull = 0xffffffffu;
+// unroll factors of the n-long loops when n is a template parameter: pairs of columns for the matrix-vector products
+// (complete) and for the rank-one update, columns for the Gauss-Jordan step.  Measured on C3 (exposure 2..8, no
+// fallbacks), M cfg/s: everything complete 11.19; update 3 -> 11.79; + Gauss-Jordan 3 -> 12.10; (2, 2) 12.07; (1, 1) 11.84;
+// matrix-vector products by 5 or 8 instead of complete: 12.2 / 12.1 with the two-tube model slower.  The kernel runs on
+// instruction fetch: ncu's stall_no_instruction went from 1.3 to 2.4 per issue with everything unrolled.
+#ifndef CTRB_MV_UNROLL
+#define CTRB_MV_UNROLL 16
+#endif
+#ifndef CTRB_R1_UNROLL
+#define CTRB_R1_UNROLL 3
+#endif
+#ifndef CTRB_INV_UNROLL
+#define CTRB_INV_UNROLL 3
+#endif
+constexpr int kMvUnroll = CTRB_MV_UNROLL, kR1Unroll = CTRB_R1_UNROLL, kInvUnroll = CTRB_INV_UNROLL;
 
 struct alignas(16) FastMem {
     double J[kLD * kMaxNq];
@@ -64,7 +79,7 @@ __device__ __noinline__ double matvec_row(const double* M, const double* v, int 
     const double2* v2 = reinterpret_cast<const double2*>(v);
     double a0 = 0.0, a1 = 0.0;
     int j = 0;
-#pragma unroll(N ? 16 : 3)
+#pragma unroll(N ? kMvUnroll : 3)
     for (; j + 1 < n; j += 2) {
         const double2 vv = v2[j >> 1];
         a0 = fma(m[j * kLD], vv.x, a0);
@@ -84,7 +99,7 @@ __device__ __noinline__ double matvec_col(const double* M, const double* v, int 
     const double2* v2 = reinterpret_cast<const double2*>(v);
     double a0 = 0.0, a1 = 0.0;
     int i = 0;
-#pragma unroll(N ? 16 : 3)
+#pragma unroll(N ? kMvUnroll : 3)
     for (; i + 1 < n; i += 2) {
         const double2 vv = v2[i >> 1];
         a0 = fma(m[i], vv.x, a0);
@@ -124,7 +139,7 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n_rt, double acnorm_l, 
         if (act && lane != r) {
             const double* pr = Tm + r;
             double* tr = Tm + lane;
-#pragma unroll(N ? 32 : 3)
+#pragma unroll(N ? kInvUnroll : 3)
             for (int j = 0; j < n; ++j) tr[j * kLD] = fma(-m, pr[j * kLD], tr[j * kLD]);
         }
         __syncwarp();
@@ -307,7 +322,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
                 const double2* vc2 = reinterpret_cast<const double2*>(M.vc);
                 const double2* vb2 = reinterpret_cast<const double2*>(M.vb);
                 int j = 0;
-#pragma unroll(N ? 16 : 3)
+#pragma unroll(N ? kR1Unroll : 3)
                 for (; j + 1 < n; j += 2) {
                     const double2 c2 = vc2[j >> 1], b2 = vb2[j >> 1];
                     jr[j * kLD] = fma(u_l, c2.x, jr[j * kLD]);
