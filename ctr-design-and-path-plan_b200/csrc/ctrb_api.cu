@@ -417,6 +417,7 @@ void ctrb_model_destroy(ctrb_model* m) {
     cudaFree(m->d_tabR32);
     cudaFree(m->d_ws_tab);
     cudaFree(m->d_b3_tab);
+    cudaFree(m->d_quad_tab);
     delete m;
 }
 

@@ -67,6 +67,15 @@ struct StModel {
     const double* b3_tab;          // [npts_last][CTRB_MAX_DOF + 3]: last tube's strain base at node j, one value per
                                    // column (every base has one non-zero per column), then (B q*)[0:3]
     int b3_row[CTRB_MAX_DOF];      // the row of that non-zero
+    const struct StQuad* quad_tab; // [max npts + 1]: calculate_integral's brackets for a section of np nodes (st_setup)
+    int quad_max;                  // largest np in the table
+};
+
+// calculate_integral (static.py:456-491) for a section of np nodes: the two abscissae's bracketing nodes, interp1d's
+// (x_new - x_lo) / (x_hi - x_lo), and the section length.  Depends on (np, delta_x) only: tabulated per design.
+struct StQuad {
+    int lo[2], hi[2];
+    double wq[2], len;
 };
 
 }  // namespace ctrb
@@ -99,6 +108,7 @@ struct ctrb_model {
     ctrb::StModel sm;
     double* d_ws_tab;
     double* d_b3_tab;
+    ctrb::StQuad* d_quad_tab;
     ctrb::ModelTables tables() const { return ctrb::ModelTables{d_tab, d_tab_inv, d_tabR32}; }
 };
 

@@ -590,7 +590,13 @@ __global__ void static_residual_kernel(StModel sm_, long long B, const int32_t* 
 }
 
 // per-design tables of StModel: one thread per node
-__global__ void static_tables_kernel(StModel sm, double* __restrict__ ws, double* __restrict__ b3) {
+__global__ void static_tables_kernel(StModel sm, double* __restrict__ ws, double* __restrict__ b3, StQuad* __restrict__ quad,
+                                     int quad_n) {
+    if ((int)(blockIdx.x * blockDim.x + threadIdx.x) < quad_n) {
+        StQuad e;
+        st_quad(sm.mc.dx, blockIdx.x * blockDim.x + threadIdx.x, e);
+        quad[blockIdx.x * blockDim.x + threadIdx.x] = e;
+    }
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int T = sm.mc.T;
     if (j < sm.mc.total_nodes) {
@@ -673,9 +679,15 @@ int launch_static_tables(ctrb_ctx* ctx, ctrb_model* m) {
     const int tot = m->mc.total_nodes, T = m->mc.T;
     CTRB_CUDA(cudaMalloc(&m->d_ws_tab, (size_t)tot * 3 * sizeof(double)));
     CTRB_CUDA(cudaMalloc(&m->d_b3_tab, (size_t)m->mc.npts[T - 1] * (CTRB_MAX_DOF + 3) * sizeof(double)));
+    int quad_max = 1;
+    for (int n = 0; n < T; ++n) quad_max = std::max(quad_max, m->mc.npts[n]);
+    CTRB_CUDA(cudaMalloc(&m->d_quad_tab, (size_t)(quad_max + 1) * sizeof(StQuad)));
     m->sm.ws_tab = m->d_ws_tab;
     m->sm.b3_tab = m->d_b3_tab;
-    static_tables_kernel<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(m->sm, m->d_ws_tab, m->d_b3_tab);
+    m->sm.quad_tab = m->d_quad_tab;
+    m->sm.quad_max = quad_max;
+    const int work = std::max(tot, quad_max + 1);
+    static_tables_kernel<<<(work + 127) / 128, 128, 0, ctx->stream>>>(m->sm, m->d_ws_tab, m->d_b3_tab, m->d_quad_tab, quad_max + 1);
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());
     return CTRB_OK;

@@ -119,7 +119,34 @@ __host__ __device__ __forceinline__ void strain_base_col(int kind, int dof, int 
 }
 
 // ------------------------------------------------------------------ per-configuration setup
-// static.py:81-95 section indices; :456-491 quadrature brackets
+// static.py:456-491 quadrature brackets of a section of np nodes (runs once per design and np: static_tables_kernel)
+__device__ __noinline__ void st_quad(double dx, int np, StQuad& e) {
+    const double cs[2] = {(1.0 / sqrt(3.0) + 1.0) / 2.0, (-1.0 / sqrt(3.0) + 1.0) / 2.0};  // static.py:601-603
+    const double length = (np - 1) * dx;
+    e.len = length;
+    for (int a = 0; a < 2; ++a) {
+        e.lo[a] = e.hi[a] = 0;
+        e.wq[a] = 0.0;
+        if (!(length > 0.0)) continue;
+        const double step = length / (np - 1);  // np.linspace(0, length, num_points)
+        const double xn = cs[a] * length;
+        // searchsorted(x_vals, xn, side='left') clipped to [1, np-1]
+        int hi = (int)ceil(xn / step);
+        if (hi < 0) hi = 0;
+        if (hi > np - 1) hi = np - 1;
+        while (hi < np - 1 && ((hi == np - 1) ? length : hi * step) < xn) ++hi;
+        while (hi > 0 && (((hi - 1) == np - 1) ? length : (hi - 1) * step) >= xn) --hi;
+        if (hi < 1) hi = 1;
+        const int lo = hi - 1;
+        const double xlo = lo * step, xhi = (hi == np - 1) ? length : hi * step;
+        e.lo[a] = lo;
+        e.hi[a] = hi;
+        e.wq[a] = (xn - xlo) / (xhi - xlo);
+    }
+}
+
+// static.py:81-95 section indices; the quadrature brackets come from the per-design table (the formula, with its
+// fifteen divisions, was 700 instructions streamed through the instruction cache once per configuration)
 __device__ __noinline__ void st_setup(const StModel& sm_, const int* idx, const double* theta, StCfg& c) {
     CTRB_USE_SM;
     const int T = sm.mc.T;
@@ -134,29 +161,19 @@ __device__ __noinline__ void st_setup(const StModel& sm_, const int* idx, const 
     c.L[1] = N[T - 2] - i22;
     c.L[2] = N[T - 1] - i33;
     for (int n = 0; n < 3; ++n) c.th[n] = n < T ? theta[n] : 0.0;
-    const double cs[2] = {(1.0 / sqrt(3.0) + 1.0) / 2.0, (-1.0 / sqrt(3.0) + 1.0) / 2.0};  // static.py:601-603
+#pragma unroll 1
     for (int s = 0; s < 3; ++s) {
         const int np = c.L[s];
-        const double length = (np - 1) * sm.mc.dx;
-        c.len[s] = length;
-        for (int a = 0; a < 2; ++a) {
-            c.lo[s][a] = c.hi[s][a] = 0;
-            c.wq[s][a] = 0.0;
-            if (!(length > 0.0)) continue;
-            const double step = length / (np - 1);  // np.linspace(0, length, num_points)
-            const double xn = cs[a] * length;
-            // searchsorted(x_vals, xn, side='left') clipped to [1, np-1]
-            int hi = (int)ceil(xn / step);
-            if (hi < 0) hi = 0;
-            if (hi > np - 1) hi = np - 1;
-            while (hi < np - 1 && ((hi == np - 1) ? length : hi * step) < xn) ++hi;
-            while (hi > 0 && (((hi - 1) == np - 1) ? length : (hi - 1) * step) >= xn) --hi;
-            if (hi < 1) hi = 1;
-            const int lo = hi - 1;
-            const double xlo = lo * step, xhi = (hi == np - 1) ? length : hi * step;
-            c.lo[s][a] = lo;
-            c.hi[s][a] = hi;
-            c.wq[s][a] = (xn - xlo) / (xhi - xlo);
+        if (np >= 0 && np <= sm.quad_max) {
+            const StQuad e = sm.quad_tab[np];
+            c.len[s] = e.len;
+            c.lo[s][0] = e.lo[0]; c.lo[s][1] = e.lo[1];
+            c.hi[s][0] = e.hi[0]; c.hi[s][1] = e.hi[1];
+            c.wq[s][0] = e.wq[0]; c.wq[s][1] = e.wq[1];
+        } else {  // indices outside the tubes (rejected by the API's validation before any launch)
+            c.len[s] = 0.0;
+            c.lo[s][0] = c.lo[s][1] = c.hi[s][0] = c.hi[s][1] = 0;
+            c.wq[s][0] = c.wq[s][1] = 0.0;
         }
     }
 }
