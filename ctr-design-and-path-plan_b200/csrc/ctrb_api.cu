@@ -418,6 +418,7 @@ void ctrb_model_destroy(ctrb_model* m) {
     cudaFree(m->d_ws_tab);
     cudaFree(m->d_b3_tab);
     cudaFree(m->d_quad_tab);
+    cudaFree(m->d_c33_tab);
     delete m;
 }
 

@@ -69,6 +69,8 @@ struct StModel {
     int b3_row[CTRB_MAX_DOF];      // the row of that non-zero
     const struct StQuad* quad_tab; // [max npts + 1]: calculate_integral's brackets for a section of np nodes (st_setup)
     int quad_max;                  // largest np in the table
+    const double* c33_tab;         // [npts_last]: block5_norm2 (the implicit last block's share of |D x|^2 from the default
+                                   // initial guess) by insertion index of the last tube -- it depends on nothing else
 };
 
 // calculate_integral (static.py:456-491) for a section of np nodes: the two abscissae's bracketing nodes, interp1d's
@@ -109,6 +111,7 @@ struct ctrb_model {
     double* d_ws_tab;
     double* d_b3_tab;
     ctrb::StQuad* d_quad_tab;
+    double* d_c33_tab;
     ctrb::ModelTables tables() const { return ctrb::ModelTables{d_tab, d_tab_inv, d_tabR32}; }
 };
 

@@ -38,6 +38,12 @@ namespace ctrb {
 // beyond 2 the larger code costs more instruction-cache misses than the saved loop overhead buys.
 #define CTRB_QR_UNROLL 2
 #endif
+// The implicit last block's constant: from the per-design table (as the fast kernel does) or evaluated per configuration.
+// Same value either way; the table is 2.6 % SLOWER here (2.64 vs 2.71 M cfg/s): with this kernel's iteration at ~48 KB of
+// code against a 32 KB instruction cache its speed follows the code layout more than the instruction count.
+#ifndef CTRB_QR_C33_TABLE
+#define CTRB_QR_C33_TABLE 0
+#endif
 #ifndef CTRB_QR_ITER_UNROLL
 #define CTRB_QR_ITER_UNROLL 2   // the same for the loops inside hybrd's iteration (dogleg, predicted reduction, Broyden vectors)
 #endif
@@ -303,10 +309,14 @@ __device__ __noinline__ void st_r1mpyq_row(int n, double* a, int lda, const doub
 __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
                                      double factor, bool reduced, int* nfev_out) {
     CTRB_USE_SM;
-    // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2)
+    // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2, tabulated per design)
     const int n = reduced ? sm.nq - sm.ndof[5] : sm.nq;
     const int nnodes = reduced ? 8 : 12;
+#if CTRB_QR_C33_TABLE
+    const double c33 = reduced ? sm.c33_tab[M.cfg.i33] : 0.0;
+#else
     const double c33 = reduced ? block5_norm2(sm, M.cfg, M.x, M.ybuf32(), lane) : 0.0;
+#endif
     const bool act = lane < n;
     const double epsmch = DBL_EPSILON, p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double* fjac = M.fjac;
@@ -625,6 +635,26 @@ __global__ void static_tables_kernel(StModel sm, double* __restrict__ ws, double
     }
 }
 
+// block5_norm2 for every insertion index of the last tube (one warp each), from the default initial guess
+__global__ void static_c33_kernel(StModel sm_, double* __restrict__ c33) {
+    load_model(sm_);
+    const StModel& sm = g_sm;
+    __shared__ StCfg cfg;
+    __shared__ double x[32], yb[32][16];
+    const int T = sm.mc.T, lane = threadIdx.x, i33 = blockIdx.x;
+    if (lane == 0) {
+        int idx[3] = {0, 0, 0};
+        double theta[3] = {0.0, 0.0, 0.0};
+        for (int n = 0; n < T; ++n) idx[n] = sm.mc.npts[n] > 2 ? sm.mc.npts[n] - 3 : 0;  // sections 1, 2 are not read
+        idx[T - 1] = i33;
+        st_setup(sm, idx, theta, cfg);
+    }
+    x[lane] = lane < sm.nq ? sm.x0[lane] : 0.0;
+    __syncwarp();
+    const double v = block5_norm2(sm, cfg, x, yb, lane);
+    if (lane == 0) c33[i33] = v;
+}
+
 // ------------------------------------------------------------------ host side
 int static_model_init(const ctrb_model_desc* d, const ModelConst& mc, StModel* out) {
     StModel sm;
@@ -688,6 +718,11 @@ int launch_static_tables(ctrb_ctx* ctx, ctrb_model* m) {
     m->sm.quad_max = quad_max;
     const int work = std::max(tot, quad_max + 1);
     static_tables_kernel<<<(work + 127) / 128, 128, 0, ctx->stream>>>(m->sm, m->d_ws_tab, m->d_b3_tab, m->d_quad_tab, quad_max + 1);
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
+    CTRB_CUDA(cudaMalloc(&m->d_c33_tab, (size_t)m->mc.npts[T - 1] * sizeof(double)));
+    static_c33_kernel<<<m->mc.npts[T - 1], 32, 0, ctx->stream>>>(m->sm, m->d_c33_tab);  // stream order: after the tables it reads
+    m->sm.c33_tab = m->d_c33_tab;
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());
     return CTRB_OK;

@@ -175,10 +175,10 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
     CTRB_USE_SM;
     CTRB_IN_SHARED(&M);
     CTRB_IN_SHARED(&st);
-    // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2)
+    // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2, tabulated per design)
     const int n = N ? N : (reduced ? sm.nq - sm.ndof[5] : sm.nq);
     const int nnodes = reduced ? 8 : 12;
-    const double c33 = reduced ? block5_norm2(sm, M.cfg, M.x, M.ybuf(), lane) : 0.0;
+    const double c33 = reduced ? sm.c33_tab[M.cfg.i33] : 0.0;
     const bool act = lane < n;
     const RowMeta rm = row_meta(sm, act ? lane : 0);
     const double epsmch = DBL_EPSILON, p1c = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
