@@ -668,9 +668,12 @@ __device__ __noinline__ SE3 integrate_section(const StModel& sm_, const StCfg& c
             sect_omega(sm, c, qs, sect, si + cg2 - 1, wB);
             e = magnus_step(wA, wB, dx);
         }
-        // inclusive scan of SE(3) products across lanes (Hillis-Steele)
+        // inclusive scan of SE(3) products across lanes (Hillis-Steele); only the first m lanes hold steps, and a round
+        // with off >= m changes none of them
+        const int m = min(32, count - base);
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
+            if (off >= m) break;
             SE3 o;
 #pragma unroll
             for (int t = 0; t < 9; ++t) o.r[t] = shfl_up_d(e.r[t], off);
