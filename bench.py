@@ -45,10 +45,10 @@ WORKLOADS = {  # name -> (model, exposure lo, hi, default configs per step per G
 }
 BYTES_PER_CONFIG = 3 * (4 + 8) + (8 + 8 + 8 + 1)  # idx + theta in, obstacle_min + goal_dist + cost + bit out
 # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (30000 C3 shallow configurations,
-# profiles/r1_ncu_final_four_kernels.json) divided by the configurations each kernel handled (22942 / 7058 / 30000);
-# the curves kernel's writes were still partly in the 126 MB L2 when the capture ended
-NCU_DRAM_BYTES_PER_CONFIG = {"static_fast_kernel": 51.0, "static_solve_kernel": 154.0, "static_curves_kernel": 887.0,
-                             "chain_eval_group_kernel<true>": 72.5}
+# profiles/r1_ncu_final_kernels_session4.json) divided by the configurations each kernel handled (22942 / 7058 / 30000;
+# 200000 for the fused kinematic kernel); the curves kernel's writes were still partly in the 126 MB L2 when the capture ended
+NCU_DRAM_BYTES_PER_CONFIG = {"static_fast_kernel": 50.2, "static_solve_kernel": 151.0, "static_curves_kernel": 780.0,
+                             "chain_eval_group_kernel<true>": 70.8}
 
 
 def make_inputs(B, seed, lo, hi):
@@ -342,7 +342,7 @@ def main():
         traffic = ((1 - fb) * NCU_DRAM_BYTES_PER_CONFIG["static_fast_kernel"]
                    + fb * NCU_DRAM_BYTES_PER_CONFIG["static_solve_kernel"] + NCU_DRAM_BYTES_PER_CONFIG["static_curves_kernel"]) * B
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_final_four_kernels.json, per configuration x launch size",
+                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_final_kernels_session4.json, per configuration x launch size",
                     "kernel": "static_fast_kernel + static_solve_kernel + static_curves_kernel (one launch sequence = Static.solve_g)",
                     "kernel_ms": k_ms, "fast_kernel_ms": float(np.mean(fast_ms)),
                     "qr_fallback_kernel_ms": k_ms - float(np.mean(fast_ms)), "qr_fallback_fraction": fb,
@@ -360,7 +360,7 @@ def main():
         achieved = BYTES_PER_CONFIG * B / (k_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": NCU_DRAM_BYTES_PER_CONFIG["chain_eval_group_kernel<true>"] * B,
-                    "traffic_source": "profiles/r1_ncu_final_four_kernels.json (200000 configurations), per configuration x launch size",
+                    "traffic_source": "profiles/r1_ncu_final_kernels_session4.json (200000 configurations), per configuration x launch size",
                     "kernel": "chain_eval_group_kernel<true>", "kernel_ms": k_ms,
                     "algorithmic_bytes_per_config": BYTES_PER_CONFIG, "peak_source": peak_src,
                     "note": "latency/compute-bound tree traversal: HBM traffic is ~61 B/config by construction; "
