@@ -394,17 +394,23 @@ int ctrb_model_create(ctrb_ctx* ctx, const ctrb_model_desc* d, ctrb_model** out)
         }
         m->is_static = 1;
     }
-    CTRB_CUDA(cudaSetDevice(ctx->device));
-    CTRB_CUDA(cudaMalloc(&m->d_tab, (size_t)12 * tot * sizeof(double)));
-    CTRB_CUDA(cudaMalloc(&m->d_tab_inv, (size_t)12 * tot * sizeof(double)));
-    CTRB_CUDA(cudaMalloc(&m->d_tabR32, (size_t)9 * tot * sizeof(float)));
-    int rc = launch_table(ctx, m);
-    if (rc == CTRB_OK && m->is_static) rc = launch_static_tables(ctx, m);
+    // every failure below releases the handle and whatever it already owns (ctrb_model_destroy frees null pointers too)
+    auto build = [&]() -> int {
+        CTRB_CUDA(cudaSetDevice(ctx->device));
+        CTRB_CUDA(cudaMalloc(&m->d_tab, (size_t)12 * tot * sizeof(double)));
+        CTRB_CUDA(cudaMalloc(&m->d_tab_inv, (size_t)12 * tot * sizeof(double)));
+        CTRB_CUDA(cudaMalloc(&m->d_tabR32, (size_t)9 * tot * sizeof(float)));
+        int rc = launch_table(ctx, m);
+        if (rc == CTRB_OK && m->is_static) rc = launch_static_tables(ctx, m);
+        if (rc) return rc;
+        CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return CTRB_OK;
+    };
+    const int rc = build();
     if (rc) {
         ctrb_model_destroy(m);
         return rc;
     }
-    CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = m;
     return CTRB_OK;
 }
