@@ -416,7 +416,7 @@ int launch_static_fast(ctrb_ctx* ctx, const StModel& sm, long long B, const int3
                        double* sol_out, int32_t* nfev_out, int32_t* info_out, long long* fb_list,
                        unsigned long long* fb_count, unsigned long long* ticket) {
     const int n = x0 == nullptr ? sm.nq - sm.ndof[5] : sm.nq;  // as fast_hybrd derives it
-    static const bool generic = getenv("CTRB_FAST_GENERIC_N") != nullptr;
+    const bool generic = getenv("CTRB_FAST_GENERIC_N") != nullptr;  // read per call: the parity test toggles it
 #define CTRB_FAST_ARGS ctx, sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out, sol_out, nfev_out, info_out, fb_list, fb_count, ticket
     if (!generic) {
         switch (n) {

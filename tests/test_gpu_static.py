@@ -180,3 +180,33 @@ def test_static_fused_eval():
         checked += 1
     assert checked > 100
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_two_tube", "c3_three_tube"])
+def test_fast_kernel_instantiations_agree(name, monkeypatch):
+    """static_fast_kernel is instantiated per system size (27 / 30 unknowns for three tubes, 12 / 15 for two; loops
+    unrolled) with a run-time-n instantiation for every other size: both must give the same iterates bit for bit, from
+    the default initial guess (reduced system) and from a caller-supplied one (full system)."""
+    m = gpu_static(name)
+    N = np.asarray(m.num_discrete_points)
+    T = m.tube_num
+    rng = np.random.default_rng(3003)
+    B = 400
+    e = np.stack([rng.integers(2, min(12, N[t] - 1) + 1, B) for t in range(T)], 1)
+    idx = (N[None, :] - 1 - e).astype(np.int32)
+    th = rng.uniform(0, 2 * np.pi, (B, T))
+    guess = np.tile(m.general_init_guess, (B, 1)) * (1.0 + 1e-3 * rng.standard_normal((B, m.num_unknowns)))
+    for x0 in (None, guess):
+        monkeypatch.delenv("CTRB_FAST_GENERIC_N", raising=False)
+        a = m.solve_g_batch(idx, th, initial_guess=x0)
+        fb_a = m.ctx.static_fallbacks()
+        monkeypatch.setenv("CTRB_FAST_GENERIC_N", "1")
+        b = m.solve_g_batch(idx, th, initial_guess=x0)
+        assert m.ctx.static_fallbacks() == fb_a
+        assert fb_a <= 0.05 * B  # the batch is solved by the fast kernel, not handed to the QR kernel
+        np.testing.assert_array_equal(a["info"], b["info"])
+        np.testing.assert_array_equal(a["nfev"], b["nfev"])
+        np.testing.assert_array_equal(a["solution"], b["solution"])
+        np.testing.assert_array_equal(a["g"], b["g"])
+        assert a["converged"].mean() > 0.9
