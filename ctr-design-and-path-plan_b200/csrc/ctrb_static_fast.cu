@@ -54,6 +54,10 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef CTRB_INV_UNROLL
 #define CTRB_INV_UNROLL 3
 #endif
+#ifndef CTRB_BLOCK_INVERT
+#define CTRB_BLOCK_INVERT 1
+#endif
+constexpr bool kBlockInvert = CTRB_BLOCK_INVERT != 0;
 constexpr int kMvUnroll = CTRB_MV_UNROLL, kR1Unroll = CTRB_R1_UNROLL, kInvUnroll = CTRB_INV_UNROLL;
 
 struct alignas(16) FastMem {
@@ -110,6 +114,149 @@ __device__ __noinline__ double matvec_col(const double* M, const double* v, int 
 }
 
 __device__ __forceinline__ double wnorm(double v) { return sqrt(warp_sum(v * v)); }
+
+// H = J^-1 for the three-tube system from the default initial guess (27 unknowns) through its block structure.  The
+// forward-difference Jacobian is block tridiagonal with blocks of 12 (section 1: blocks (1,1), (2,1)), 3 (the (3,1)
+// torsion, which also turns the frame section 2 starts from) and 12 (section 2: blocks (2,2), (3,2)) unknowns, with
+// exact zeros in the two off-corner 12 x 12 blocks (warp_fdjac writes them as 0.0):
+//     J = [A11 A12 0; A21 A22 A23; 0 A32 A33],   J^-1 = diag(P, 0, Q) + W S^-1 Z,   P = A11^-1, Q = A33^-1,
+//     W = [P A12; -I; Q A32],  Z = [A21 P, -I, A23 Q],  S = A22 - A21 P A12 - A23 Q A32  (3 x 3).
+// P and Q are found together, one per half-warp (rows 0..11 on lanes 0..11, rows 15..26 on lanes 16..27), by the same
+// exchange steps as fast_invert: 12 steps on 12 columns instead of 27 on 27.  Returns false when any pivot (or S) is
+// small; the caller then runs the general Gauss-Jordan, which decides whether the Jacobian is singular.
+__device__ __noinline__ bool fast_invert_block27(FastMem& M, double acnorm_l, int lane) {
+    CTRB_IN_SHARED(&M);
+    constexpr int n = 27, nb = 12, c2 = 12;  // c2: first row / column of the middle block
+    double* Tm = M.H;
+    const double* Jm = M.J;
+    for (int e = lane; e < kLD * n; e += 32) Tm[e] = Jm[e];
+    __syncwarp();
+    const int half = lane >> 4, li = lane & 15;
+    const bool act = li < nb;
+    const int cb = half ? 15 : 0;          // first row / column of this half-warp's diagonal block
+    const int row = cb + (act ? li : 0);   // this lane's row (and, where lane = column, its column)
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+    bool used = false;
+    int mycol = 0, prow = 0;               // block-local: the column this row pivoted; the pivot row of column li
+#pragma unroll 1
+    for (int k = 0; k < nb; ++k) {
+        const double a = act ? Tm[row + (cb + k) * kLD] : 0.0;
+        const unsigned long long key = (act && !used) ? (unsigned long long)__double_as_longlong(fabs(a)) : 0ULL;
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mh = __reduce_max_sync(hmask, hi);
+        const unsigned ml = __reduce_max_sync(hmask, hi == mh ? lo : 0u);
+        const int r = __ffs(__ballot_sync(kFull, hi == mh && lo == ml && act && !used) & hmask) - 1;  // pivot lane
+        const double thr = 1e-12 * __shfl_sync(kFull, acnorm_l, cb + k);
+        const double piv = __shfl_sync(kFull, a, r < 0 ? 0 : r);
+        const bool ok = r >= 0 && fabs(piv) > thr && fabs(piv) < 1.7e308;
+        if (!__all_sync(kFull, ok)) return false;
+        const int rrow = cb + (r & 15);
+        const double ipiv = 1.0 / piv;
+        const double m = (lane == r) ? 0.0 : a * ipiv;
+        if (act && lane != r) {
+            const double* pr = Tm + rrow + cb * kLD;
+            double* tr = Tm + row + cb * kLD;
+#pragma unroll 3
+            for (int j = 0; j < nb; ++j) tr[j * kLD] = fma(-m, pr[j * kLD], tr[j * kLD]);
+        }
+        __syncwarp();
+        if (act) Tm[rrow + row * kLD] *= ipiv;  // lane = column of the pivot row
+        __syncwarp();
+        if (act) Tm[row + (cb + k) * kLD] = (lane == r) ? ipiv : -m;
+        __syncwarp();
+        if (lane == r) {
+            used = true;
+            mycol = k;
+        }
+        if (act && li == k) prow = r & 15;
+    }
+    {   // unscramble: P[mycol(i)][prow(j)] = T[i][j] inside each diagonal block
+        double rv[nb];
+#pragma unroll
+        for (int j = 0; j < nb; ++j) rv[j] = act ? Tm[row + (cb + j) * kLD] : 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < nb; ++j) {
+            const int pj = __shfl_sync(kFull, prow, (half << 4) + j);
+            if (act) Tm[(cb + mycol) + (cb + pj) * kLD] = rv[j];
+        }
+        __syncwarp();
+    }
+    // u = this row of P A12 (Q A32), v = this column of A21 P (A23 Q)
+    double u0 = 0.0, u1 = 0.0, u2 = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    if (act) {
+        const double* pr = Tm + row + cb * kLD;           // row of P / Q
+        const double* pc = Tm + cb + row * kLD;           // column of P / Q
+        const double* a12 = Jm + cb + c2 * kLD;           // A12 / A32: rows cb.., columns 12..14
+        const double* a21 = Jm + c2 + cb * kLD;           // A21 / A23: rows 12..14, columns cb..
+#pragma unroll 3
+        for (int j = 0; j < nb; ++j) {
+            const double p = pr[j * kLD], q = pc[j];
+            u0 = fma(p, a12[j], u0);
+            u1 = fma(p, a12[j + kLD], u1);
+            u2 = fma(p, a12[j + 2 * kLD], u2);
+            v0 = fma(a21[j * kLD], q, v0);
+            v1 = fma(a21[j * kLD + 1], q, v1);
+            v2 = fma(a21[j * kLD + 2], q, v2);
+        }
+    }
+    // S = A22 - A21 (P A12) - A23 (Q A32): the sums run over the rows of both diagonal blocks, i.e. over the lanes
+    double S[3][3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const double ab = act ? Jm[(c2 + b) + row * kLD] : 0.0;  // A21[b][i] / A23[b][i]
+        S[b][0] = Jm[(c2 + b) + (c2 + 0) * kLD] - warp_sum(ab * u0);
+        S[b][1] = Jm[(c2 + b) + (c2 + 1) * kLD] - warp_sum(ab * u1);
+        S[b][2] = Jm[(c2 + b) + (c2 + 2) * kLD] - warp_sum(ab * u2);
+    }
+    // G = S^-1 by the adjugate (every lane; S is the same in all of them)
+    const double c00 = S[1][1] * S[2][2] - S[1][2] * S[2][1], c01 = S[1][2] * S[2][0] - S[1][0] * S[2][2],
+                 c02 = S[1][0] * S[2][1] - S[1][1] * S[2][0];
+    const double det = S[0][0] * c00 + S[0][1] * c01 + S[0][2] * c02;
+    double scale = 1.0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) scale *= fmax(fabs(S[b][0]), fmax(fabs(S[b][1]), fabs(S[b][2])));
+    if (!(fabs(det) > 1e-10 * scale) || !(fabs(det) < 1.7e308)) return false;
+    const double idet = 1.0 / det;
+    double G[3][3];
+    G[0][0] = c00 * idet;
+    G[1][0] = c01 * idet;
+    G[2][0] = c02 * idet;
+    G[0][1] = (S[0][2] * S[2][1] - S[0][1] * S[2][2]) * idet;
+    G[1][1] = (S[0][0] * S[2][2] - S[0][2] * S[2][0]) * idet;
+    G[2][1] = (S[0][1] * S[2][0] - S[0][0] * S[2][1]) * idet;
+    G[0][2] = (S[0][1] * S[1][2] - S[0][2] * S[1][1]) * idet;
+    G[1][2] = (S[0][2] * S[1][0] - S[0][0] * S[1][2]) * idet;
+    G[2][2] = (S[0][0] * S[1][1] - S[0][1] * S[1][0]) * idet;
+    // back to lane = row / column i of the full matrix: rows 15..26 sit one lane higher
+    const int src = lane >= 15 ? lane + 1 : lane;
+    const bool midl = lane >= c2 && lane < c2 + 3;
+    double w0 = __shfl_sync(kFull, u0, src), w1 = __shfl_sync(kFull, u1, src), w2 = __shfl_sync(kFull, u2, src);
+    double z0 = __shfl_sync(kFull, v0, src), z1 = __shfl_sync(kFull, v1, src), z2 = __shfl_sync(kFull, v2, src);
+    if (midl) {  // W and Z carry -I in the middle block
+        w0 = lane == c2 ? -1.0 : 0.0; w1 = lane == c2 + 1 ? -1.0 : 0.0; w2 = lane == c2 + 2 ? -1.0 : 0.0;
+        z0 = w0; z1 = w1; z2 = w2;
+    }
+    M.va[lane] = z0;
+    M.vb[lane] = z1;
+    M.vc[lane] = z2;
+    __syncwarp();
+    if (lane < n) {
+        const double t0 = fma(w0, G[0][0], fma(w1, G[1][0], w2 * G[2][0]));
+        const double t1 = fma(w0, G[0][1], fma(w1, G[1][1], w2 * G[2][1]));
+        const double t2 = fma(w0, G[0][2], fma(w1, G[1][2], w2 * G[2][2]));
+        double* hr = Tm + lane;
+        const bool top = lane < nb, bot = lane >= 15;
+#pragma unroll 3
+        for (int j = 0; j < n; ++j) {
+            const bool diag = (top && j < nb) || (bot && j >= 15);
+            const double d = diag ? hr[j * kLD] : 0.0;
+            hr[j * kLD] = fma(t0, M.va[j], fma(t1, M.vb[j], fma(t2, M.vc[j], d)));
+        }
+    }
+    __syncwarp();
+    return true;
+}
 
 // H = J^-1 by Gauss-Jordan exchange steps with implicit partial pivoting; lane = row.  Returns false when a
 // pivot falls below 1e-12 of its column norm (numerically singular Jacobian).
@@ -195,7 +342,10 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
         bool jeval = true;
         const double acnorm_l = warp_fdjac(sm, M.cfg, st, rm, M.x, M.J, M.ybuf(), f_l, pa, pb, n, lane);
         nfev += sm.nq;  // MINPACK's count: one evaluation per unknown
-        if (!fast_invert<N>(M, n, acnorm_l, lane)) return -1;
+        // three tubes from the default initial guess: block-structured inverse; anything it declines (a small pivot)
+        // goes through the general Gauss-Jordan, which alone decides what is handed to the QR kernel
+        const bool blocked = kBlockInvert && reduced && n == 27 && sm.mc.T == 3 && fast_invert_block27(M, acnorm_l, lane);
+        if (!blocked && !fast_invert<N>(M, n, acnorm_l, lane)) return -1;
         if (iter == 1) {
             diag_l = acnorm_l == 0.0 ? 1.0 : acnorm_l;
             xnorm = sqrt(warp_sum(act ? (diag_l * x_l) * (diag_l * x_l) : 0.0) + c33);
