@@ -312,6 +312,10 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
     // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2, tabulated per design)
     const int n = reduced ? sm.nq - sm.ndof[5] : sm.nq;
     const int nnodes = reduced ? 8 : 12;
+    // Three tubes from the default initial guess: the forward-difference Jacobian is block tridiagonal (12 | 3 | 12
+    // unknowns, exact zeros in the two corner blocks, see fast_invert_block27), so the Householder vectors of the first
+    // 12 columns end at row 14.  The loops over them stop there: the skipped terms are products with exact zeros.
+    const bool tri = reduced && n == 27 && sm.mc.T == 3;
 #if CTRB_QR_C33_TABLE
     const double c33 = reduced ? sm.c33_tab[M.cfg.i33] : 0.0;
 #else
@@ -359,12 +363,13 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
                 if (lane == 0) fjac[j + j * kNP] += 1;
                 __syncwarp();
                 if (lane > j && act) {  // lane = column k
+                    const int iend = (tri && j < 12) ? 15 : n;  // rows 15.. of this Householder vector are exact zeros
                     double sum = 0;
 #pragma unroll kQrUnroll
-                    for (int i = j; i < n; ++i) sum += fjac[i + j * kNP] * fjac[i + lane * kNP];
+                    for (int i = j; i < iend; ++i) sum += fjac[i + j * kNP] * fjac[i + lane * kNP];
                     const double temp = sum / fjac[j + j * kNP];
 #pragma unroll kQrUnroll
-                    for (int i = j; i < n; ++i) fjac[i + lane * kNP] -= temp * fjac[i + j * kNP];
+                    for (int i = j; i < iend; ++i) fjac[i + lane * kNP] -= temp * fjac[i + j * kNP];
                 }
             }
             if (lane == 0) M.wa1[j] = -ajnorm;
@@ -409,12 +414,13 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
             __syncwarp();
             if (M.wa3[k] != 0) {
                 if (lane >= k && act) {
+                    const int iend = (tri && k < 12) ? 15 : n;  // wa3 = Householder vector k: exact zeros from row 15 on
                     double sum = 0;
 #pragma unroll kQrUnroll
-                    for (int i = k; i < n; ++i) sum += fjac[i + lane * kNP] * M.wa3[i];
+                    for (int i = k; i < iend; ++i) sum += fjac[i + lane * kNP] * M.wa3[i];
                     const double temp = sum / M.wa3[k];
 #pragma unroll kQrUnroll
-                    for (int i = k; i < n; ++i) fjac[i + lane * kNP] -= temp * M.wa3[i];
+                    for (int i = k; i < iend; ++i) fjac[i + lane * kNP] -= temp * M.wa3[i];
                 }
             }
             __syncwarp();
