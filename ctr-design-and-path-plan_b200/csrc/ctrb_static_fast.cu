@@ -318,7 +318,7 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n_rt, double acnorm_l, 
 // configuration has to go through the QR kernel
 template <int N>
 __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
-                                       double factor, bool reduced, int* nfev_out) {
+                                       double factor, bool reduced, bool allow_block, int* nfev_out) {
     CTRB_USE_SM;
     CTRB_IN_SHARED(&M);
     CTRB_IN_SHARED(&st);
@@ -344,7 +344,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
         nfev += sm.nq;  // MINPACK's count: one evaluation per unknown
         // three tubes from the default initial guess: block-structured inverse; anything it declines (a small pivot)
         // goes through the general Gauss-Jordan, which alone decides what is handed to the QR kernel
-        const bool blocked = kBlockInvert && reduced && n == 27 && sm.mc.T == 3 && fast_invert_block27(M, acnorm_l, lane);
+        const bool blocked = kBlockInvert && allow_block && reduced && n == 27 && sm.mc.T == 3 && fast_invert_block27(M, acnorm_l, lane);
         if (!blocked && !fast_invert<N>(M, n, acnorm_l, lane)) return -1;
         if (iter == 1) {
             diag_l = acnorm_l == 0.0 ? 1.0 : acnorm_l;
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
                        const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                        double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
                        int32_t* __restrict__ info_out, long long* __restrict__ fb_list,
-                       unsigned long long* __restrict__ fb_count, unsigned long long* __restrict__ ticket) {
+                       unsigned long long* __restrict__ fb_count, unsigned long long* __restrict__ ticket, int allow_block) {
     load_model(sm_);
     const StModel& sm = g_sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
         // and a one-step section 1 or 2 gives the x and x^2 curvature coefficients identical columns
         const bool degenerate = (T == 3 && c.L[0] < 3) || c.L[1] < 3 || c.L[2] < 2;
         int nfev = 0;
-        const int info = degenerate ? -1 : fast_hybrd<N>(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, &nfev);
+        const int info = degenerate ? -1 : fast_hybrd<N>(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, allow_block != 0, &nfev);
         __syncwarp();
         if (info < 0) {
             if (lane == 0) fb_list[atomicAdd(fb_count, 1ULL)] = b;
@@ -545,6 +545,9 @@ static int launch_static_fast_n(ctrb_ctx* ctx, const StModel& sm, long long B, c
                                 const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
                                 double* sol_out, int32_t* nfev_out, int32_t* info_out, long long* fb_list,
                                 unsigned long long* fb_count, unsigned long long* ticket) {
+    // CTRB_FAST_BLOCK_INVERT=0: the general Gauss-Jordan inverse for every configuration (parity test of the block-structured one)
+    const char* be = getenv("CTRB_FAST_BLOCK_INVERT");
+    const int allow_block = !(be && atoi(be) == 0);
     const size_t smem = sizeof(FastMem) * kFWarps;
     CTRB_CUDA(cudaFuncSetAttribute(static_fast_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
@@ -552,7 +555,7 @@ static int launch_static_fast_n(ctrb_ctx* ctx, const StModel& sm, long long B, c
     const long long blocks_needed = (B + kFWarps - 1) / kFWarps;
     const int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * std::max(per_sm, 1));
     static_fast_kernel<N><<<grid, kFWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out,
-                                                                    sol_out, nfev_out, info_out, fb_list, fb_count, ticket);
+                                                                    sol_out, nfev_out, info_out, fb_list, fb_count, ticket, allow_block);
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());
     return CTRB_OK;
