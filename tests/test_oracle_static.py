@@ -68,3 +68,36 @@ def test_hybrd_restatement(gs, name):
             # iteration follows the same path except where rounding flips a trust-region decision
             if tag == "default":
                 assert abs(nfev + 2 - nfev_ref) <= 0.4 * nfev_ref, (name, c, tag, nfev, nfev_ref)
+
+
+def test_three_tube_jacobian_is_block_tridiagonal():
+    """The structure the CUDA kernels rely on (fast_invert_block27, the QR kernel's shortened Householder loops, the
+    sparse forward-difference Jacobian): for three tubes the residual blocks of section 1 -- (1,1), (2,1) -- do not
+    depend on the unknowns of section 2 -- (2,2), (3,2) -- and vice versa, the last block (3,3) is coupled to nothing,
+    and only the (3,1) torsion touches both sections.  Checked on the marched residual of the reference (its C port):
+    perturbing an unknown leaves the uncoupled residual components EXACTLY unchanged (static.py:261-454).  The same
+    check run once on the Python reference itself (ctrdapp.model.static.Static.static_equilibrium imported from the
+    reference tree in the dev container, configurations [26, 63, 96] and [28, 58, 95]) gives the same pattern."""
+    s, _ = _model("c3_three_tube")
+    x0 = orc.static_init_guess(s)
+    assert x0.size == 30
+    sec1, mid, sec2, last = range(0, 12), range(12, 15), range(15, 27), range(27, 30)
+    rng = np.random.default_rng(5005)
+    N = [34, 67, 100]
+    for _ in range(12):
+        e = rng.integers(2, 13, 3)
+        idx = [N[t] - 1 - int(e[t]) for t in range(3)]
+        th = rng.uniform(0, 2 * np.pi, 3)
+        x = x0 * (1.0 + 0.05 * rng.standard_normal(30)) + 1e-3 * rng.standard_normal(30)
+        F = orc.static_residual(s, idx, th, x)
+        coupled = np.zeros((30, 30), bool)
+        for j in range(30):
+            xp = x.copy()
+            xp[j] += 1e-4 * max(1.0, abs(x[j]))
+            coupled[:, j] = orc.static_residual(s, idx, th, xp) != F
+        assert not coupled[np.ix_(sec1, sec2)].any()     # section-1 rows, section-2 unknowns
+        assert not coupled[np.ix_(sec2, sec1)].any()     # section-2 rows, section-1 unknowns of tubes 1 and 2
+        assert not coupled[np.ix_(range(27), last)].any() and not coupled[np.ix_(last, range(27))].any()
+        assert coupled[np.ix_(mid, sec1)].any() and coupled[np.ix_(mid, sec2)].any()      # the (3,1) rows see both
+        assert coupled[np.ix_(sec1, mid)].any() and coupled[np.ix_(sec2, mid)].any()      # and both see the (3,1) torsion
+        assert coupled[np.ix_(sec1, sec1)].any() and coupled[np.ix_(sec2, sec2)].any() and coupled[np.ix_(last, last)].any()
