@@ -101,3 +101,23 @@ def test_three_tube_jacobian_is_block_tridiagonal():
         assert coupled[np.ix_(mid, sec1)].any() and coupled[np.ix_(mid, sec2)].any()      # the (3,1) rows see both
         assert coupled[np.ix_(sec1, mid)].any() and coupled[np.ix_(sec2, mid)].any()      # and both see the (3,1) torsion
         assert coupled[np.ix_(sec1, sec1)].any() and coupled[np.ix_(sec2, sec2)].any() and coupled[np.ix_(last, last)].any()
+
+
+def test_block_tridiagonal_inverse_formula():
+    """The algebra of fast_invert_block27 (ctrb_static_fast.cu), in NumPy: for J = [A11 A12 0; A21 A22 A23; 0 A32 A33]
+    with blocks of 12, 3 and 12,  J^-1 = diag(P, 0, Q) + W S^-1 Z  with P = A11^-1, Q = A33^-1, W = [P A12; -I; Q A32],
+    Z = [A21 P, -I, A23 Q], S = A22 - A21 P A12 - A23 Q A32."""
+    rng = np.random.default_rng(6006)
+    for _ in range(20):
+        J = rng.standard_normal((27, 27))
+        J[0:12, 15:27] = 0.0
+        J[15:27, 0:12] = 0.0
+        A12, A21, A22, A23, A32 = J[0:12, 12:15], J[12:15, 0:12], J[12:15, 12:15], J[12:15, 15:27], J[15:27, 12:15]
+        P, Q = np.linalg.inv(J[0:12, 0:12]), np.linalg.inv(J[15:27, 15:27])
+        S = A22 - A21 @ P @ A12 - A23 @ Q @ A32
+        W = np.vstack([P @ A12, -np.eye(3), Q @ A32])
+        Z = np.hstack([A21 @ P, -np.eye(3), A23 @ Q])
+        H = W @ np.linalg.inv(S) @ Z
+        H[0:12, 0:12] += P
+        H[15:27, 15:27] += Q
+        assert np.max(np.abs(H @ J - np.eye(27))) < 1e-9 * np.linalg.cond(J)
