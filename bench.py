@@ -51,6 +51,14 @@ NCU_DRAM_BYTES_PER_CONFIG = {"static_fast_kernel": 50.2, "static_solve_kernel": 
                              "chain_eval_group_kernel<true>": 70.8}
 
 
+def workload_description(kind):
+    """model / environment strings shared by both arms' `config` (the reference arm runs the same workload on the CPU)"""
+    model = (f"3-tube {kind} (linear bases, q_dof [2,3,3]), tube_lengths [33,66,99], delta_x 1"
+             + (", last_strain_base degree 2, 30 unknowns, MINPACK hybrd xtol 1.49e-8" if kind == "static" else ""))
+    env = "colon_straight.STL (11492 triangles) translated to a mid-lumen pose + Sphere(5) goal"
+    return model, env
+
+
 def make_inputs(B, seed, lo, hi):
     rng = np.random.default_rng(seed)
     e = np.stack([rng.integers(lo, min(hi, NPTS[t] - 1) + 1, B) for t in range(3)], 1)
@@ -144,12 +152,14 @@ def run_reference(args, rank):
     ms = 1e3 * float(np.mean(times))
     value = args.ref_sample / (ms * 1e-3)
     sample = f"{args.ref_sample} configs/step of {args.workload} (seed 1003), collide fraction {(obs < 0).mean():.3f}"
+    model_s, env_s = workload_description(kind)
     line = {"impl": "reference", "metric": "configs/sec (g-curve + collision + cost)", "value": value,
             "unit": "configs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": args.workload, "configs_per_step": args.ref_sample,
-                                            "model": f"3-tube {kind}, 100 arc-length nodes",
-                                            "environment": "colon_straight.STL (11492 triangles), mid-lumen pose"},
+                                            "model": model_s, "environment": env_s, "exposure_per_tube": [lo, hi],
+                                            "collide_fraction": float((obs < 0).mean()),
+                                            "parallelism": f"{threads} host threads (pthreads), bounded sample of the workload"},
             "cpu_baseline": {"value": value, "unit": "configs/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "configs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -455,9 +465,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "configs_per_step_per_gpu": B,
-                       "model": f"3-tube {kind} (linear bases, q_dof [2,3,3]), tube_lengths [33,66,99], delta_x 1"
-                                + (", last_strain_base degree 2, 30 unknowns, MINPACK hybrd xtol 1.49e-8" if kind == "static" else ""),
-                       "environment": "colon_straight.STL (11492 triangles) translated to a mid-lumen pose + Sphere(5) goal",
+                       "model": workload_description(kind)[0], "environment": workload_description(kind)[1],
                        "exposure_per_tube": [lo, hi], "collide_fraction": collide_frac,
                        "l2": f"per step {BYTES_PER_CONFIG * B / 1e6:.0f} MB of inputs+outputs"
                              + (f" + {128 * 30 * B / 1e6:.0f} MB of section curves" if kind == "static" else "")
