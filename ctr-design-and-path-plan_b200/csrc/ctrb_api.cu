@@ -63,13 +63,15 @@ int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube
 int launch_argmin(ctrb_ctx* ctx, long long B, const double* cost, unsigned long long* key_out);
 int launch_eval_curves_cost(ctrb_ctx* ctx, const ctrb_env* env, const ctrb_cost_desc* cd, long long B, int tube_num,
                             const double* g, const long long* offsets, int max_nodes, const double* rad,
-                            double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide);
+                            double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide, int pos_only);
 int launch_fma_peak(ctrb_ctx* ctx, int precision, double* tflops);
 int static_model_init(const ctrb_model_desc* d, const ModelConst& mc, StModel* out);
 int launch_static_tables(ctrb_ctx* ctx, ctrb_model* m);
 int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
                         const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
-                        double* sol_out, int32_t* nfev_out, int32_t* info_out);
+                        double* sol_out, int32_t* nfev_out, int32_t* info_out, int pos_only);
+int launch_static_curves(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
+                         const double* sol, const long long* offsets, double* g_out, int pos_only);
 int launch_static_residual(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
                            const double* q, double* F);
 
@@ -229,7 +231,7 @@ int ctrb_ctx_create(int device, ctrb_ctx** out) {
         CTRB_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
         CTRB_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < 8; ++k)
         for (int i = 0; i < 2; ++i) {
             CTRB_CUDA(cudaEventCreate(&c->kev[k][i]));
             CTRB_CUDA(cudaEventRecord(c->kev[k][i], c->stream));
@@ -239,6 +241,9 @@ int ctrb_ctx_create(int device, ctrb_ctx** out) {
     cudaDeviceProp prop;
     CTRB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->opt[CTRB_OPT_FAST_BLOCK_INVERT] = 1;
+    c->opt[CTRB_OPT_EVAL_GROUP] = 1;
+    c->opt[CTRB_OPT_GCURVE_BLOCKS] = 3;
     if (prop.major < 10) {
         set_error("device %d is sm_%d%d; libctrb200 is built for sm_100a only", device, prop.major, prop.minor);
         delete c;
@@ -261,7 +266,7 @@ void ctrb_ctx_destroy(ctrb_ctx* c) {
         cudaEventDestroy(c->ev_chunk[i]);
         cudaEventDestroy(c->ev_done[i]);
     }
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < 8; ++k)
         for (int i = 0; i < 2; ++i) cudaEventDestroy(c->kev[k][i]);
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->stream2);
@@ -281,6 +286,22 @@ int ctrb_ctx_set_stream(ctrb_ctx* c, void* cuda_stream) {
     CTRB_CUDA(cudaSetDevice(c->device));
     CTRB_CUDA(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return CTRB_OK;
+}
+
+int ctrb_ctx_set_option(ctrb_ctx* c, int option, int value) {
+    CTRB_REQUIRE(c, "ctx is NULL");
+    CTRB_REQUIRE(option >= 0 && option < CTRB_OPT_COUNT, "unknown option %d", option);
+    if (option == CTRB_OPT_GCURVE_BLOCKS) CTRB_REQUIRE(value >= 1 && value <= 32, "CTRB_OPT_GCURVE_BLOCKS must be in [1, 32]");
+    else CTRB_REQUIRE(value == 0 || value == 1, "option %d takes 0 or 1", option);
+    c->opt[option] = value;
+    return CTRB_OK;
+}
+
+int ctrb_ctx_get_option(const ctrb_ctx* c, int option, int* value) {
+    CTRB_REQUIRE(c && value, "bad argument");
+    CTRB_REQUIRE(option >= 0 && option < CTRB_OPT_COUNT, "unknown option %d", option);
+    *value = c->opt[option];
     return CTRB_OK;
 }
 
@@ -309,7 +330,7 @@ int ctrb_ctx_elapsed_ms(ctrb_ctx* c, float* ms) {
 }
 
 int ctrb_ctx_last_kernel_ms(ctrb_ctx* c, int kernel_id, float* ms) {
-    CTRB_REQUIRE(c && ms && kernel_id >= 0 && kernel_id < 5, "ctrb_ctx_last_kernel_ms: bad argument");
+    CTRB_REQUIRE(c && ms && kernel_id >= 0 && kernel_id < 7, "ctrb_ctx_last_kernel_ms: bad argument");
     CTRB_CUDA(cudaSetDevice(c->device));
     CTRB_CUDA(cudaEventSynchronize(c->kev[kernel_id][1]));
     CTRB_CUDA(cudaEventElapsedTime(ms, c->kev[kernel_id][0], c->kev[kernel_id][1]));
@@ -321,7 +342,7 @@ int ctrb_static_last_fallbacks(ctrb_ctx* c, uint64_t* count) {
     CTRB_CUDA(cudaSetDevice(c->device));
     CTRB_CUDA(cudaStreamSynchronize(c->stream));
     unsigned long long h = 0;
-    CTRB_CUDA(cudaMemcpy(&h, c->d_counters + 10, sizeof h, cudaMemcpyDeviceToHost));
+    CTRB_CUDA(cudaMemcpy(&h, c->d_counters + 11, sizeof h, cudaMemcpyDeviceToHost));
     *count = h;
     return CTRB_OK;
 }
@@ -810,9 +831,10 @@ int ctrb_static_solve_g_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, con
     CTRB_REQUIRE(idx && theta, "NULL buffer");
     CTRB_REQUIRE(!g_out || node_offsets, "g_out needs node_offsets");
     const size_t n = (size_t)B * m->mc.T, nqs = (size_t)B * m->sm.nq;
+    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 11, 0, sizeof(unsigned long long), ctx->stream));
     if (mem == CTRB_MEM_DEVICE) {
         return launch_static_solve(ctx, m->sm, B, idx, theta, initial_guess, x0_per_config, xtol,
-                                   (const long long*)node_offsets, g_out, solution_q, nfev, info);
+                                   (const long long*)node_offsets, g_out, solution_q, nfev, info, 0);
     }
     int rc = check_idx_host(m, B, idx);
     if (rc) return rc;
@@ -833,12 +855,40 @@ int ctrb_static_solve_g_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, con
         if (rc) return rc;
     }
     rc = launch_static_solve(ctx, m->sm, B, di, dt, dx0, x0_per_config, xtol, (const long long*)doff, (double*)dg, dsol, dnf,
-                             dinf);
+                             dinf, 0);
     if (rc) return rc;
     st.back(solution_q, dsol, nqs, mem);
     st.back(nfev, dnf, (size_t)B, mem);
     st.back(info, dinf, (size_t)B, mem);
     if (g_out) CTRB_CUDA(cudaMemcpyAsync(g_out, dg, total_nodes * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return st.finish(mem);
+}
+
+int ctrb_static_curves_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx, const double* theta,
+                             const double* q, const int64_t* node_offsets, double* g_out, int mem) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(m && B >= 0, "bad argument");
+    CTRB_REQUIRE(m->is_static, "not a static model handle");
+    if (B == 0) return CTRB_OK;
+    CTRB_REQUIRE(idx && theta && q && node_offsets && g_out, "NULL buffer");
+    const size_t n = (size_t)B * m->mc.T, nqs = (size_t)B * m->sm.nq;
+    if (mem == CTRB_MEM_DEVICE)
+        return launch_static_curves(ctx, m->sm, B, idx, theta, q, (const long long*)node_offsets, g_out, 0);
+    int rc = check_idx_host(m, B, idx);
+    if (rc) return rc;
+    Stage st(ctx);
+    const int32_t* di = st.in(idx, n, mem);
+    const double* dt = st.in(theta, n, mem);
+    const double* dq = st.in(q, nqs, mem);
+    const int64_t* doff = st.in(node_offsets, n + 1, mem);
+    if (st.rc) return st.rc;
+    const size_t total_nodes = (size_t)node_offsets[n];
+    void* dg = nullptr;
+    rc = ctx_scratch(ctx, 10, total_nodes * 16 * sizeof(double), &dg);
+    if (rc) return rc;
+    rc = launch_static_curves(ctx, m->sm, B, di, dt, dq, (const long long*)doff, (double*)dg, 0);
+    if (rc) return rc;
+    CTRB_CUDA(cudaMemcpyAsync(g_out, dg, total_nodes * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return st.finish(mem);
 }
 
@@ -869,23 +919,30 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
     int32_t* dinf = st.out(info, (size_t)B, mem);
     int32_t* dnf = st.out(nfev, (size_t)B, mem);
     if (st.rc) return st.rc;
-    // ragged offsets and the g-curve scratch live on the device only
+    // The ragged offsets and the curves live on the device only.  The collision kernel reads node positions, so the curves
+    // kernel writes positions (24 B per node, not 128).  Their scratch is sized for the longest possible curves
+    // (every tube fully exposed), not from the batch's own node count: reading that count back would be a hidden
+    // synchronisation in CTRB_MEM_DEVICE mode.  Batches above 2^22 configurations run as consecutive launch sequences on
+    // the stream so that the scratch stays bounded (C3: 2^22 x 201 nodes x 24 B = 20 GB of the 180).
+    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 11, 0, sizeof(unsigned long long), ctx->stream));
+    const int64_t CH = std::min<int64_t>(B, (int64_t)1 << 22);
     void* doff = nullptr;
-    int rc = ctx_scratch(ctx, 9, (n + 1) * sizeof(long long), &doff);
+    int rc = ctx_scratch(ctx, 9, ((size_t)CH * T + 1) * sizeof(long long), &doff);
     if (rc) return rc;
-    rc = launch_offsets(ctx, m, B, di, 0, (long long*)doff);
-    if (rc) return rc;
-    long long total = 0;
-    CTRB_CUDA(cudaMemcpyAsync(&total, (long long*)doff + n, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
-    CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
     void* dg = nullptr;
-    rc = ctx_scratch(ctx, 10, (size_t)total * 16 * sizeof(double), &dg);
+    rc = ctx_scratch(ctx, 10, (size_t)CH * m->mc.total_nodes * 3 * sizeof(double), &dg);
     if (rc) return rc;
-    rc = launch_static_solve(ctx, m->sm, B, di, dt, nullptr, 0, 0.0, (const long long*)doff, (double*)dg, nullptr, dnf, dinf);
-    if (rc) return rc;
-    rc = launch_eval_curves_cost(ctx, env, cd, B, T, (const double*)dg, (const long long*)doff, m->mc.total_nodes, rad, dob,
-                                 dgo, dco, dcl);
-    if (rc) return rc;
+    for (int64_t b0 = 0; b0 < B; b0 += CH) {
+        const int64_t nb = std::min(CH, B - b0);
+        rc = launch_offsets(ctx, m, nb, di + b0 * T, 0, (long long*)doff);
+        if (rc) return rc;
+        rc = launch_static_solve(ctx, m->sm, nb, di + b0 * T, dt + b0 * T, nullptr, 0, 0.0, (const long long*)doff, (double*)dg,
+                                 nullptr, dnf ? dnf + b0 : nullptr, dinf ? dinf + b0 : nullptr, 1);
+        if (rc) return rc;
+        rc = launch_eval_curves_cost(ctx, env, cd, nb, T, (const double*)dg, (const long long*)doff, m->mc.total_nodes, rad,
+                                     dob + b0, dgo + b0, dco ? dco + b0 : nullptr, dcl ? dcl + b0 : nullptr, 1);
+        if (rc) return rc;
+    }
     st.back(obstacle_min, dob, (size_t)B, mem);
     st.back(goal_dist, dgo, (size_t)B, mem);
     st.back(cost, dco, (size_t)B, mem);

@@ -67,9 +67,11 @@ struct EvalParams {
     long long B;
     const int32_t* idx;
     const double* theta;
-    // non-fused input
+    // non-fused input: node k of a tube at g + (offsets[..] + k) * g_stride, its position component j at
+    // [g_poff + j * g_pstep] (4x4 row-major nodes: 16, 3, 4; position-only nodes: 3, 0, 1)
     const double* g;
     const long long* offsets;
+    int g_stride, g_poff, g_pstep;
     int tube_num;
     double rad[CTRB_MAX_TUBES];
     // outputs
@@ -253,11 +255,11 @@ __global__ void __launch_bounds__(kCWarps * 32, CTRB_EVAL_MINBLOCKS) chain_eval_
                 if (total + cnt[n] > P.max_nodes) cnt[n] = max(0, P.max_nodes - total);  // guarded on the host
                 first[n] = total;
                 for (int k = lane; k < cnt[n]; k += 32) {
-                    const double* gg = P.g + (o0 + k) * 16;
+                    const double* gg = P.g + (o0 + k) * P.g_stride + P.g_poff;
                     double* dst = s_pos + (size_t)(total + k) * 3;
-                    dst[0] = __ldg(gg + 3);
-                    dst[1] = __ldg(gg + 7);
-                    dst[2] = __ldg(gg + 11);
+                    dst[0] = __ldg(gg);
+                    dst[1] = __ldg(gg + P.g_pstep);
+                    dst[2] = __ldg(gg + 2 * P.g_pstep);
                 }
                 total += cnt[n];
             }
@@ -820,12 +822,12 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                         }
                     } else {
                         for (int n = 0; n < T; ++n) {
-                            const double* gg = P.g + P.offsets[b * T + n] * 16;
+                            const double* gg = P.g + P.offsets[b * T + n] * P.g_stride + P.g_poff;
 #pragma unroll 1
                             for (int k = 0; k < cnt[n]; ++k) {
-                                dst[0] = __ldg(gg + (size_t)k * 16 + 3);
-                                dst[1] = __ldg(gg + (size_t)k * 16 + 7);
-                                dst[2] = __ldg(gg + (size_t)k * 16 + 11);
+                                dst[0] = __ldg(gg + (size_t)k * P.g_stride);
+                                dst[1] = __ldg(gg + (size_t)k * P.g_stride + P.g_pstep);
+                                dst[2] = __ldg(gg + (size_t)k * P.g_stride + 2 * P.g_pstep);
                                 dst += 3;
                                 if (k + 1 < cnt[n]) *it++ = (unsigned)(node + k) | ((unsigned)lane << 10) | ((unsigned)n << 15);
                             }
@@ -861,12 +863,12 @@ __global__ void __launch_bounds__(kGWarps * 32, CTRB_GROUP_BLOCKS) chain_eval_gr
                             }
                             g = se3_mul(a, load_tab(P.tb.tab, tot, P.mc.node_base[n] + P.mc.npts[n] - 1));
                         } else {
-                            const double* gg = P.g + P.offsets[bs * T + n] * 16;
+                            const double* gg = P.g + P.offsets[bs * T + n] * P.g_stride + P.g_poff;
                             for (int k = lane; k < cn; k += 32) {
                                 double* dst = W.pos + (size_t)(node + k) * 3;
-                                dst[0] = __ldg(gg + (size_t)k * 16 + 3);
-                                dst[1] = __ldg(gg + (size_t)k * 16 + 7);
-                                dst[2] = __ldg(gg + (size_t)k * 16 + 11);
+                                dst[0] = __ldg(gg + (size_t)k * P.g_stride);
+                                dst[1] = __ldg(gg + (size_t)k * P.g_stride + P.g_pstep);
+                                dst[2] = __ldg(gg + (size_t)k * P.g_stride + 2 * P.g_pstep);
                             }
                         }
                         for (int k = lane; k + 1 < cn; k += 32)
@@ -1213,9 +1215,8 @@ size_t eval_smem_bytes(int max_nodes) {
 int launch_eval(ctrb_ctx* ctx, const EvalParams& P, bool fused) {
     if (P.B <= 0) return CTRB_OK;
     // grouped kernel (several configurations per warp) whenever a configuration fits the warp's node pool;
-    // CTRB_EVAL_GROUP=0 forces one warp per configuration
-    const char* genv = getenv("CTRB_EVAL_GROUP");
-    const bool group_off = genv && atoi(genv) == 0;
+    // CTRB_OPT_EVAL_GROUP = 0 forces one warp per configuration
+    const bool group_off = ctx->opt[CTRB_OPT_EVAL_GROUP] == 0;
     if (P.max_nodes <= kPoolMax && P.bvh_depth + 2 <= kGStack && !group_off) {
         const int pool = P.max_nodes <= kPoolMin ? kPoolMin : kPoolMax;
         const size_t smem_p = (size_t)kGWarps * (sizeof(GroupMem) + (size_t)pool * (3 * sizeof(double) + sizeof(unsigned int)));
@@ -1306,12 +1307,16 @@ int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube
     P.counters = ctx->d_counters;
     P.bvh_depth = env->stats[2];
     P.max_nodes = max_nodes;
+    P.g_stride = 16;
+    P.g_poff = 3;
+    P.g_pstep = 4;
     return launch_eval(ctx, P, false);
 }
 
+// pos_only: g holds 3 doubles per node (the node positions) instead of 4x4 matrices
 int launch_eval_curves_cost(ctrb_ctx* ctx, const ctrb_env* env, const ctrb_cost_desc* cd, long long B, int tube_num,
                             const double* g, const long long* offsets, int max_nodes, const double* rad,
-                            double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide) {
+                            double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide, int pos_only) {
     EvalParams P;
     memset(&P, 0, sizeof P);
     P.env = env->d_ec;
@@ -1328,6 +1333,9 @@ int launch_eval_curves_cost(ctrb_ctx* ctx, const ctrb_env* env, const ctrb_cost_
     P.counters = ctx->d_counters;
     P.bvh_depth = env->stats[2];
     P.max_nodes = max_nodes;
+    P.g_stride = pos_only ? 3 : 16;
+    P.g_poff = pos_only ? 0 : 3;
+    P.g_pstep = pos_only ? 1 : 4;
     return launch_eval(ctx, P, false);
 }
 

@@ -90,13 +90,14 @@ struct ctrb_ctx {
     cudaEvent_t ev[2];
     cudaEvent_t ev_chunk[2];  // host-memory pipeline: chunk inputs have landed (recorded on stream2)
     cudaEvent_t ev_done[2];   //                       chunk kernels have finished (recorded on stream)
-    cudaEvent_t kev[5][2];  // per-kernel start/stop of the most recent launch (ctrb_kernel_id)
+    cudaEvent_t kev[8][2];  // per-kernel start/stop of the most recent launch (ctrb_kernel_id)
     int64_t launches;
     // grow-only device scratch
     void* scratch[32];        // [1..8] Stage buffers, [9..15] per-call scratch, [17..24] second set of Stage buffers
     size_t scratch_bytes[32];
-    unsigned long long* d_counters;  // [16]: [0..7] collision work counters + ticket, [8..10] static-solve tickets + fallback count
+    unsigned long long* d_counters;  // [16]: [0..7] collision work counters + ticket, [8..10] static-solve tickets + fallback count, [11] fallbacks summed over the chunks of one call
     int sm_count;
+    int opt[16];              // ctrb_option values (ctrb_ctx_set_option); defaults set by ctrb_ctx_create
 };
 
 struct ctrb_model {

@@ -496,7 +496,7 @@ int launch_gcurve(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_t
     // persistent grid of resident blocks only (a fixed 4 per SM left the fp32 kernel, whose shared memory then allowed 3,
     // with a quarter of its blocks in a second wave: 4.28 TB/s).  Measured on C2 (10^6 configurations), blocks per SM ->
     // TB/s fp64 / fp32: 2 -> 5.76 / 5.55, 3 -> 5.91 / 6.12, 4 -> 5.71 / 5.63, 5+ (fp32) -> 5.63: twelve write streams
-    // per SM are enough to cover the store latency and more only scatter the DRAM pages.  CTRB_GCURVE_BLOCKS overrides.
+    // per SM are enough to cover the store latency and more only scatter the DRAM pages.  CTRB_OPT_GCURVE_BLOCKS overrides.
     int per_sm = 1;
     if (precision == CTRB_F64) {
         CTRB_CUDA(cudaFuncSetAttribute(kin_gcurve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -505,7 +505,7 @@ int launch_gcurve(ctrb_ctx* ctx, const ctrb_model* m, long long B, const int32_t
         CTRB_CUDA(cudaFuncSetAttribute(kin_gcurve_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CTRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kin_gcurve_kernel<float>, kGWarps * 32, smem));
     }
-    static const int max_blocks = getenv("CTRB_GCURVE_BLOCKS") ? atoi(getenv("CTRB_GCURVE_BLOCKS")) : 3;
+    const int max_blocks = ctx->opt[CTRB_OPT_GCURVE_BLOCKS] > 0 ? ctx->opt[CTRB_OPT_GCURVE_BLOCKS] : 3;
     per_sm = std::max(1, std::min(per_sm, max_blocks));
     int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * per_sm);
     KernelTimer kt(ctx, CTRB_KERNEL_GCURVE);

@@ -526,7 +526,9 @@ __global__ void __launch_bounds__(kSWarps * 32, CTRB_QR_BLOCKS)
                         const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                         double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
                         int32_t* __restrict__ info_out, unsigned long long* __restrict__ ticket,
-                        const long long* __restrict__ list, const unsigned long long* __restrict__ list_count) {
+                        const long long* __restrict__ list, const unsigned long long* __restrict__ list_count,
+                        unsigned long long* __restrict__ list_total) {
+    if (list && list_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(list_total, *list_count);
     load_model(sm_);
     const StModel& sm = g_sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -570,6 +572,7 @@ struct CurveMem {
     StCfg cfg;
     double q[kNV];
 };
+template <bool kPos>  // kPos: node positions only (3 doubles per node) -- what the fused solve -> collision path reads
 __global__ void __launch_bounds__(kCWarps * 32)
     static_curves_kernel(const __grid_constant__ StModel sm_, long long B, const int32_t* __restrict__ idx,
                          const double* __restrict__ theta, const double* __restrict__ sol,
@@ -584,7 +587,7 @@ __global__ void __launch_bounds__(kCWarps * 32)
         if (lane == 0) st_setup(sm, idx + b * T, theta + b * T, M.cfg);
         if (lane < n) M.q[lane] = sol[b * n + lane];
         __syncwarp();
-        st_write_curves(sm, M.cfg, M.q, offsets, b, g_out, lane);
+        st_write_curves<kPos>(sm, M.cfg, M.q, offsets, b, g_out, lane);
         __syncwarp();
     }
 }
@@ -739,16 +742,30 @@ int launch_static_fast(ctrb_ctx* ctx, const StModel& sm, long long B, const int3
                        double* sol_out, int32_t* nfev_out, int32_t* info_out, long long* fb_list,
                        unsigned long long* fb_count, unsigned long long* ticket);
 
-// Static.solve_g for B configurations.  Two kernels: static_fast_kernel carries hybrd's
-// iteration on the explicit Jacobian and its inverse and hands back the configurations whose Jacobian is
-// (numerically) singular -- one-step sections, SURVEY App. B#5 -- which static_solve_kernel then solves with
-// MINPACK's own QR machinery.  CTRB_STATIC_SOLVER=qr sends everything through the QR kernel.
+// integrate_g of given unknowns (one warp per configuration); pos_only: 3 doubles per node instead of 16
+int launch_static_curves(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
+                         const double* sol, const long long* offsets, double* g_out, int pos_only) {
+    if (B <= 0) return CTRB_OK;
+    KernelTimer kc(ctx, CTRB_KERNEL_STATIC_CURVES);
+    const long long blocks = (B + kCWarps - 1) / kCWarps;
+    const int cgrid = (int)std::min<long long>(blocks, (long long)ctx->sm_count * 16);
+    if (pos_only) static_curves_kernel<true><<<cgrid, kCWarps * 32, 0, ctx->stream>>>(sm, B, idx, theta, sol, offsets, g_out);
+    else static_curves_kernel<false><<<cgrid, kCWarps * 32, 0, ctx->stream>>>(sm, B, idx, theta, sol, offsets, g_out);
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
+    return CTRB_OK;
+}
+
+// Static.solve_g for B configurations: static_fast_kernel carries hybrd's iteration on the
+// explicit Jacobian and its inverse and hands back the configurations it cannot treat -- zero-length sections, a Jacobian
+// that turns out numerically singular, and, with CTRB_OPT_STATIC_ONE_STEP = 1, one-step sections --
+// which static_solve_kernel then solves with MINPACK's own QR machinery; static_curves_kernel integrates the section
+// curves.  CTRB_OPT_STATIC_SOLVER = 1 sends everything through the QR kernel.
 int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int32_t* idx, const double* theta,
                         const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
-                        double* sol_out, int32_t* nfev_out, int32_t* info_out) {
+                        double* sol_out, int32_t* nfev_out, int32_t* info_out, int pos_only) {
     if (B <= 0) return CTRB_OK;
-    const char* mode = getenv("CTRB_STATIC_SOLVER");
-    const bool qr_only = mode && strcmp(mode, "qr") == 0;
+    const bool qr_only = ctx->opt[CTRB_OPT_STATIC_SOLVER] == 1;
     const size_t smem = sizeof(HybrdMem) * kSWarps;
     CTRB_CUDA(cudaFuncSetAttribute(static_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks_needed = (B + kSWarps - 1) / kSWarps;
@@ -770,27 +787,23 @@ int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int
         if (rc) return rc;
         fb_list = (long long*)p;
     }
+    KernelTimer kt(ctx, CTRB_KERNEL_STATIC_SOLVE);
+    if (!qr_only) {
+        KernelTimer kf(ctx, CTRB_KERNEL_STATIC_FAST);
+        int rc = launch_static_fast(ctx, sm, B, idx, theta, x0, x0_per_config, xtol > 0 ? xtol : 1.49012e-8, offsets, g_out,
+                                    sol_out, nfev_out, info_out, fb_list, ctx->d_counters + 10, ctx->d_counters + 9);
+        if (rc) return rc;
+    }
     {
-        KernelTimer kt(ctx, CTRB_KERNEL_STATIC_SOLVE);
-        if (!qr_only) {
-            KernelTimer kf(ctx, CTRB_KERNEL_STATIC_FAST);
-            int rc = launch_static_fast(ctx, sm, B, idx, theta, x0, x0_per_config, xtol > 0 ? xtol : 1.49012e-8, offsets, g_out,
-                                        sol_out, nfev_out, info_out, fb_list, ctx->d_counters + 10, ctx->d_counters + 9);
-            if (rc) return rc;
-        }
+        KernelTimer kq(ctx, CTRB_KERNEL_STATIC_QR);
         static_solve_kernel<<<grid, kSWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config,
                                                                       xtol > 0 ? xtol : 1.49012e-8, offsets, g_out, sol_out,
                                                                       nfev_out, info_out, ctx->d_counters + 8, fb_list,
-                                                                      ctx->d_counters + 10);
+                                                                      ctx->d_counters + 10, ctx->d_counters + 11);
         ctx->launches++;
-        if (g_out) {
-            const long long blocks = (B + kCWarps - 1) / kCWarps;
-            const int cgrid = (int)std::min<long long>(blocks, (long long)ctx->sm_count * 16);
-            static_curves_kernel<<<cgrid, kCWarps * 32, 0, ctx->stream>>>(sm, B, idx, theta, sol_out, offsets, g_out);
-        }
+        CTRB_CUDA(cudaGetLastError());
     }
-    ctx->launches++;
-    CTRB_CUDA(cudaGetLastError());
+    if (g_out) return launch_static_curves(ctx, sm, B, idx, theta, sol_out, offsets, g_out, pos_only);
     return CTRB_OK;
 }
 

@@ -420,9 +420,11 @@ __device__ __noinline__ double res_assemble(const StModel& sm_, const StCfg& c, 
 
 constexpr int kJLD = 31;  // leading dimension of the column-major n x n matrices (odd: conflict-free row and column access)
 
-// per-lane description of residual row `lane` (which block of static.py:63 it belongs to)
+// per-lane description of residual row `lane` (which block of static.py:63 it belongs to); `scale` multiplies the row
+// (1 everywhere except under the one-step-section rule, see pin_mask)
 struct RowMeta {
     int blk, k, sec, yo;
+    double scale;
 };
 
 __device__ __forceinline__ RowMeta row_meta(const StModel& sm_, int comp) {
@@ -435,7 +437,36 @@ __device__ __forceinline__ RowMeta row_meta(const StModel& sm_, int comp) {
     r.k = comp - sm.qoff[r.blk];
     r.sec = r.blk < 3 ? 0 : (r.blk < 5 ? 1 : 2);
     r.yo = (r.blk == 0 || r.blk == 3 || r.blk == 5) ? 0 : ((r.blk == 1 || r.blk == 4) ? 9 : 12);
+    r.scale = 1.0;
     return r;
+}
+
+// One-step sections (two nodes).  calculate_integral (static.py:456-491) samples a section's integrand at
+// its nodes only, and a one-step section has the nodes x = 0 and x = dx: the curvature polynomial c0 + c1 x + c2 x^2 of
+// its tube==section block enters the residual through c0 and c1 dx + c2 dx^2 alone, so the Jacobian columns of c1 and
+// c2 are proportional (identical for dx = 1), and so are the residual rows that weigh the integrand by x and x^2: the
+// system is consistent and rank-deficient by three per one-step section.  MINPACK's qrfac meets an (exactly or nearly)
+// zero diagonal of R there, and what dogleg's back substitution makes of it -- 0/0 in exact arithmetic, rounding noise
+// over rounding noise in floating point -- decides where in the null space hybrd lands (the reference's own result changes
+// under a 1e-13 perturbation of its initial guess in a fifth of such configurations).  The rule used here is hybrd on
+// the reduced system, i.e. what MINPACK's rank-deficient rule gives when the zero is exact: the step component of the
+// coincident column is zero, so c2 keeps its initial value, and the duplicated row is carried once with the weight
+// sqrt(1 + dx^2) that keeps |F|, J^T F and the column norms what they are in the full system.  Implemented without changing
+// the system size: pinned unknown j has column e_j and row e_j^T in the Jacobian and a zero residual component (the
+// Broyden updates preserve that structure exactly: u_j = 0, v_j = 0), row j - 1 carries the weight.
+// Bit j of the mask = unknown j is pinned.
+__device__ __forceinline__ unsigned pin_mask(const StModel& sm_, const StCfg& c) {
+    CTRB_USE_SM;
+    unsigned m = 0;
+    const unsigned x2 = (1u << 2) | (1u << 5) | (1u << 8);  // the x^2 coefficients of the three curvature components
+    if (sm.mc.T == 3 && c.L[0] == 2) m |= x2 << sm.qoff[0];
+    if (c.L[1] == 2) m |= x2 << sm.qoff[3];
+    return m;
+}
+__device__ __forceinline__ void pin_row_meta(const StModel& sm_, unsigned pin, int lane, RowMeta& rm) {
+    CTRB_USE_SM;
+    if ((pin >> lane) & 1u) rm.scale = 0.0;
+    else if (lane < 31 && ((pin >> (lane + 1)) & 1u)) rm.scale = sqrt(1.0 + sm.mc.dx * sm.mc.dx);
 }
 
 // calculate_integral (static.py:456-491) of one integrand component over one section: the four node values are
@@ -462,7 +493,7 @@ __device__ __forceinline__ double warp_residual(const StModel& sm_, const StCfg&
     __syncwarp();
     double a = 0.0, b = 0.0;
     if (act) {
-        a = asm_part(cfg, y, rm.sec * 4, rm.sec, rm.yo + rm.k);
+        a = rm.scale * asm_part(cfg, y, rm.sec * 4, rm.sec, rm.yo + rm.k);  // scale: 1.0 (exact) unless the row is pinned / weighted
         if (rm.blk == 2) b = asm_part(cfg, y, 4, 1, 12 + rm.k);
     }
     __syncwarp();
@@ -539,7 +570,7 @@ __device__ __noinline__ double block5_norm2(const StModel& sm_, const StCfg& cfg
 // scratch for 32 node vectors; returns this lane's column norm.
 __device__ __noinline__ double warp_fdjac(const StModel& sm_, const StCfg& cfg, const SlotTable& st, const RowMeta& rm,
                                           const double* x, double* J, double (*yb)[16], double f_l, double p1b, double p2b,
-                                          int n, int lane) {
+                                          int n, int lane, unsigned pin = 0u) {
     CTRB_USE_SM;
     const bool act = lane < n;
     const double eps = sqrt(DBL_EPSILON);
@@ -568,7 +599,7 @@ __device__ __noinline__ double warp_fdjac(const StModel& sm_, const StCfg& cfg, 
                 double val = 0.0;
                 if (hit1 || hit2) {
                     const int b1 = (pair && rm.sec == 1) ? (s8 + 1) * 4 : s8 * 4;
-                    const double p1 = hit1 ? asm_part(cfg, yb, b1, rm.sec, rm.yo + rm.k) : p1b;
+                    const double p1 = hit1 ? rm.scale * asm_part(cfg, yb, b1, rm.sec, rm.yo + rm.k) : p1b;
                     double Fp = p1;
                     if (rm.blk == 2) {
                         const int b2 = pair ? (s8 + 1) * 4 : s8 * 4;
@@ -580,6 +611,7 @@ __device__ __noinline__ double warp_fdjac(const StModel& sm_, const StCfg& cfg, 
                     if (h == 0.0) h = eps;
                     val = (Fp - f_l) / h;
                 }
+                if ((pin >> j) & 1u) val = lane == j ? 1.0 : 0.0;  // pinned unknown: column e_j (its row is zero: scale 0)
                 J[lane + j * kJLD] = val;
             }
         }
@@ -639,23 +671,35 @@ __device__ __noinline__ void sect_omega(const StModel& sm_, const StCfg& c, cons
     }
 }
 
+// one curve node: a 4x4 row-major matrix (16 doubles), or -- kPos, for the fused solve -> collision path, which only
+// reads positions -- its position (3 doubles)
+template <bool kPos>
+__device__ __forceinline__ void store_node(double* out, size_t k, const SE3& g) {
+    if (kPos) {
+        double* dst = out + k * 3;
+        dst[0] = g.p[0]; dst[1] = g.p[1]; dst[2] = g.p[2];
+    } else {
+        double* dst = out + k * 16;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            dst[r * 4 + 0] = g.r[r * 3 + 0];
+            dst[r * 4 + 1] = g.r[r * 3 + 1];
+            dst[r * 4 + 2] = g.r[r * 3 + 2];
+            dst[r * 4 + 3] = g.p[r];
+        }
+        dst[12] = 0; dst[13] = 0; dst[14] = 0; dst[15] = 1;
+    }
+}
+
 // Writes `count` nodes of one section curve: node 0 = g0, node k = g0 * E_1 ... E_k with
 // E_k the Magnus step at absolute index start + k.  Returns the last node (all lanes).
+template <bool kPos>
 __device__ __noinline__ SE3 integrate_section(const StModel& sm_, const StCfg& c, const double* qs, int sect, int start, int count,
                                  SE3 g0, double* out, int lane) {
     CTRB_USE_SM;
     const double dx = sm.mc.dx;
     const double cg1 = 0.5 - sqrt(3.0) / 6, cg2 = 0.5 + sqrt(3.0) / 6;  // static.py:597-599
-    if (lane == 0 && out) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            out[r * 4 + 0] = g0.r[r * 3 + 0];
-            out[r * 4 + 1] = g0.r[r * 3 + 1];
-            out[r * 4 + 2] = g0.r[r * 3 + 2];
-            out[r * 4 + 3] = g0.p[r];
-        }
-        out[12] = 0; out[13] = 0; out[14] = 0; out[15] = 1;
-    }
+    if (lane == 0 && out) store_node<kPos>(out, 0, g0);
     SE3 carry = g0;
     for (int base = 1; base < count; base += 32) {
         const int k = base + lane;
@@ -682,17 +726,7 @@ __device__ __noinline__ SE3 integrate_section(const StModel& sm_, const StCfg& c
             if (lane >= off) e = se3_mul(o, e);
         }
         SE3 g = se3_mul(carry, e);
-        if (k < count && out) {
-            double* dst = out + (size_t)k * 16;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                dst[r * 4 + 0] = g.r[r * 3 + 0];
-                dst[r * 4 + 1] = g.r[r * 3 + 1];
-                dst[r * 4 + 2] = g.r[r * 3 + 2];
-                dst[r * 4 + 3] = g.p[r];
-            }
-            dst[12] = 0; dst[13] = 0; dst[14] = 0; dst[15] = 1;
-        }
+        if (k < count && out) store_node<kPos>(out, (size_t)k, g);
         const int last = min(31, count - 1 - base);
 #pragma unroll
         for (int t = 0; t < 9; ++t) carry.r[t] = shfl_d(g.r[t], last);
@@ -716,27 +750,29 @@ __device__ __forceinline__ double ipoly3_abs(const double* q, double a, double b
 
 // Static.solve_g's curve assembly (static.py:110-130) from a solved q (shared-memory vector): the whole warp
 // writes the T section curves of configuration b into the packed g_out.
+template <bool kPos>
 __device__ __noinline__ void st_write_curves(const StModel& sm_, const StCfg& c, const double* q, const long long* offsets,
                                              long long b, double* g_out, int lane) {
+    constexpr int kNode = kPos ? 3 : 16;  // doubles per node
     CTRB_USE_SM;
     const int T = sm.mc.T;
     const double dx = sm.mc.dx;
     SE3 g11_last, g21_last, g31_last;
     se3_identity(g11_last);
     if (T == 3) {
-        g11_last = integrate_section(sm, c, q + sm.qoff[0], 1, c.i11, c.L[0], se3_rx(c.th[0]),
-                                     g_out + offsets[b * T + 0] * 16, lane);
+        g11_last = integrate_section<kPos>(sm, c, q + sm.qoff[0], 1, c.i11, c.L[0], se3_rx(c.th[0]),
+                                           g_out + offsets[b * T + 0] * kNode, lane);
         g21_last = se3_rx(c.th[1] + ipoly3_abs(q + sm.qoff[1], c.i21 * dx, (c.i21 + c.L[0] - 1) * dx));
         g31_last = se3_rx(c.th[2] + ipoly3_abs(q + sm.qoff[2], c.i31 * dx, (c.i31 + c.L[0] - 1) * dx));
     } else {
         g21_last = se3_rx(c.th[0]);  // static.py:114-118
         g31_last = se3_rx(c.th[1]);
     }
-    SE3 g22_last = integrate_section(sm, c, q + sm.qoff[3], 2, c.i22, c.L[1], se3_mul(g11_last, g21_last),
-                                     g_out + offsets[b * T + (T - 2)] * 16, lane);
+    SE3 g22_last = integrate_section<kPos>(sm, c, q + sm.qoff[3], 2, c.i22, c.L[1], se3_mul(g11_last, g21_last),
+                                           g_out + offsets[b * T + (T - 2)] * kNode, lane);
     SE3 g32_last = se3_rx(ipoly3_abs(q + sm.qoff[4], c.i32 * dx, (c.i32 + c.L[1] - 1) * dx));
-    integrate_section(sm, c, q + sm.qoff[5], 3, c.i33, c.L[2], se3_mul(se3_mul(g22_last, g31_last), g32_last),
-                      g_out + offsets[b * T + (T - 1)] * 16, lane);
+    integrate_section<kPos>(sm, c, q + sm.qoff[5], 3, c.i33, c.L[2], se3_mul(se3_mul(g22_last, g31_last), g32_last),
+                            g_out + offsets[b * T + (T - 1)] * kNode, lane);
 }
 
 }  // namespace

@@ -40,6 +40,7 @@ constexpr int kFWarps = CTRB_FAST_WARPS;   // warps (= configurations in flight)
 constexpr int kLD = kJLD;    // leading dimension, column-major: element (i, j) at i + j * kLD.  Odd, so both
                              // "lane = row" (stride 1) and "lane = column" (stride 31) accesses are conflict-free
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kFastAllowBlock = 1, kFastPinOneStep = 2;  // kernel flags
 // unroll factors of the n-long loops when n is a template parameter: pairs of columns for the matrix-vector products
 // (complete) and for the rank-one update, columns for the Gauss-Jordan step.  Measured on C3 (exposure 2..8, no
 // fallbacks), M cfg/s: everything complete 11.19; update 3 -> 11.79; + Gauss-Jordan 3 -> 12.10; (2, 2) 12.07; (1, 1) 11.84;
@@ -318,7 +319,7 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n_rt, double acnorm_l, 
 // configuration has to go through the QR kernel
 template <int N>
 __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
-                                       double factor, bool reduced, bool allow_block, int* nfev_out) {
+                                       double factor, bool reduced, bool allow_block, unsigned pin, int* nfev_out) {
     CTRB_USE_SM;
     CTRB_IN_SHARED(&M);
     CTRB_IN_SHARED(&st);
@@ -327,7 +328,8 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
     const int nnodes = reduced ? 8 : 12;
     const double c33 = reduced ? sm.c33_tab[M.cfg.i33] : 0.0;
     const bool act = lane < n;
-    const RowMeta rm = row_meta(sm, act ? lane : 0);
+    RowMeta rm = row_meta(sm, act ? lane : 0);
+    if (pin) pin_row_meta(sm, pin, lane, rm);  // one-step sections (pin_mask): pinned rows vanish, their twins carry the weight
     const double epsmch = DBL_EPSILON, p1c = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double x_l = act ? M.x[lane] : 0.0;
     double pa, pb;
@@ -340,7 +342,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
 #pragma unroll 1
     for (;;) {
         bool jeval = true;
-        const double acnorm_l = warp_fdjac(sm, M.cfg, st, rm, M.x, M.J, M.ybuf(), f_l, pa, pb, n, lane);
+        const double acnorm_l = warp_fdjac(sm, M.cfg, st, rm, M.x, M.J, M.ybuf(), f_l, pa, pb, n, lane, pin);
         nfev += sm.nq;  // MINPACK's count: one evaluation per unknown
         // three tubes from the default initial guess: block-structured inverse; anything it declines (a small pivot)
         // goes through the general Gauss-Jordan, which alone decides what is handed to the QR kernel
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
                        const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                        double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
                        int32_t* __restrict__ info_out, long long* __restrict__ fb_list,
-                       unsigned long long* __restrict__ fb_count, unsigned long long* __restrict__ ticket, int allow_block) {
+                       unsigned long long* __restrict__ fb_count, unsigned long long* __restrict__ ticket, int flags) {
     load_model(sm_);
     const StModel& sm = g_sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -521,11 +523,17 @@ __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
         M.vc[lane] = 0.0;
         __syncwarp();
         const StCfg& c = M.cfg;
-        // zero-length sections make whole residual blocks vanish (static.py:478-479): singular by construction
-        // and a one-step section 1 or 2 gives the x and x^2 curvature coefficients identical columns
-        const bool degenerate = (T == 3 && c.L[0] < 3) || c.L[1] < 3 || c.L[2] < 2;
+        // zero-length sections make whole residual blocks vanish (static.py:478-479): singular by construction, left to the
+        // QR kernel.  A one-step section 1 or 2 gives the x and x^2 curvature coefficients proportional columns (SURVEY
+        // App. B#5): solved here on the reduced system (pin_mask), or handed to the QR kernel when the caller asked for
+        // MINPACK's own treatment of them (CTRB_OPT_STATIC_ONE_STEP = 1)
+        const int lmin = (flags & kFastPinOneStep) ? 2 : 3;
+        const bool degenerate = (T == 3 && c.L[0] < lmin) || c.L[1] < lmin || c.L[2] < 2;
+        const unsigned pin = (flags & kFastPinOneStep) ? pin_mask(sm, c) : 0u;
         int nfev = 0;
-        const int info = degenerate ? -1 : fast_hybrd<N>(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, allow_block != 0, &nfev);
+        const int info = degenerate ? -1
+                                    : fast_hybrd<N>(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced,
+                                                    (flags & kFastAllowBlock) != 0, pin, &nfev);
         __syncwarp();
         if (info < 0) {
             if (lane == 0) fb_list[atomicAdd(fb_count, 1ULL)] = b;
@@ -545,9 +553,10 @@ static int launch_static_fast_n(ctrb_ctx* ctx, const StModel& sm, long long B, c
                                 const double* x0, int x0_per_config, double xtol, const long long* offsets, double* g_out,
                                 double* sol_out, int32_t* nfev_out, int32_t* info_out, long long* fb_list,
                                 unsigned long long* fb_count, unsigned long long* ticket) {
-    // CTRB_FAST_BLOCK_INVERT=0: the general Gauss-Jordan inverse for every configuration (parity test of the block-structured one)
-    const char* be = getenv("CTRB_FAST_BLOCK_INVERT");
-    const int allow_block = !(be && atoi(be) == 0);
+    // CTRB_OPT_FAST_BLOCK_INVERT = 0: the general Gauss-Jordan inverse for every configuration (parity test of the
+    // block-structured one); CTRB_OPT_STATIC_ONE_STEP = 1: one-step sections go to the QR kernel
+    const int flags = (ctx->opt[CTRB_OPT_FAST_BLOCK_INVERT] ? kFastAllowBlock : 0) |
+                      (ctx->opt[CTRB_OPT_STATIC_ONE_STEP] == 0 ? kFastPinOneStep : 0);
     const size_t smem = sizeof(FastMem) * kFWarps;
     CTRB_CUDA(cudaFuncSetAttribute(static_fast_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
@@ -555,7 +564,7 @@ static int launch_static_fast_n(ctrb_ctx* ctx, const StModel& sm, long long B, c
     const long long blocks_needed = (B + kFWarps - 1) / kFWarps;
     const int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * std::max(per_sm, 1));
     static_fast_kernel<N><<<grid, kFWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out,
-                                                                    sol_out, nfev_out, info_out, fb_list, fb_count, ticket, allow_block);
+                                                                    sol_out, nfev_out, info_out, fb_list, fb_count, ticket, flags);
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());
     return CTRB_OK;
@@ -569,7 +578,7 @@ int launch_static_fast(ctrb_ctx* ctx, const StModel& sm, long long B, const int3
                        double* sol_out, int32_t* nfev_out, int32_t* info_out, long long* fb_list,
                        unsigned long long* fb_count, unsigned long long* ticket) {
     const int n = x0 == nullptr ? sm.nq - sm.ndof[5] : sm.nq;  // as fast_hybrd derives it
-    const bool generic = getenv("CTRB_FAST_GENERIC_N") != nullptr;  // read per call: the parity test toggles it
+    const bool generic = ctx->opt[CTRB_OPT_FAST_GENERIC_N] != 0;  // run-time-n instantiation (parity test)
 #define CTRB_FAST_ARGS ctx, sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out, sol_out, nfev_out, info_out, fb_list, fb_count, ticket
     if (!generic) {
         switch (n) {

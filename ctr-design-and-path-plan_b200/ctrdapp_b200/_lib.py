@@ -54,6 +54,8 @@ SYMBOLS = {
     "ctrb_ctx_destroy": (None, [_vp]),
     "ctrb_ctx_synchronize": (C.c_int, [_vp]),
     "ctrb_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "ctrb_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "ctrb_ctx_get_option": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
     "ctrb_measure_fma_peak": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "ctrb_ctx_launch_count": (_i64, [_vp]),
     "ctrb_ctx_mark": (C.c_int, [_vp, C.c_int]),
@@ -77,6 +79,7 @@ SYMBOLS = {
     "ctrb_static_residual_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_int]),
     "ctrb_static_solve_g_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp,
                                             C.c_int]),
+    "ctrb_static_curves_batch": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "ctrb_static_eval_batch": (C.c_int, [_vp, _vp, _vp, C.POINTER(CostDesc), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _vp, C.c_int]),
     "ctrb_check_collision_batch": (C.c_int, [_vp, _vp, _i64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int]),
@@ -186,7 +189,35 @@ class Context:
         check(lib().ctrb_ctx_elapsed_ms(self._h, C.byref(ms)))
         return ms.value
 
-    KERNELS = {"chain_eval": 0, "static_solve": 1, "gcurve": 2, "eta_ftl": 3, "static_fast": 4}
+    KERNELS = {"chain_eval": 0, "static_solve": 1, "gcurve": 2, "eta_ftl": 3, "static_fast": 4, "static_qr": 5,
+               "static_curves": 6}
+    # ctrb_option (include/ctrb200.h): run-time switches for parity tests and measurement
+    OPTIONS = {"static_solver": 0, "static_one_step": 1, "fast_generic_n": 2, "fast_block_invert": 3, "eval_group": 4,
+               "gcurve_blocks": 5}
+
+    def set_option(self, name, value):
+        check(lib().ctrb_ctx_set_option(self._h, self.OPTIONS[name], int(value)))
+
+    def get_option(self, name):
+        v = C.c_int()
+        check(lib().ctrb_ctx_get_option(self._h, self.OPTIONS[name], C.byref(v)))
+        return v.value
+
+    def options(self, **kw):
+        """context manager: set options, restore the previous values on exit"""
+        import contextlib
+
+        @contextlib.contextmanager
+        def _cm():
+            old = {k: self.get_option(k) for k in kw}
+            try:
+                for k, v in kw.items():
+                    self.set_option(k, v)
+                yield self
+            finally:
+                for k, v in old.items():
+                    self.set_option(k, v)
+        return _cm()
 
     def last_kernel_ms(self, name):
         ms = C.c_float()

@@ -75,6 +75,18 @@ class Static(Kinematic):
                                                   L.ptr(info), L.MEM_HOST))
         return {"g": g, "offsets": off, "solution": sol, "nfev": nfev, "info": info, "converged": info == 1}
 
+    def curves_batch(self, idx, theta, q):
+        """integrate_g alone (static.py:165-198 through the calls of :110-130): the section curves of GIVEN
+        unknowns q [B, nq] -> dict(g [nodes,4,4], offsets)."""
+        idx = _i32(idx).reshape(-1, self.tube_num)
+        theta = _f64(theta).reshape(-1, self.tube_num)
+        q = _f64(q).reshape(-1, self.num_unknowns)
+        off = self.node_offsets(idx, False)
+        g = np.empty((int(off[-1]), 4, 4))
+        L.check(L.lib().ctrb_static_curves_batch(self.ctx.handle, self._h, idx.shape[0], L.ptr(idx), L.ptr(theta), L.ptr(q),
+                                                 L.ptr(off), L.ptr(g), L.MEM_HOST))
+        return {"g": g, "offsets": off}
+
     # ------------------------------------------------------------------ reference-shaped
     def solve_g(self, indices=None, thetas=None, initial_guess=None, full=False):
         """static.py:71-135 (`full` is ignored there as well).  The reference prints nfev and q per

@@ -141,9 +141,30 @@ typedef enum {
     CTRB_KERNEL_STATIC_SOLVE = 1, /* static_solve_kernel */
     CTRB_KERNEL_GCURVE = 2,       /* kin_gcurve_kernel */
     CTRB_KERNEL_ETA_FTL = 3,      /* kin_eta_ftl_kernel */
-    CTRB_KERNEL_STATIC_FAST = 4   /* static_fast_kernel alone (STATIC_SOLVE spans it and the QR kernel) */
+    CTRB_KERNEL_STATIC_FAST = 4,  /* static_fast_kernel alone (STATIC_SOLVE spans it, the QR kernel and the curves) */
+    CTRB_KERNEL_STATIC_QR = 5,    /* static_solve_kernel alone (the configurations the fast kernel handed back) */
+    CTRB_KERNEL_STATIC_CURVES = 6 /* static_curves_kernel alone (integrate_g of the solved unknowns) */
 } ctrb_kernel_id;
 int ctrb_ctx_last_kernel_ms(ctrb_ctx* ctx, int kernel_id, float* ms);
+
+/* Run-time switches of a ctx, for parity tests and measurement; the defaults are the product path.  A ctx is used
+ * by one thread at a time, so an option set before a batch call holds for that call; nothing is read from the
+ * process environment. */
+typedef enum {
+    CTRB_OPT_STATIC_SOLVER = 0,     /* 0 (default): explicit-inverse kernel, QR kernel for what it hands back;
+                                       1: every configuration through the QR kernel (MINPACK's own factor machinery) */
+    CTRB_OPT_STATIC_ONE_STEP = 1,   /* one-step sections (two nodes; rank-deficient Jacobian):
+                                       0 (default): hybrd on the reduced system in the explicit-inverse kernel (the x^2
+                                       curvature coefficient of such a section keeps its initial value);
+                                       1: MINPACK's literal treatment in the QR kernel (null-space component decided by rounding) */
+    CTRB_OPT_FAST_GENERIC_N = 2,    /* 1: run-time-n instantiation of the explicit-inverse kernel (default 0: size-templated) */
+    CTRB_OPT_FAST_BLOCK_INVERT = 3, /* 0: general Gauss-Jordan inverse (default 1: block-structured for three tubes) */
+    CTRB_OPT_EVAL_GROUP = 4,        /* 0: one warp per configuration in the collision kernel (default 1: grouped) */
+    CTRB_OPT_GCURVE_BLOCKS = 5,     /* resident blocks per SM of the g-curve kernel's persistent grid (default 3) */
+    CTRB_OPT_COUNT = 6
+} ctrb_option;
+int ctrb_ctx_set_option(ctrb_ctx* ctx, int option, int value);
+int ctrb_ctx_get_option(const ctrb_ctx* ctx, int option, int* value);
 
 /* Measured CUDA-core FMA peak of this device (dependent-free FMA chains on every SM), the
  * denominator of the compute roofline of the collision kernel: precision CTRB_F32 / CTRB_F64. */
@@ -218,6 +239,11 @@ int ctrb_static_solve_g_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, con
                               const double* theta /*[B][T]*/, const double* initial_guess, int x0_per_config,
                               double xtol, const int64_t* node_offsets /*[B*T+1]*/, double* g_out /* nullable */,
                               double* solution_q, int32_t* nfev, int32_t* info, int mem);
+/* integrate_g alone (static.py:165-198 through the six calls of :110-130): the section curves of GIVEN unknowns
+ * q [B][nq], no root find.  g_out / node_offsets as above. */
+int ctrb_static_curves_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx /*[B][T]*/,
+                             const double* theta /*[B][T]*/, const double* q /*[B][nq]*/,
+                             const int64_t* node_offsets /*[B*T+1]*/, double* g_out, int mem);
 
 /* ---- collision on given curves: replaces CollisionChecker.check_collision
  *      (collision_checker.py:35-70) for B curves.  g is packed fp64 4x4 nodes with

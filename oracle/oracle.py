@@ -422,8 +422,45 @@ def static_curves(s, indices, thetas, sol):
     return _split(g, counts.tolist(), (4, 4))
 
 
-def static_solve_g(s, indices, thetas, initial_guess=None, xtol=0.0):
-    """Static.solve_g (static.py:71-135) -> (g list, solution x, nfev, info)."""
+def static_batch(s, idx, theta, env=None, rad=None, goal_weight=0.0, one_step_rule=0, x0=None, q_in=None,
+                 want_residual=False, nthreads=None):
+    """Threaded batch behind the parity tests (orc_static_batch).  Without q_in: Static.solve_g per configuration
+    (one_step_rule 0 = the reference's literal hybrd, 1 = the reduced system for one-step sections) from x0 [B, n] or
+    the default guess.  With q_in [B, n]: no solve, the given unknowns are evaluated.  env: also curves -> collision
+    -> own cost.  -> dict(solution, info, nfev[, residual][, obs, goal, cost])."""
+    idx = np.ascontiguousarray(idx, np.int32)
+    theta = _f64(theta)
+    B = idx.shape[0]
+    n = static_init_guess(s).shape[0]
+    sol = np.zeros((B, n))
+    fres = np.zeros((B, n)) if want_residual else None
+    info, nfev = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    obs = goal = cost = None
+    if env is not None:
+        obs, goal, cost = np.zeros(B), np.zeros(B), np.zeros(B)
+    x0a = None if x0 is None else _f64(x0).reshape(B, n)
+    qa = None if q_in is None else _f64(q_in).reshape(B, n)
+    f = lib().orc_static_batch
+    f.argtypes = None
+    nul = None
+    rc = f(C.byref(s), C.c_void_p(env._h) if env is not None else nul, C.c_int(B), _ip(idx), _dp(theta),
+           _dp(_f64(rad)) if rad is not None else nul, C.c_double(goal_weight), C.c_int(one_step_rule),
+           _dp(x0a) if x0a is not None else nul, _dp(qa) if qa is not None else nul, _dp(sol),
+           _dp(fres) if fres is not None else nul, _dp(obs) if obs is not None else nul,
+           _dp(goal) if goal is not None else nul, _dp(cost) if cost is not None else nul, _ip(info), _ip(nfev),
+           C.c_int(nthreads or len(os.sched_getaffinity(0))))
+    if rc:
+        raise NotImplementedError("unsupported obstacle in oracle")
+    out = {"solution": sol, "info": info, "nfev": nfev}
+    if want_residual:
+        out["residual"] = fres
+    if env is not None:
+        out.update(obs=obs, goal=goal, cost=cost)
+    return out
+
+
+def static_solve_g(s, indices, thetas, initial_guess=None, xtol=0.0, one_step_rule=0):
+    """Static.solve_g (static.py:71-135) -> (g list, solution x, nfev, info).  one_step_rule: see static_batch."""
     T = s.m.tube_num
     tot = sum(s.m.npts[n] for n in range(T))
     g = np.zeros((tot, 4, 4))
@@ -431,8 +468,9 @@ def static_solve_g(s, indices, thetas, initial_guess=None, xtol=0.0):
     sol = np.zeros(64)
     nfev, info = C.c_int(), C.c_int()
     x0 = None if initial_guess is None else _dp(_f64(initial_guess))
-    lib().orc_static_solve_g.argtypes = None
-    lib().orc_static_solve_g(C.byref(s), _ip(np.ascontiguousarray(indices, np.int32)), _dp(_f64(thetas)), x0,
-                             C.c_double(xtol), _dp(g), _ip(counts), _dp(sol), C.byref(nfev), C.byref(info))
+    lib().orc_static_solve_g_ex.argtypes = None
+    lib().orc_static_solve_g_ex(C.byref(s), _ip(np.ascontiguousarray(indices, np.int32)), _dp(_f64(thetas)), x0,
+                                C.c_double(xtol), C.c_int(one_step_rule), _dp(g), _ip(counts), _dp(sol), C.byref(nfev),
+                                C.byref(info))
     n = lib().orc_static_ndof(C.byref(s), _ip(np.ascontiguousarray(indices, np.int32)), _dp(_f64(thetas)))
     return _split(g, counts.tolist(), (4, 4)), sol[:n].copy(), nfev.value, info.value

@@ -218,9 +218,9 @@ def test_large_batch_properties():
 
 
 @pytest.mark.parametrize("B", [1, 31, 33, 1000, 2369, 100_003])
-def test_grouped_and_one_warp_per_config_kernels_agree(B, monkeypatch):
+def test_grouped_and_one_warp_per_config_kernels_agree(B):
     """chain_eval_group_kernel (several configurations per warp; chunk size chosen from the batch size) and
-    chain_eval_kernel (one warp per configuration; CTRB_EVAL_GROUP=0) are two schedules of the same exact query:
+    chain_eval_kernel (one warp per configuration; ctx option eval_group = 0) are two schedules of the same exact query:
     identical bits, distances and costs on ragged batch sizes, mixed short and long configurations included."""
     from ctrdapp_b200.collision import CollisionChecker
     m = gpu_model("c3_three_tube")
@@ -230,10 +230,9 @@ def test_grouped_and_one_warp_per_config_kernels_agree(B, monkeypatch):
     long_ones = rng.random(B) < 0.2            # a fifth of the batch fully random (up to 198 cylinders)
     idx2, _ = random_configs(m.num_discrete_points, B, rng)
     idx[long_ones] = idx2[long_ones]
-    monkeypatch.delenv("CTRB_EVAL_GROUP", raising=False)
     a = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
-    monkeypatch.setenv("CTRB_EVAL_GROUP", "0")
-    b = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
+    with cc.ctx.options(eval_group=0):
+        b = cc.evaluate_batch(m, idx, theta, RAD3, goal_weight=3.0)
     for x, y in zip(a, b):
         np.testing.assert_array_equal(x, y)
 

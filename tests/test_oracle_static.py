@@ -121,3 +121,48 @@ def test_block_tridiagonal_inverse_formula():
         H[0:12, 0:12] += P
         H[15:27, 15:27] += Q
         assert np.max(np.abs(H @ J - np.eye(27))) < 1e-9 * np.linalg.cond(J)
+
+
+def test_one_step_rule_is_minpack_on_the_reduced_system():
+    """orc_static_solve_g_ex(one_step_rule=1) -- the semantics of the product's default treatment of one-step sections
+    (include/ctrb200.h, CTRB_OPT_STATIC_ONE_STEP) -- is hybrd on the system without the coincident columns and rows.
+    Pinned against the real MINPACK: scipy.optimize.root(method='hybr') on the reduced function assembled in Python from
+    the oracle's marched residual must land on the same unknowns; configurations without a one-step section are
+    untouched by the rule (bit-identical to the literal hybrd)."""
+    from scipy import optimize
+    s, _ = _model("c3_three_tube")
+    x0 = orc.static_init_guess(s)
+    N = np.array([34, 67, 100])
+    rng = np.random.default_rng(77)
+    B = 36
+    e = rng.integers(1, 9, (B, 3))
+    e[0::3, 0] = 1
+    e[1::3, 1] = 1
+    e[2::3, 0:2] = 1
+    e[B - 6:] = rng.integers(2, 9, (6, 3))       # no one-step section
+    idx = (N[None, :] - 1 - e).astype(np.int32)
+    th = rng.uniform(0, 2 * np.pi, (B, 3))
+    r1 = orc.static_batch(s, idx, th, one_step_rule=1, want_residual=True)
+    r0 = orc.static_batch(s, idx, th, one_step_rule=0)
+    for b in range(B):
+        pinned = ([2, 5, 8] if e[b, 0] == 1 else []) + ([17, 20, 23] if e[b, 1] == 1 else [])
+        if not pinned:
+            np.testing.assert_array_equal(r1["solution"][b], r0["solution"][b])
+            assert r1["nfev"][b] == r0["nfev"][b] and r1["info"][b] == r0["info"][b]
+            continue
+        keep = np.array([i for i in range(30) if i not in pinned])
+        scale = np.ones(30)
+        scale[[p - 1 for p in pinned]] = np.sqrt(2.0)    # delta_x = 1: the row of c_1 stands for those of c_1 and c_2
+
+        def fun(z):
+            x = x0.copy()
+            x[keep] = z
+            return (orc.static_residual(s, idx[b], th[b], x) * scale)[keep]
+        sol = optimize.root(fun, x0[keep], method="hybr")
+        x = x0.copy()
+        x[keep] = sol.x
+        assert bool(sol.success) == (r1["info"][b] == 1)
+        assert np.max(np.abs(x - r1["solution"][b])) <= 1e-6 * max(1.0, np.max(np.abs(x))), (b, e[b])
+        np.testing.assert_array_equal(r1["solution"][b][pinned], x0[pinned])   # the x^2 coefficients keep their initial value
+        # a root of the FULL residual: the dropped rows are copies of kept ones
+        assert np.linalg.norm(r1["residual"][b]) <= 3.0 * np.linalg.norm(sol.fun) + 1e-9
