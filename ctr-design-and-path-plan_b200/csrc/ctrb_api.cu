@@ -293,6 +293,7 @@ int ctrb_ctx_set_option(ctrb_ctx* c, int option, int value) {
     CTRB_REQUIRE(c, "ctx is NULL");
     CTRB_REQUIRE(option >= 0 && option < CTRB_OPT_COUNT, "unknown option %d", option);
     if (option == CTRB_OPT_GCURVE_BLOCKS) CTRB_REQUIRE(value >= 1 && value <= 32, "CTRB_OPT_GCURVE_BLOCKS must be in [1, 32]");
+    else if (option == CTRB_OPT_MAX_NODES_HINT) CTRB_REQUIRE(value >= 0 && value <= 1 << 20, "CTRB_OPT_MAX_NODES_HINT must be in [0, 2^20]");
     else CTRB_REQUIRE(value == 0 || value == 1, "option %d takes 0 or 1", option);
     c->opt[option] = value;
     return CTRB_OK;
@@ -344,6 +345,16 @@ int ctrb_static_last_fallbacks(ctrb_ctx* c, uint64_t* count) {
     unsigned long long h = 0;
     CTRB_CUDA(cudaMemcpy(&h, c->d_counters + 11, sizeof h, cudaMemcpyDeviceToHost));
     *count = h;
+    return CTRB_OK;
+}
+
+int ctrb_ctx_device_status(ctrb_ctx* c, int32_t* flags) {
+    CTRB_REQUIRE(c && flags, "ctrb_ctx_device_status: bad argument");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long h = 0;
+    CTRB_CUDA(cudaMemcpy(&h, c->d_counters + 12, sizeof h, cudaMemcpyDeviceToHost));
+    *flags = (int32_t)(h & 0xffffffffu);
     return CTRB_OK;
 }
 
@@ -637,10 +648,11 @@ int ctrb_eta_ftl_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int3
     CTRB_REQUIRE(prev_idx && delta_theta && prev_g && prev_offsets && eta_out, "NULL buffer");
     CTRB_REQUIRE((new_idx != nullptr) != (velocity != nullptr), "pass exactly one of new_idx and velocity");
     const size_t n = (size_t)B * m->mc.T;
-    void* dflag = nullptr;
-    int rc = ctx_scratch(ctx, 0, sizeof(int), &dflag);
-    if (rc) return rc;
-    CTRB_CUDA(cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
+    // device-side error flag of this call ("prev_g too short"): read back below for host buffers, through
+    // ctrb_ctx_device_status for device buffers (no synchronisation here)
+    void* dflag = ctx->d_counters + 12;
+    int rc = CTRB_OK;
+    CTRB_CUDA(cudaMemsetAsync(dflag, 0, sizeof(unsigned long long), ctx->stream));
     if (mem == CTRB_MEM_DEVICE) {
         return launch_eta_ftl(ctx, m, B, prev_idx, new_idx, velocity, delta_theta, prev_g, (const long long*)prev_offsets, eta_out,
                               ftl_out, ftl_mag, (int*)dflag);
@@ -688,8 +700,14 @@ int ctrb_check_collision_batch(ctrb_ctx* ctx, const ctrb_env* env, int64_t B, in
     if (B == 0) return CTRB_OK;
     CTRB_REQUIRE(g && node_offsets && rad && obstacle_min && goal_dist, "NULL buffer");
     const size_t n = (size_t)B * tube_num;
+    if (mem == CTRB_MEM_DEVICE && ctx->opt[CTRB_OPT_MAX_NODES_HINT] > 0) {
+        // the caller states the longest curve (nodes per configuration): nothing to read back, no synchronisation
+        return launch_eval_curves(ctx, env, B, tube_num, g, (const long long*)node_offsets, ctx->opt[CTRB_OPT_MAX_NODES_HINT], rad,
+                                  obstacle_min, goal_dist);
+    }
     if (mem == CTRB_MEM_DEVICE) {
-        // max nodes per configuration is needed for the shared-memory carve-up: read the offsets back
+        // max nodes per configuration is needed for the shared-memory carve-up: without CTRB_OPT_MAX_NODES_HINT the
+        // offsets are read back (one stream synchronisation, documented in the header)
         std::vector<int64_t> h(n + 1);
         CTRB_CUDA(cudaMemcpyAsync(h.data(), node_offsets, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CTRB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -937,7 +955,8 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
         rc = launch_offsets(ctx, m, nb, di + b0 * T, 0, (long long*)doff);
         if (rc) return rc;
         rc = launch_static_solve(ctx, m->sm, nb, di + b0 * T, dt + b0 * T, nullptr, 0, 0.0, (const long long*)doff, (double*)dg,
-                                 nullptr, dnf ? dnf + b0 : nullptr, dinf ? dinf + b0 : nullptr, 1);
+                                 nullptr, dnf ? dnf + b0 : nullptr, dinf ? dinf + b0 : nullptr,
+                                 ctx->opt[CTRB_OPT_STATIC_CURVES_SCAN] ? 2 : 1);
         if (rc) return rc;
         rc = launch_eval_curves_cost(ctx, env, cd, nb, T, (const double*)dg, (const long long*)doff, m->mc.total_nodes, rad,
                                      dob + b0, dgo + b0, dco ? dco + b0 : nullptr, dcl ? dcl + b0 : nullptr, 1);

@@ -592,6 +592,107 @@ __global__ void __launch_bounds__(kCWarps * 32)
     }
 }
 
+// The same curves for the fused solve -> collision path, which reads node positions only: ONE THREAD per configuration
+// walks its three section curves serially (Magnus step, SE(3) product, 24 B store per node).  The warp-per-configuration
+// scan above keeps 5 of 32 lanes busy on a "shallow" section (5 nodes) and spends four scan rounds on it; a lane per
+// configuration does each node's work once: ~400 instructions per node and lane, 32 configurations per warp.
+// (The 4x4 output of Static.solve_g keeps the scan kernel: its stores are coalesced 128 B rows.)
+__device__ __forceinline__ void omega_poly(const double* qs, double x, double w[3]) {
+    w[0] = poly3(qs, x);
+    w[1] = poly3(qs + 3, x);
+    w[2] = poly3(qs + 6, x);
+}
+__device__ __forceinline__ void omega_last(const StModel& sm_, const double* qs, double x, double w[3]) {
+    CTRB_USE_SM;
+    const int T = sm.mc.T, dof = sm.mc.dof[T - 1];
+    w[0] = w[1] = w[2] = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < dof; ++k) {
+        int r;
+        double v;
+        strain_base_col(sm.mc.kind[T - 1], dof, k, x, &r, &v);
+        const double t = v * qs[k];
+        w[0] += r == 0 ? t : 0.0;
+        w[1] += r == 1 ? t : 0.0;
+        w[2] += r == 2 ? t : 0.0;
+    }
+}
+// nodes 0 .. count-1 of one section curve (positions), serially; returns the last node.  kLast: the section of the last
+// tube alone (its own strain base, evaluated at the section coordinate + idx33 once more, static_bases.py:77-81)
+template <bool kLast>
+__device__ __forceinline__ SE3 chain_section_pos(const StModel& sm_, const double* qs, int i33, int start, int count, SE3 g,
+                                                 double* __restrict__ out) {
+    CTRB_USE_SM;
+    const double dx = sm.mc.dx;
+    const double cg1 = 0.5 - sqrt(3.0) / 6, cg2 = 0.5 + sqrt(3.0) / 6;  // static.py:597-599
+    out[0] = g.p[0]; out[1] = g.p[1]; out[2] = g.p[2];
+#pragma unroll 1
+    for (int k = 1; k < count; ++k) {
+        const double si = (double)(start + k);
+        double wA[3], wB[3];
+        if (kLast) {
+            omega_last(sm, qs, (si + cg1 - 1 + i33) * dx, wA);
+            omega_last(sm, qs, (si + cg2 - 1 + i33) * dx, wB);
+        } else {
+            omega_poly(qs, (si + cg1 - 1) * dx, wA);
+            omega_poly(qs, (si + cg2 - 1) * dx, wB);
+        }
+        g = se3_mul(g, magnus_step(wA, wB, dx));
+        out[3 * k + 0] = g.p[0]; out[3 * k + 1] = g.p[1]; out[3 * k + 2] = g.p[2];
+    }
+    return g;
+}
+constexpr int kCPThreads = 128;
+__global__ void __launch_bounds__(kCPThreads)
+    static_curves_pos_kernel(const __grid_constant__ StModel sm_, long long B, const int32_t* __restrict__ idx,
+                             const double* __restrict__ theta, const double* __restrict__ sol,
+                             const long long* __restrict__ offsets, double* __restrict__ pos_out) {
+    load_model(sm_);
+    const StModel& sm = g_sm;
+    const long long b = (long long)blockIdx.x * kCPThreads + threadIdx.x;
+    if (b >= B) return;
+    const int T = sm.mc.T, n = sm.nq;
+    const int* N = sm.mc.npts;
+    const double dx = sm.mc.dx;
+    const int32_t* ib = idx + b * T;
+    const double* q = sol + b * n;
+    int i11 = ib[0];
+    const int i22 = ib[T - 2], i33 = ib[T - 1];   // static.py:81-95
+    int i21 = i22 - (N[0] - i11 - 1);
+    const int i32 = i33 - (N[T - 2] - i22 - 1);
+    int i31 = i32 - (N[0] - i11 - 1);
+    if (T == 2) i11 = i21 = i31 = 0;
+    const int L0 = T == 3 ? N[0] - i11 : 1, L1 = N[T - 2] - i22, L2 = N[T - 1] - i33;
+    double qs[9];
+    SE3 g11_last, g21_last, g31_last;
+    se3_identity(g11_last);
+    if (T == 3) {  // static.py:110-113
+#pragma unroll
+        for (int k = 0; k < 9; ++k) qs[k] = q[sm.qoff[0] + k];
+        g11_last = chain_section_pos<false>(sm, qs, 0, i11, L0, se3_rx(theta[b * T + 0]), pos_out + offsets[b * T + 0] * 3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) qs[k] = q[sm.qoff[1] + k];
+        g21_last = se3_rx(theta[b * T + 1] + ipoly3_abs(qs, i21 * dx, (i21 + L0 - 1) * dx));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) qs[k] = q[sm.qoff[2] + k];
+        g31_last = se3_rx(theta[b * T + 2] + ipoly3_abs(qs, i31 * dx, (i31 + L0 - 1) * dx));
+    } else {       // static.py:114-118
+        g21_last = se3_rx(theta[b * T + 0]);
+        g31_last = se3_rx(theta[b * T + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) qs[k] = q[sm.qoff[3] + k];
+    const SE3 g22_last = chain_section_pos<false>(sm, qs, 0, i22, L1, se3_mul(g11_last, g21_last),
+                                                  pos_out + offsets[b * T + (T - 2)] * 3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) qs[k] = q[sm.qoff[4] + k];
+    const SE3 g32_last = se3_rx(ipoly3_abs(qs, i32 * dx, (i32 + L1 - 1) * dx));
+#pragma unroll 1
+    for (int k = 0; k < CTRB_MAX_DOF; ++k) qs[k] = k < sm.ndof[5] ? q[sm.qoff[5] + k] : 0.0;
+    chain_section_pos<true>(sm, qs, i33, i33, L2, se3_mul(se3_mul(g22_last, g31_last), g32_last),
+                            pos_out + offsets[b * T + (T - 1)] * 3);
+}
+
 // residual only (parity tests): one thread per (config) evaluates F(q)
 __global__ void static_residual_kernel(StModel sm_, long long B, const int32_t* __restrict__ idx,
                                        const double* __restrict__ theta, const double* __restrict__ q,
@@ -749,8 +850,14 @@ int launch_static_curves(ctrb_ctx* ctx, const StModel& sm, long long B, const in
     KernelTimer kc(ctx, CTRB_KERNEL_STATIC_CURVES);
     const long long blocks = (B + kCWarps - 1) / kCWarps;
     const int cgrid = (int)std::min<long long>(blocks, (long long)ctx->sm_count * 16);
-    if (pos_only) static_curves_kernel<true><<<cgrid, kCWarps * 32, 0, ctx->stream>>>(sm, B, idx, theta, sol, offsets, g_out);
-    else static_curves_kernel<false><<<cgrid, kCWarps * 32, 0, ctx->stream>>>(sm, B, idx, theta, sol, offsets, g_out);
+    if (pos_only == 1) {
+        static_curves_pos_kernel<<<(unsigned)((B + kCPThreads - 1) / kCPThreads), kCPThreads, 0, ctx->stream>>>(sm, B, idx, theta, sol,
+                                                                                                              offsets, g_out);
+    } else if (pos_only == 2) {  // the scan kernel writing positions (parity test of the lane-per-configuration kernel)
+        static_curves_kernel<true><<<cgrid, kCWarps * 32, 0, ctx->stream>>>(sm, B, idx, theta, sol, offsets, g_out);
+    } else {
+        static_curves_kernel<false><<<cgrid, kCWarps * 32, 0, ctx->stream>>>(sm, B, idx, theta, sol, offsets, g_out);
+    }
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());
     return CTRB_OK;

@@ -63,6 +63,7 @@ SYMBOLS = {
     "ctrb_ctx_last_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
     "ctrb_static_last_fallbacks": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "ctrb_ctx_work_counters": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "ctrb_ctx_device_status": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "ctrb_model_create": (C.c_int, [_vp, C.POINTER(ModelDesc), C.POINTER(_vp)]),
     "ctrb_model_destroy": (None, [_vp]),
     "ctrb_model_num_points": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
@@ -193,7 +194,7 @@ class Context:
                "static_curves": 6}
     # ctrb_option (include/ctrb200.h): run-time switches for parity tests and measurement
     OPTIONS = {"static_solver": 0, "static_one_step": 1, "fast_generic_n": 2, "fast_block_invert": 3, "eval_group": 4,
-               "gcurve_blocks": 5}
+               "gcurve_blocks": 5, "max_nodes_hint": 6, "static_curves_scan": 7}
 
     def set_option(self, name, value):
         check(lib().ctrb_ctx_set_option(self._h, self.OPTIONS[name], int(value)))
@@ -228,6 +229,11 @@ class Context:
         n = C.c_uint64()
         check(lib().ctrb_static_last_fallbacks(self._h, C.byref(n)))
         return int(n.value)
+
+    def device_status(self):
+        f = C.c_int32()
+        check(lib().ctrb_ctx_device_status(self._h, C.byref(f)))
+        return int(f.value)
 
     def work_counters(self):
         out = (C.c_uint64 * 4)()

@@ -106,7 +106,7 @@ class Kinematic(Model):
         prev_offsets = np.ascontiguousarray(prev_offsets, np.int64)
         B = prev_idx.shape[0]
         eta = np.empty((B, self.tube_num, 6))
-        ftl = np.empty((int(prev_offsets[-1]), 6)) if want_ftl else None
+        ftl = np.zeros((int(prev_offsets[-1]), 6)) if want_ftl else None  # rows beyond npts - prev_idx stay zero
         mag = np.empty((B, 4))
         L.check(L.lib().ctrb_eta_ftl_batch(self.ctx.handle, self._h, B, L.ptr(prev_idx), L.ptr(new_idx),
                                            L.ptr(velocity), L.ptr(delta_theta), L.ptr(prev_g), L.ptr(prev_offsets), L.ptr(eta),
@@ -129,7 +129,15 @@ class Kinematic(Model):
         prev_idx, new_idx = self.calculate_indices_batch(this_insertion - delta_insertion, this_insertion)
         g, off = self.solve_g_batch(new_idx, this_theta, full=False) if need_g_out else (None, None)
         eta, ftl, mag = self.eta_ftl_batch(prev_idx, new_idx, delta_theta, prev_g, prev_offsets, want_ftl=want_ftl)
-        true_ins = lengths - new_idx * self.delta_x if invert_insert else new_idx * float(self.delta_x)
+        # kinematic.py:74-78: `length - ind * delta_x` is Python arithmetic -- integer tube lengths and delta_x give integer
+        # insertions (tree.txt then reads "3, 6, 9", and TreeFromFile parses them back with int())
+        integral = isinstance(self.delta_x, (int, np.integer)) and \
+            all(isinstance(v, (int, np.integer)) for v in self.max_tube_length)
+        if integral:
+            li = np.asarray(self.max_tube_length, np.int64)[None, :]
+            true_ins = li - new_idx.astype(np.int64) * int(self.delta_x) if invert_insert else new_idx.astype(np.int64) * int(self.delta_x)
+        else:
+            true_ins = lengths - new_idx * self.delta_x if invert_insert else new_idx * float(self.delta_x)
         return {"g": g, "offsets": off, "eta": eta, "insert_indices": new_idx, "prev_indices": prev_idx,
                 "true_insertions": true_ins, "ftl": ftl, "ftl_mag": mag}
 

@@ -156,7 +156,10 @@ class RRT(Solver):
             out["true_insertion"][c] = res["true_insertions"][c].tolist()
             out["ftl_mag"][c] = res["ftl_mag"][c]
             if want_arrays:
-                out["ftl"][c] = [res["ftl"][offs[c * T + n]:offs[c * T + n + 1]] for n in range(T)]
+                # kin_eta_ftl_kernel writes npts - prev_idx rows per tube (kinematic.py:181-193); the parent's curve holds
+                # exactly that many nodes unless the index rounding moved (then the library reports an error)
+                need = [self.model.num_discrete_points[n] - int(res["prev_indices"][c][n]) for n in range(T)]
+                out["ftl"][c] = [res["ftl"][offs[c * T + n]:offs[c * T + n] + need[n]] for n in range(T)]
         return out
 
     def _packed(self, node_index):

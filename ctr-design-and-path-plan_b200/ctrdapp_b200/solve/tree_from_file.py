@@ -25,7 +25,11 @@ def _order_nodes(file):
             f = line.split(" | ")
             ind = int(f[0])
             parent = None if ind == 0 else int(f[3])
-            nodes.append({"ins": [int(v) for v in f[1].split(", ")], "rot": [float(v) for v in f[2].split(", ")],
+            # the reference parses insertions with int() (tree_from_file.py:28), which only reads back trees whose tube
+            # lengths and delta_x are integers; fractional insertions ("2.5") are accepted here as well
+            ins = [float(v) for v in f[1].split(", ")]
+            ins = [int(v) if v == int(v) else v for v in ins]
+            nodes.append({"ins": ins, "rot": [float(v) for v in f[2].split(", ")],
                           "parent": parent, "cost": float(f[4]), "goal": _to_bool(f[5])})
             children.setdefault(parent, []).append(ind)
     order = deque(children.get(0, []))
@@ -58,7 +62,7 @@ class TreeFromFile(RRT):
             return
         nodes = [self.nodes_list[i] for i in todo]
         # insertion indices from the values (inverse insertion, tree_from_file.py:42)
-        idx = [[int((length - ins) / self.delta_x) for ins, length in zip(n["ins"], self.tube_lengths)] for n in nodes]
+        idx = [[int(round((length - ins) / self.delta_x)) for ins, length in zip(n["ins"], self.tube_lengths)] for n in nodes]
         T = self.tube_num
         if hasattr(self.model, "solve_g_batch"):
             g, off = self.model.solve_g_batch(idx, [n["rot"] for n in nodes], full=False)

@@ -16,7 +16,13 @@
  *     CTRB_MEM_HOST (the library stages through pinned buffers and copies
  *     H2D/D2H itself, synchronous on return) or CTRB_MEM_DEVICE (pointers are
  *     device pointers on the ctx's device; the call is stream-ordered on the
- *     ctx's stream and returns without synchronising).
+ *     ctx's stream and returns without synchronising).  The exceptions are
+ *     named where they occur: entry points that return a host scalar
+ *     (ctrb_argmin_cost, the *_last_* / counter / status queries),
+ *     ctrb_check_collision_batch without CTRB_OPT_MAX_NODES_HINT, and the
+ *     first call at a larger batch size, when a grow-only scratch buffer is
+ *     reallocated.  Indices in device memory are not validated: the caller
+ *     guarantees 0 <= idx[b][t] < npts[t].
  *   - handles (model, env) are immutable after create: concurrent batch calls
  *     with different ctx objects are legal.  A ctx owns one CUDA stream and
  *     its scratch buffers and must not be used from two threads at once.
@@ -161,7 +167,11 @@ typedef enum {
     CTRB_OPT_FAST_BLOCK_INVERT = 3, /* 0: general Gauss-Jordan inverse (default 1: block-structured for three tubes) */
     CTRB_OPT_EVAL_GROUP = 4,        /* 0: one warp per configuration in the collision kernel (default 1: grouped) */
     CTRB_OPT_GCURVE_BLOCKS = 5,     /* resident blocks per SM of the g-curve kernel's persistent grid (default 3) */
-    CTRB_OPT_COUNT = 6
+    CTRB_OPT_MAX_NODES_HINT = 6,    /* ctrb_check_collision_batch(CTRB_MEM_DEVICE): upper bound on the nodes of one
+                                       configuration's curves; 0 (default) = read the offsets back, which synchronises */
+    CTRB_OPT_STATIC_CURVES_SCAN = 7,/* ctrb_static_eval_batch: 1 = node positions from the warp-per-configuration scan kernel
+                                       instead of the thread-per-configuration one (default 0); parity test of the two */
+    CTRB_OPT_COUNT = 8
 } ctrb_option;
 int ctrb_ctx_set_option(ctrb_ctx* ctx, int option, int value);
 int ctrb_ctx_get_option(const ctrb_ctx* ctx, int option, int* value);
@@ -274,6 +284,10 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
  * (bench publishes them): [0] BVH nodes visited, [1] fp32 point-triangle
  * prefilter tests, [2] exact fp64 cylinder-triangle tests, [3] configurations. Synchronises. */
 int ctrb_ctx_work_counters(ctrb_ctx* ctx, uint64_t out[4]);
+/* device-side error flags of the most recent ctrb_eta_ftl_batch on this ctx: bit 0 = a tube of prev_g held fewer
+ * nodes than npts - prev_idx (IndexError in the reference).  Host-buffer calls report this as CTRB_ERR_INVALID
+ * themselves; device-buffer calls do not synchronise, so their caller asks here.  Synchronises. */
+int ctrb_ctx_device_status(ctrb_ctx* ctx, int32_t* flags);
 
 /* ---- nearest neighbours of the planner's node store: replaces DynamicTree.nearest_neighbor /
  *      find_all_nearest_neighbor (dynamic_tree.py:66-120), i.e. pympnn.KDTree_topologies.k_nearest_neighbor,

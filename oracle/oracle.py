@@ -459,6 +459,22 @@ def static_batch(s, idx, theta, env=None, rad=None, goal_weight=0.0, one_step_ru
     return out
 
 
+def curves_eval_batch(env, g, offsets, tube_num, rad, goal_weight, nthreads=None):
+    """check_collision + SOAPWG own cost on GIVEN packed curves (g [nodes,4,4], offsets [B*T+1]) -> obs, goal, cost."""
+    g = _f64(g).reshape(-1, 16)
+    off = np.ascontiguousarray(offsets, np.int64)
+    B = (off.size - 1) // tube_num
+    obs, goal, cost = np.zeros(B), np.zeros(B), np.zeros(B)
+    f = lib().orc_curves_eval_batch
+    f.argtypes = None
+    rc = f(C.c_void_p(env._h), C.c_int(B), C.c_int(tube_num), _dp(g), off.ctypes.data_as(C.POINTER(C.c_longlong)),
+           _dp(_f64(rad)), C.c_double(goal_weight), _dp(obs), _dp(goal), _dp(cost),
+           C.c_int(nthreads or len(os.sched_getaffinity(0))))
+    if rc:
+        raise NotImplementedError("unsupported obstacle in oracle")
+    return obs, goal, cost
+
+
 def static_solve_g(s, indices, thetas, initial_guess=None, xtol=0.0, one_step_rule=0):
     """Static.solve_g (static.py:71-135) -> (g list, solution x, nfev, info).  one_step_rule: see static_batch."""
     T = s.m.tube_num
