@@ -61,6 +61,7 @@ int launch_eval_curves(ctrb_ctx* ctx, const ctrb_env* env, long long B, int tube
                        const long long* offsets, int max_nodes, const double* rad, double* obstacle_min,
                        double* goal_dist);
 int launch_argmin(ctrb_ctx* ctx, long long B, const double* cost, unsigned long long* key_out);
+int launch_argmin_finish(ctrb_ctx* ctx, const unsigned long long* key, long long index_base, long long* out);
 int launch_eval_curves_cost(ctrb_ctx* ctx, const ctrb_env* env, const ctrb_cost_desc* cd, long long B, int tube_num,
                             const double* g, const long long* offsets, int max_nodes, const double* rad,
                             double* obstacle_min, double* goal_dist, double* cost, uint8_t* collide, int pos_only);
@@ -1032,6 +1033,39 @@ int ctrb_argmin_cost(ctrb_ctx* ctx, int64_t B, const double* cost, int64_t index
         *best_index = index_base + (int64_t)h[1];
     }
     return CTRB_OK;
+}
+
+int ctrb_argmin_cost_device(ctrb_ctx* ctx, int64_t B, const double* cost, int64_t index_base, int64_t* key_index) {
+    CTRB_ENTER(ctx);
+    CTRB_REQUIRE(B >= 0 && key_index && (B == 0 || cost), "bad argument");
+    CTRB_REQUIRE(B < (1LL << 31), "at most 2^31-1 costs per call");
+    void* dkey = nullptr;
+    int rc = ctx_scratch(ctx, 0, 2 * sizeof(unsigned long long), &dkey);
+    if (rc) return rc;
+    if (B > 0) {
+        rc = launch_argmin(ctx, B, cost, (unsigned long long*)dkey);
+        if (rc) return rc;
+    } else {
+        CTRB_CUDA(cudaMemsetAsync(dkey, 0xff, 2 * sizeof(unsigned long long), ctx->stream));
+    }
+    return launch_argmin_finish(ctx, (const unsigned long long*)dkey, index_base, (long long*)key_index);
+}
+
+// the monotone map of argmin_key_kernel (cost_key) with the sign bit flipped so that SIGNED comparison orders the costs
+int64_t ctrb_cost_to_key(double cost) {
+    unsigned long long b;
+    std::memcpy(&b, &cost, sizeof b);
+    b = (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+    return (int64_t)(b ^ 0x8000000000000000ULL);
+}
+
+double ctrb_key_to_cost(int64_t key) {
+    if (key == INT64_MAX) return INFINITY;
+    unsigned long long b = (unsigned long long)key ^ 0x8000000000000000ULL;
+    b = (b & 0x8000000000000000ULL) ? (b & 0x7fffffffffffffffULL) : ~b;
+    double c;
+    std::memcpy(&c, &b, sizeof c);
+    return c;
 }
 
 }  // extern "C"

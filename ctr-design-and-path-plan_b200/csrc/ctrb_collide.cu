@@ -1364,6 +1364,21 @@ __global__ void argmin_index_kernel(long long B, const double* __restrict__ cost
     }
 }
 
+// key_out (from launch_argmin) -> out[0] = signed order-preserving key, out[1] = index_base + index (INT64_MAX: none)
+__global__ void argmin_finish_kernel(const unsigned long long* __restrict__ key, long long index_base, long long* __restrict__ out) {
+    const unsigned long long k = key[0], i = key[1];
+    const bool none = k == ~0ULL || i == ~0ULL;
+    out[0] = none ? 0x7fffffffffffffffLL : (long long)(k ^ 0x8000000000000000ULL);
+    out[1] = none ? 0x7fffffffffffffffLL : index_base + (long long)i;
+}
+
+int launch_argmin_finish(ctrb_ctx* ctx, const unsigned long long* key, long long index_base, long long* out) {
+    argmin_finish_kernel<<<1, 1, 0, ctx->stream>>>(key, index_base, out);
+    ctx->launches++;
+    CTRB_CUDA(cudaGetLastError());
+    return CTRB_OK;
+}
+
 int launch_argmin(ctrb_ctx* ctx, long long B, const double* cost, unsigned long long* key_out) {
     CTRB_CUDA(cudaMemsetAsync(key_out, 0xff, 2 * sizeof(unsigned long long), ctx->stream));
     int grid = (int)std::min<long long>((B + 255) / 256, (long long)ctx->sm_count * 8);

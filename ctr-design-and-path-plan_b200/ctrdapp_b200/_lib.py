@@ -88,6 +88,9 @@ SYMBOLS = {
                                   C.c_int]),
     "ctrb_knn_batch": (C.c_int, [_vp, C.c_int32, _i64, _vp, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_int]),
     "ctrb_argmin_cost": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(C.c_double), C.POINTER(_i64), C.c_int]),
+    "ctrb_argmin_cost_device": (C.c_int, [_vp, _i64, _vp, _i64, _vp]),
+    "ctrb_key_to_cost": (C.c_double, [_i64]),
+    "ctrb_cost_to_key": (_i64, [C.c_double]),
 }
 
 _lib = None

@@ -62,17 +62,42 @@ class NelderMead(Optimizer):
         init_simplex = conf.get('initial_simplex') or calculate_simplex(conf.get('strain_bases'), radius, conf.get('tube_lengths'),
                                                                         conf.get('q_dof'), self.initial_guess)
         start = time.time()
+        # Speculative evaluation only pays when other ranks would idle: by default one speculative point per idle rank
+        # (none in a single process, where the run is then SciPy's algorithm evaluation for evaluation, as the
+        # reference's); 'speculate' in the configuration overrides (True = all three, or a count).
+        world = self._eval.world_size()
+        speculate = conf.get('speculate')
+        if speculate is None:
+            speculate = min(3, world - 1)
         res = nelder_mead(self._record, init_simplex, xatol=self.precision, fatol=self.precision,
-                          maxfev=conf.get('optimize_iterations'), speculate=bool(conf.get('speculate', True)))
-        result = OptimizeResult(res.x, self.best_solver.get('solver'), res.success, res.nfev, res.nit, time.time() - start,
-                                self.solver_results)
+                          maxfev=conf.get('optimize_iterations'), speculate=speculate, on_request=self._expect)
+        # speculative points the algorithm then asked for are ordinary evaluations; the others stay tagged, so that
+        # optimize_process.txt lists what the reference's sequential run would have listed
+        used = {tuple(np.asarray(x, float)) for x in res.used_speculative}
+        for entry in self.solver_results:
+            if entry.get('speculative') and tuple(entry['q']) in used:
+                entry['speculative'] = False
+        # every rank ran its own share of the designs: the solver behind the overall best cost lives on ONE rank
+        best_rank = self._eval.owner_of_lowest(self.best_solver.get('cost'))
+        mine = self._eval.rank() == best_rank
+        result = OptimizeResult(res.x, self.best_solver.get('solver') if mine else None, res.success, res.nfev, res.nit,
+                                time.time() - start, [e for e in self.solver_results if not e.get('speculative')])
         result.num_speculative_eval = res.nfev_speculative
+        result.speculative_results = [e for e in self.solver_results if e.get('speculative')]
+        result.best_rank = best_rank          # the rank whose result.best_solver is set: call save_result there
+        result.owns_best_solver = mine
         return result
+
+    def _expect(self, n_speculative):
+        self._n_speculative = n_speculative
 
     def _record(self, xs):
         costs = self._eval(xs)
-        for x, c in zip(xs, costs):
-            self.solver_results.append({'q': list(np.asarray(x, float)), 'cost': c})
+        n_spec = getattr(self, "_n_speculative", 0)
+        for k, (x, c) in enumerate(zip(xs, costs)):
+            # the trailing n_spec points of the request are speculative until the algorithm asks for them (find_min
+            # clears the tag then)
+            self.solver_results.append({'q': list(np.asarray(x, float)), 'cost': c, 'speculative': k >= len(xs) - n_spec})
         return costs
 
     def solver_heuristic(self, x):

@@ -20,8 +20,17 @@ class NelderMeadResult(dict):
     __getattr__ = dict.get
 
 
-def nelder_mead(eval_many, initial_simplex, xatol=1e-4, fatol=1e-4, maxfev=None, maxiter=None, speculate=True):
+def nelder_mead(eval_many, initial_simplex, xatol=1e-4, fatol=1e-4, maxfev=None, maxiter=None, speculate=True, on_request=None):
+    """speculate: False / 0 = SciPy's one point at a time; True / 3 = reflected + expanded + both contracted points side by
+    side; 1 or 2 = that many of [expanded, contracted, inner-contracted] beside the reflected point (as many as there are
+    idle ranks).  The result's `used_speculative` lists the speculative points the sequential algorithm then asked for.
+    on_request(n_speculative) is called before every eval_many request with the number of its TRAILING points that are
+    speculative (0 for the initial simplex, a shrink step or a point the algorithm asks for by itself)."""
+    note = on_request or (lambda n_speculative: None)
     sim = np.array(initial_simplex, dtype=np.float64)
+    nspec = 3 if speculate is True else int(speculate or 0)
+    nspec = max(0, min(3, nspec))
+    used = []
     n = sim.shape[1]
     if sim.shape[0] != n + 1:
         raise ValueError("`initial_simplex` should be an array of shape (N+1,N)")
@@ -34,6 +43,7 @@ def nelder_mead(eval_many, initial_simplex, xatol=1e-4, fatol=1e-4, maxfev=None,
 
     budget = int(min(n + 1, maxfev))
     fsim = np.full(n + 1, np.inf)
+    note(0)
     fsim[:budget] = eval_many([sim[k] for k in range(budget)])
     nfev += budget
     order = np.argsort(fsim, kind="stable")
@@ -47,16 +57,13 @@ def nelder_mead(eval_many, initial_simplex, xatol=1e-4, fatol=1e-4, maxfev=None,
         xe = (1 + rho * chi) * xbar - rho * chi * sim[-1]
         xc = (1 + psi * rho) * xbar - psi * rho * sim[-1]
         xcc = (1 - psi) * xbar + psi * sim[-1]
-        if speculate:
-            fxr, fxe, fxc, fxcc = eval_many([xr, xe, xc, xcc])
-            spec += 4
-            lazy = {"e": fxe, "c": fxc, "cc": fxcc}
-        else:
-            (fxr,) = eval_many([xr])
-            lazy = {}
+        cand = [("e", xe), ("c", xc), ("cc", xcc)][:nspec]
+        note(len(cand))
+        vals = eval_many([xr] + [x for _, x in cand])
+        fxr = vals[0]
+        lazy = {tag: (x, v) for (tag, x), v in zip(cand, vals[1:])}
+        spec += len(cand)
         nfev += 1
-        if speculate:
-            spec -= 1
 
         def need(tag, x):
             """value of a point the sequential algorithm evaluates now"""
@@ -64,7 +71,9 @@ def nelder_mead(eval_many, initial_simplex, xatol=1e-4, fatol=1e-4, maxfev=None,
             nfev += 1
             if tag in lazy:
                 spec -= 1
-                return lazy[tag]
+                used.append(np.array(lazy[tag][0]))
+                return lazy[tag][1]
+            note(0)
             return eval_many([x])[0]
 
         doshrink = False
@@ -91,6 +100,7 @@ def nelder_mead(eval_many, initial_simplex, xatol=1e-4, fatol=1e-4, maxfev=None,
         if doshrink:
             for j in range(1, n + 1):
                 sim[j] = sim[0] + sigma * (sim[j] - sim[0])
+            note(0)
             fsim[1:] = eval_many([sim[j] for j in range(1, n + 1)])
             nfev += n
         order = np.argsort(fsim, kind="stable")
@@ -98,7 +108,7 @@ def nelder_mead(eval_many, initial_simplex, xatol=1e-4, fatol=1e-4, maxfev=None,
         nit += 1
     success = nfev < maxfev and nit < maxiter
     return NelderMeadResult(x=sim[0].copy(), fun=float(fsim[0]), nit=nit, nfev=nfev, nfev_speculative=spec, success=bool(success),
-                            final_simplex=(sim, fsim))
+                            final_simplex=(sim, fsim), used_speculative=used)
 
 
 class DistributedEvaluator:
@@ -109,6 +119,29 @@ class DistributedEvaluator:
     def __init__(self, func, device="cpu", group=None):
         self.func, self.device, self.group = func, device, group
         self.calls = 0
+
+    def world_size(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
+    def rank(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 0
+        return dist.get_rank(self.group)
+
+    def owner_of_lowest(self, local_value):
+        """rank holding the lowest of the ranks' local values (lowest rank on a tie); one all_gather of a float64"""
+        import torch
+        import torch.distributed as dist
+        if self.world_size() == 1:
+            return 0
+        mine = torch.tensor([float(local_value)], dtype=torch.float64, device=self.device)
+        out = torch.empty(self.world_size(), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        return int(np.argmin(out.cpu().numpy()))
 
     def __call__(self, xs):
         import torch

@@ -305,6 +305,14 @@ int ctrb_knn_batch(ctrb_ctx* ctx, int32_t dim, int64_t N, const double* points, 
  * key = monotone fp64 bits of the cost (upper 64 - 24 bits) ... see DESIGN.md. */
 int ctrb_argmin_cost(ctrb_ctx* ctx, int64_t B, const double* cost, int64_t index_base, double* best_cost,
                      int64_t* best_index, int mem);
+/* The same reduction left on the device (cost and key_index are device pointers; stream-ordered, no synchronisation):
+ * key_index[0] = order-preserving signed 64-bit image of the lowest finite cost (INT64_MAX if there is none; decode
+ * with ctrb_key_to_cost), key_index[1] = index_base + its lowest index (INT64_MAX if none).  One process per GPU then
+ * needs two 8-byte all-reduce(min) steps -- the key, then the index among the ranks that hold that key -- to agree on
+ * the best node (ctrdapp_b200/dist.py: reduce_best). */
+int ctrb_argmin_cost_device(ctrb_ctx* ctx, int64_t B, const double* cost, int64_t index_base, int64_t* key_index);
+double ctrb_key_to_cost(int64_t key);
+int64_t ctrb_cost_to_key(double cost);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,10 @@ def main():
         lo, hi = cdist.shard_range(len(costs), rank, world)
         c, i = cdist.local_best(costs[lo:hi], lo)
         best = cdist.gather_best(c, i)
+        # the same through the device-shaped path: this rank's [key, index] tensor, two all-reduce(min) steps
+        import torch
+        t = torch.tensor([cdist.cost_to_key(c) if i >= 0 else cdist.INT64_MAX, i if i >= 0 else cdist.INT64_MAX], dtype=torch.int64)
+        assert cdist.decode_best(cdist.reduce_best(t)) == best
         per = len(costs) // world
         allc = cdist.gather_costs(costs[rank * per:(rank + 1) * per]).numpy()
         print(json.dumps({"rank": rank, "best": best, "costs_ok": bool(np.array_equal(allc, costs[:per * world], equal_nan=True))}),

@@ -15,5 +15,8 @@ dist.init_process_group("gloo", rank=rank, world_size=world)
 ev = DistributedEvaluator(rosen)
 simplex = np.random.default_rng(11).uniform(-1.5, 1.5, (6, 5))
 res = nelder_mead(ev, simplex, xatol=1e-6, fatol=1e-6, maxfev=3000)
+# the rank that holds the lowest local value (here: a made-up one per rank) is the same on both ranks
+owner = ev.owner_of_lowest(3.0 - rank)
+assert owner == world - 1 and ev.world_size() == world and ev.rank() == rank
 np.savez(out / f"rank{rank}.npz", x=res.x, nit=res.nit, nfev=res.nfev, calls=ev.calls)
 dist.destroy_process_group()

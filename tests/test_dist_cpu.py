@@ -51,3 +51,21 @@ def test_gloo_two_ranks_best_node(tmp_path):
     for so, _ in outs:
         res = json.loads(so.strip().splitlines()[-1])
         assert tuple(res["best"]) == want and res["costs_ok"]
+
+
+def test_cost_key_is_order_preserving():
+    """The packed key of the best-node reduction (ctrb_cost_to_key / dist.cost_to_key): signed 64-bit, a < b iff key(a) < key(b),
+    exact round trip, NaN / inf (colliding, no candidate) above every finite cost; the C and the NumPy version agree."""
+    from ctrdapp_b200 import _lib
+    rng = np.random.default_rng(3)
+    v = np.concatenate([rng.standard_normal(2000) * 10.0 ** rng.integers(-300, 300, 2000), [0.0, 1e-320, -1e-320, 1.0, -1.0]])
+    k = cdist.cost_to_key(v)
+    order = np.argsort(v, kind="stable")
+    assert np.all(np.diff(k[order]) >= 0) and np.all((np.diff(k[order]) > 0) == (np.diff(v[order]) > 0))
+    lib = _lib.lib()
+    for x, kk in zip(v[:200], k[:200]):
+        assert lib.ctrb_cost_to_key(float(x)) == int(kk)
+        assert cdist.key_to_cost(int(kk)) == x and lib.ctrb_key_to_cost(int(kk)) == x
+    assert cdist.cost_to_key(float("nan")) == cdist.INT64_MAX and cdist.cost_to_key(float("inf")) == cdist.INT64_MAX
+    assert cdist.key_to_cost(cdist.INT64_MAX) == float("inf")
+    assert cdist.gather_best(2.5, 7) == (2.5, 7)            # no process group: identity

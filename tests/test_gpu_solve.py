@@ -185,6 +185,31 @@ def test_batched_search_invariants(solver, tmp_path):
     assert len(lines) == len(s.tree.nodes) and lines[0].startswith("0 | 0, 0, 0 | 0, 0, 0 | None | ")
     s.save_best_solution(tmp_path)
     assert (tmp_path / "solution_path.txt").read_text().startswith("Q: ")
+    # the reference's writer -> the reference's reader: integer tube lengths and delta_x give integer insertions
+    # ("3, 6, 9", kinematic.py:74-78), which TreeFromFile parses back (tree_from_file.py:28) and re-solves
+    import os
+    from ctrdapp_b200.solve.tree_from_file import TreeFromFile
+    assert all("." not in ln.split(" | ")[1] for ln in lines)
+    run_dir = tmp_path / "output" / "reload"
+    run_dir.mkdir(parents=True)
+    s.save_tree(run_dir)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        t = TreeFromFile(m, _factory("square_obstacle_avg_plus_weighted_goal"), CollisionChecker(env),
+                         dict(conf, run_identifier="reload", solver_type="tree_from_file"))
+    finally:
+        os.chdir(cwd)
+    assert len(t.tree.nodes) == len(s.tree.nodes)
+    key = lambda n: (tuple(float(v) for v in n.insertion), tuple(np.round(n.rotation, 12)))  # noqa: E731
+    assert sorted(key(n) for n in t.tree.nodes) == sorted(key(n) for n in s.tree.nodes)
+    by_key = {key(n): n for n in s.tree.nodes}
+    for n in t.tree.nodes[1::9]:
+        src = by_key[key(n)]
+        assert [len(c) for c in n.g_curves] == [len(c) for c in src.g_curves]
+        assert np.max(np.abs(np.concatenate(n.g_curves) - np.concatenate(src.g_curves))) < 1e-9
+        if n.parent is not None:   # same parent configuration
+            assert key(t.tree.nodes[n.parent]) == key(s.tree.nodes[src.parent])
 
 
 def test_c4_follow_the_leader_goal_mesh():

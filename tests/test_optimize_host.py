@@ -24,7 +24,7 @@ def bumpy(x):
 
 
 @pytest.mark.parametrize("f,dim,seed", [(rosen, 2, 0), (rosen, 5, 1), (bumpy, 5, 2), (bumpy, 8, 3)])
-@pytest.mark.parametrize("speculate", [True, False])
+@pytest.mark.parametrize("speculate", [True, False, 1, 2])
 def test_same_iterates_as_scipy(f, dim, seed, speculate):
     rng = np.random.default_rng(seed)
     simplex = rng.uniform(-1.5, 1.5, (dim + 1, dim))
@@ -34,7 +34,48 @@ def test_same_iterates_as_scipy(f, dim, seed, speculate):
     assert got.nit == ref.nit and got.nfev == ref.nfev and got.success == ref.success
     np.testing.assert_array_equal(got.x, ref.x)
     assert got.fun == ref.fun
-    assert (got.nfev_speculative > 0) == speculate
+    assert (got.nfev_speculative > 0) == bool(speculate)
+    # the speculative points the algorithm asked for + the discarded ones account for every extra evaluation
+    calls = []
+    got2 = nelder_mead(lambda xs: calls.append(len(xs)) or [f(x) for x in xs], simplex, xatol=1e-6, fatol=1e-6, maxfev=4000,
+                       speculate=speculate)
+    assert sum(calls) == got2.nfev + got2.nfev_speculative
+
+
+def test_neldermead_driver_tags_speculative_evaluations(monkeypatch):
+    """NelderMead.find_min in one process: no speculation by default (one RRT run per evaluation SciPy would make, as in the
+    reference, so `optimize_iterations` bounds the real work); with speculation on, optimize_process lists exactly the sequential
+    algorithm's evaluations and the discarded speculative runs are kept apart."""
+    from ctrdapp_b200.optimize import neldermead as nm
+
+    class FakeSolver:
+        found_solution = True
+
+        def __init__(self, cost):
+            self.cost = cost
+
+        def get_best_cost(self):
+            return self.cost, 0
+
+    monkeypatch.setattr(nm, "create_model", lambda conf, x, ctx=None: np.asarray(x))
+    monkeypatch.setattr(nm, "create_solver", lambda model, hf, cc, conf: FakeSolver(rosen(model)))
+    simplex = np.random.default_rng(4).uniform(-1.5, 1.5, (4, 3)).tolist()
+    conf = {"tube_number": 1, "optimizer_precision": 1e-3, "tube_radius": {"outer": [0.9]}, "strain_bases": ["linear"],
+            "tube_lengths": [50], "q_dof": [3], "initial_simplex": simplex, "optimize_iterations": 120}
+    ref = nelder_mead(lambda xs: [rosen(x) for x in xs], simplex, xatol=1e-3, fatol=1e-3, maxfev=120, speculate=False)
+    for speculate in (None, 3):
+        c = dict(conf)
+        if speculate is not None:
+            c["speculate"] = speculate
+        opt = nm.NelderMead(None, None, None, c)
+        res = opt.find_min()
+        assert res.num_function_eval == ref.nfev and res.num_iterations == ref.nit
+        assert len(res.optimize_process) == ref.nfev                      # what the sequential algorithm evaluated
+        assert opt.count == ref.nfev + res.num_speculative_eval             # every RRT run is accounted for
+        assert (res.num_speculative_eval == 0) == (speculate is None)
+        assert len(res.speculative_results) == res.num_speculative_eval
+        assert res.owns_best_solver and res.best_rank == 0
+        assert res.best_solver.cost == min(e["cost"] for e in res.optimize_process + res.speculative_results)
 
 
 def test_budget_is_respected():
