@@ -52,8 +52,9 @@ class TreeFromFile(RRT):
         configuration = dict(configuration)
         configuration["heuristic_type"] = "only_goal_distance"  # costs are taken from the file as they are
         heuristic_factory = create_heuristic_factory(configuration, {"only_goal_distance": []})
-        self.delta_x = configuration.get("delta_x")
-        self.tube_lengths = configuration.get("tube_lengths")
+        # the reference reads both from the configuration (tree_from_file.py:20-21); the model holds the same values
+        self.delta_x = configuration.get("delta_x") or model.delta_x
+        self.tube_lengths = configuration.get("tube_lengths") or model.max_tube_length
         super().__init__(model, heuristic_factory, collision_detector, configuration)
 
     def _round(self, k):
