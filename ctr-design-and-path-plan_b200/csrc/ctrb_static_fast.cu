@@ -49,11 +49,14 @@ constexpr int kFastAllowBlock = 1, kFastPinOneStep = 2;  // kernel flags
 #ifndef CTRB_MV_UNROLL
 #define CTRB_MV_UNROLL 16
 #endif
+// Round 2, with the one-step configurations in this kernel (more Jacobian evaluations per configuration, so more of the
+// code is live at once): the same sweep now favours the rolled loops -- rank-one update 3 / 2 / 1: 98.1 / 97.2 / 95.8 ms per
+// 2^20 shallow configurations, Gauss-Jordan 3 / 1: 98.1 / 97.4; matrix-vector products 4 / 8 / complete: 104.9 / 98.1 / 98.1.
 #ifndef CTRB_R1_UNROLL
-#define CTRB_R1_UNROLL 3
+#define CTRB_R1_UNROLL 1
 #endif
 #ifndef CTRB_INV_UNROLL
-#define CTRB_INV_UNROLL 3
+#define CTRB_INV_UNROLL 1
 #endif
 #ifndef CTRB_BLOCK_INVERT
 #define CTRB_BLOCK_INVERT 1

@@ -10,7 +10,7 @@ for l in sys.stdin:
     except Exception: print(l.strip()[:300]); continue
     print(d['case'], d['ms'], d['Mcfg_per_s'], 'fb', d['fallbacks'], 'conv', d['converged'], 'nfev', d['nfev']['mean'])
 "
-  python tools/perf_static3.py 262144 1:33 2>&1 | grep -v "one_step_option\": 1" | python -c "
+  python tools/perf_static3.py 131072 1:33 2>&1 | grep -v "one_step_option\": 1" | python -c "
 import sys, json
 for l in sys.stdin:
     try: d=json.loads(l)
