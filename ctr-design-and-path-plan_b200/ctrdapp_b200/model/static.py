@@ -15,6 +15,24 @@ from .. import _lib as L
 from .kinematic import Kinematic, _f64, _i32
 
 
+def check_degree(degree):
+    """`degree` of the section polynomials (static_bases.py:61-74).  The reference's _simple_basis writes the three
+    curvature components at the hard-coded column offsets 0, 3 and 6 of a 3 (degree + 1)-column matrix, so only degree 2
+    gives a well-formed basis (probe: tools/probe_static_degree.py, profiles/r2_probe_static_degree.txt):
+      degree 0, 1  IndexError in the reference (columns 3.. / 6.. do not exist)      -> the same exception here
+      degree >= 3  the reference runs, on a basis in which two curvature components share a coefficient (columns 3 and 6)
+                   and the trailing coefficients multiply nothing (zero Jacobian columns): its output is an artefact of
+                   MINPACK's singular-matrix handling, and three tubes need 39 unknowns         -> NotImplementedError"""
+    degree = int(degree)
+    if degree < 2:
+        raise IndexError(f"index {3 if degree < 1 else 6} is out of bounds for axis 1 with size {3 * (degree + 1)} "
+                         f"(static degree {degree}: the reference fails the same way, static_bases.py:68)")
+    if degree > 2:
+        raise NotImplementedError(f"static degree {degree}: the reference's basis is malformed for degree > 2 (static_bases.py:68 "
+                                  f"overlaps the curvature components at columns 3 and 6 and leaves {2 * (degree - 2)} coefficients "
+                                  f"unused); only degree 2 is built")
+
+
 class Static(Kinematic):
     def __init__(self, tube_num, q, q_dof, max_tube_length, delta_x, strain_base, radius, degree=2,
                  basis_type="last_strain_base", ctx=None):
@@ -23,6 +41,7 @@ class Static(Kinematic):
         if basis_type != "last_strain_base":
             raise NameError(f'{basis_type} is not a static basis this library builds; the reference\'s "simple" and '
                             f'"all_strain_bases" do not run either (SURVEY App. B#2)')
+        check_degree(degree)
         self._static_desc = (radius, degree)
         super().__init__(tube_num, q, q_dof, max_tube_length, delta_x, strain_base, ctx=ctx)
 

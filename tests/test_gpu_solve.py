@@ -251,7 +251,9 @@ def test_nelder_mead_design_optimisation(tmp_path):
     opt = create_optimizer(create_heuristic_factory(conf, HDICT), cc, [0.02, 0.001, 0.05, 0.0001, 0.002], conf)
     res = opt.find_min()
     assert res.num_function_eval >= 6 and res.best_solver is not None
-    assert len(res.optimize_process) == res.num_function_eval + res.num_speculative_eval
+    # one process: no speculation, the run is SciPy's algorithm evaluation for evaluation (the reference's)
+    assert len(res.optimize_process) == res.num_function_eval and res.num_speculative_eval == 0
+    assert res.owns_best_solver and res.best_rank == 0
     costs = [e["cost"] for e in res.optimize_process]
     assert min(costs) == pytest.approx(res.best_solver.get_best_cost()[0])
     assert len(res.best_q) == 5

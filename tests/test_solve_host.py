@@ -114,3 +114,21 @@ def test_stl_loader_binary_and_ascii():
         np.testing.assert_allclose(v.min(0), lo, atol=0.06)
         np.testing.assert_allclose(v.max(0), hi, atol=0.06)
         np.testing.assert_array_equal(orc.read_stl(FIXTURES / name).reshape(-1, 3), v.astype(np.float64))
+
+
+def test_static_degree_matches_the_reference_probe():
+    """static `degree` (static_bases.py:61-74): degree 0 / 1 fail in the reference with an IndexError (its hard-coded
+    column offsets 3 and 6), degree > 2 runs on a malformed basis (profiles/r2_probe_static_degree.txt): the mirror raises
+    the same exception type for the former and NotImplementedError for the latter, before touching the device."""
+    import pathlib
+    from ctrdapp_b200.model.static import Static, check_degree
+    check_degree(2)
+    for d in (0, 1):
+        with pytest.raises(IndexError, match="out of bounds for axis 1"):
+            check_degree(d)
+        with pytest.raises(IndexError):
+            Static(2, [np.zeros(2), np.zeros(3)], [2, 3], [120, 120], 1, ["linear", "linear"], {"outer": [0.9, 0.6], "inner": [0.7, 0.4]}, d)
+    with pytest.raises(NotImplementedError, match="malformed"):
+        check_degree(3)
+    probe = (pathlib.Path(__file__).resolve().parent.parent / "profiles" / "r2_probe_static_degree.txt").read_text()
+    assert probe.count("FAILS: IndexError") == 2 and "all-zero columns: [10, 11]" in probe
