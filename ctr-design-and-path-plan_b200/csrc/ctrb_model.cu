@@ -315,15 +315,23 @@ __global__ void node_count_scan3(long long n_items, long long* __restrict__ offs
 // One warp per configuration.  eta_n is a T-step recurrence (all lanes redundantly, it is
 // ~60 FLOP per tube); the per-node FTL twist is lane-parallel over the parent's nodes:
 //   ftl_k = Ad(P_k^-1) eta_n - V_n xi(i dx) = [R^T w - V w_i ; R^T (v - p x w) - V e_x]
-constexpr int kEWarps = 8;
+#ifndef CTRB_FTL_WARPS
+#define CTRB_FTL_WARPS 8
+#endif
+#ifndef CTRB_FTL_UNROLL2
+#define CTRB_FTL_UNROLL2 0
+#endif
+constexpr int kEWarps = CTRB_FTL_WARPS;
 
+// rows 0..2 of a 4x4 node: three 256-bit loads (sm_100 has them; the node is 32-byte aligned) through the read-only path
+__device__ __forceinline__ void ld_row(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 __device__ __forceinline__ SE3 load_g64(const double* g) {
     SE3 o;
-    const double2* p = reinterpret_cast<const double2*>(g);
-    double2 v0 = __ldg(p + 0), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3), v4 = __ldg(p + 4), v5 = __ldg(p + 5);
-    o.r[0] = v0.x; o.r[1] = v0.y; o.r[2] = v1.x; o.p[0] = v1.y;
-    o.r[3] = v2.x; o.r[4] = v2.y; o.r[5] = v3.x; o.p[1] = v3.y;
-    o.r[6] = v4.x; o.r[7] = v4.y; o.r[8] = v5.x; o.p[2] = v5.y;
+    ld_row(g, o.r[0], o.r[1], o.r[2], o.p[0]);
+    ld_row(g + 4, o.r[3], o.r[4], o.r[5], o.p[1]);
+    ld_row(g + 8, o.r[6], o.r[7], o.r[8], o.p[2]);
     return o;
 }
 
@@ -344,44 +352,81 @@ __global__ void __launch_bounds__(kEWarps * 32)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = mc.T;
     for (long long b = (long long)blockIdx.x * kEWarps + warp; b < B; b += (long long)gridDim.x * kEWarps) {
-        double eta[6] = {0, 0, 0, 0, 0, 0};
-        double vel_sum = 0.0;
-        double sum_mag = 0.0, sum_tmag = 0.0, tip_mag = 0.0, tip_tmag = 0.0;
-        long long n_nodes = 0;
-        for (int n = 0; n < T; ++n) {
-            const int pi = prev_idx[b * T + n];
+        // ---- phase 1, lane n = tube n: its share Ad(P_n[0]) (dtheta_n e_x + v_n xi(mid)) of eta (kinematic.py:168-177).
+        // The T first-node loads are in flight together (they were one exposed DRAM latency per tube when the tubes were
+        // walked one after the other); eta_n = sum_{m <= n} share_m and V_n = sum_{m <= n} v_m follow by a prefix sum over lanes.
+        double sh[6] = {0, 0, 0, 0, 0, 0};
+        double vsum_l = 0.0;
+        long long o0_l = 0;
+        int pi_l = 0, cnt_l = 0;
+        bool bad = false;
+        if (lane < T) {
+            const int n = lane;
+            pi_l = prev_idx[b * T + n];
             // kinematic.py:71: velocity from the rounded indices, unless the caller passes it (solve_eta's own signature)
-            const double v = velocity ? velocity[b * T + n] : (pi - new_idx[b * T + n]) * mc.dx;
-            vel_sum += v;                                          // :163
-            const double mid = pi * mc.dx - v / 2;                 // :165
+            const double v = velocity ? velocity[b * T + n] : (pi_l - new_idx[b * T + n]) * mc.dx;
+            vsum_l = v;                                            // :163
+            const double mid = pi_l * mc.dx - v / 2;               // :165
             double wm[3];
             strain_omega(mc, n, mid, wm);
-            const long long o0 = prev_off[b * T + n], o1 = prev_off[b * T + n + 1];
-            const int cnt = mc.npts[n] - pi;
-            if (o1 - o0 < cnt || cnt < 1) {  // the reference raises IndexError here
-                if (lane == 0) atomicExch(err_flag, 1);
-                break;
-            }
-            SE3 p0 = load_g64(prev_g + o0 * 16);
-            // twist in the tube's base frame: dtheta e_x + v xi(mid)  (:171-172)
-            double tw[3] = {delta_theta[b * T + n] + v * wm[0], v * wm[1], v * wm[2]};
-            double tv[3] = {v, 0.0, 0.0};
-            double Rw[3], Rv[3];
+            o0_l = prev_off[b * T + n];
+            const long long o1 = prev_off[b * T + n + 1];
+            cnt_l = mc.npts[n] - pi_l;
+            bad = o1 - o0_l < cnt_l || cnt_l < 1;                  // the reference raises IndexError here
+            if (!bad) {
+                const SE3 p0 = load_g64(prev_g + o0_l * 16);
+                // twist in the tube's base frame: dtheta e_x + v xi(mid)  (:171-172)
+                const double tw[3] = {delta_theta[b * T + n] + v * wm[0], v * wm[1], v * wm[2]};
+                double Rw[3], Rv[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                Rw[i] = p0.r[i * 3] * tw[0] + p0.r[i * 3 + 1] * tw[1] + p0.r[i * 3 + 2] * tw[2];
-                Rv[i] = p0.r[i * 3] * tv[0] + p0.r[i * 3 + 1] * tv[1] + p0.r[i * 3 + 2] * tv[2];
+                for (int i = 0; i < 3; ++i) {
+                    Rw[i] = p0.r[i * 3] * tw[0] + p0.r[i * 3 + 1] * tw[1] + p0.r[i * 3 + 2] * tw[2];
+                    Rv[i] = p0.r[i * 3] * v;
+                }
+                // Ad(g)[w;v] = [R w ; p x (R w) + R v]
+                sh[0] = Rw[0];
+                sh[1] = Rw[1];
+                sh[2] = Rw[2];
+                sh[3] = p0.p[1] * Rw[2] - p0.p[2] * Rw[1] + Rv[0];
+                sh[4] = p0.p[2] * Rw[0] - p0.p[0] * Rw[2] + Rv[1];
+                sh[5] = p0.p[0] * Rw[1] - p0.p[1] * Rw[0] + Rv[2];
             }
-            // Ad(g)[w;v] = [R w ; p x (R w) + R v]
-            eta[0] += Rw[0];
-            eta[1] += Rw[1];
-            eta[2] += Rw[2];
-            eta[3] += p0.p[1] * Rw[2] - p0.p[2] * Rw[1] + Rv[0];
-            eta[4] += p0.p[2] * Rw[0] - p0.p[0] * Rw[2] + Rv[1];
-            eta[5] += p0.p[0] * Rw[1] - p0.p[1] * Rw[0] + Rv[2];
-            if (lane < 6) eta_out[(b * T + n) * 6 + lane] = eta[lane];
-            for (int k = lane; k < cnt; k += 32) {                 // :178-193
-                SE3 g = load_g64(prev_g + (o0 + k) * 16);
+        }
+        // the first tube with too short a parent curve ends the configuration there (as the sequential walk did)
+        const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+        const int t_ok = badmask ? __ffs(badmask) - 1 : T;
+        if (badmask && lane == 0) atomicExch(err_flag, 1);
+        // inclusive prefix over lanes 0..T-1 in tube order: eta_n accumulates share_0 + ... + share_n exactly as the loop did
+#pragma unroll
+        for (int m = 1; m < CTRB_MAX_TUBES; ++m) {
+            double add[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) add[j] = __shfl_up_sync(0xffffffffu, sh[j], 1);
+            const double va = __shfl_up_sync(0xffffffffu, vsum_l, 1);
+            // after step m lane n holds the sum of shares max(0, n - m) .. n; adding the neighbour's running sum once per step
+            // in this order reproduces ((s0 + s1) + s2) + s3
+            if (lane == m && lane < T) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) sh[j] = add[j] + sh[j];
+                vsum_l = va + vsum_l;
+            }
+        }
+        if (lane < t_ok) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) eta_out[(b * T + lane) * 6 + j] = sh[j];
+        }
+        double sum_mag = 0.0, sum_tmag = 0.0, tip_mag = 0.0, tip_tmag = 0.0;
+        long long n_nodes = 0;
+        // ---- phase 2: the follow-the-leader twists of every parent node, lanes over nodes
+        for (int n = 0; n < t_ok; ++n) {
+            double eta[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) eta[j] = __shfl_sync(0xffffffffu, sh[j], n);
+            const double vel_sum = __shfl_sync(0xffffffffu, vsum_l, n);
+            const long long o0 = __shfl_sync(0xffffffffu, o0_l, n);
+            const int pi = __shfl_sync(0xffffffffu, pi_l, n), cnt = __shfl_sync(0xffffffffu, cnt_l, n);
+            // one parent node per lane and trip (two with CTRB_FTL_UNROLL2: both nodes' loads are in flight before either is used)
+            auto node = [&](const SE3& g, int k) {                 // :178-193
                 double wi[3];
                 strain_omega(mc, n, mc.dx * (pi + k), wi);
                 double u[3] = {eta[3] - (g.p[1] * eta[2] - g.p[2] * eta[1]),
@@ -407,7 +452,18 @@ __global__ void __launch_bounds__(kEWarps * 32)
                     tip_mag = m;
                     tip_tmag = tm;
                 }
+            };
+#if CTRB_FTL_UNROLL2
+            for (int k = lane; k < cnt; k += 64) {
+                const bool two = k + 32 < cnt;
+                const SE3 g = load_g64(prev_g + (o0 + k) * 16);
+                const SE3 g2 = load_g64(prev_g + (o0 + (two ? k + 32 : k)) * 16);
+                node(g, k);
+                if (two) node(g2, k + 32);
             }
+#else
+            for (int k = lane; k < cnt; k += 32) node(load_g64(prev_g + (o0 + k) * 16), k);
+#endif
             n_nodes += cnt;
         }
 #pragma unroll
