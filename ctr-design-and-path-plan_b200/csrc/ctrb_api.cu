@@ -237,8 +237,8 @@ int ctrb_ctx_create(int device, ctrb_ctx** out) {
             CTRB_CUDA(cudaEventCreate(&c->kev[k][i]));
             CTRB_CUDA(cudaEventRecord(c->kev[k][i], c->stream));
         }
-    CTRB_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
-    CTRB_CUDA(cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)));
+    CTRB_CUDA(cudaMalloc(&c->d_counters, 32 * sizeof(unsigned long long)));
+    CTRB_CUDA(cudaMemset(c->d_counters, 0, 32 * sizeof(unsigned long long)));
     cudaDeviceProp prop;
     CTRB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -346,6 +346,16 @@ int ctrb_static_last_fallbacks(ctrb_ctx* c, uint64_t* count) {
     unsigned long long h = 0;
     CTRB_CUDA(cudaMemcpy(&h, c->d_counters + 11, sizeof h, cudaMemcpyDeviceToHost));
     *count = h;
+    return CTRB_OK;
+}
+
+int ctrb_static_last_fallback_reasons(ctrb_ctx* c, uint64_t out[6]) {
+    CTRB_REQUIRE(c && out, "ctrb_static_last_fallback_reasons: bad argument");
+    CTRB_CUDA(cudaSetDevice(c->device));
+    CTRB_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long h[6];
+    CTRB_CUDA(cudaMemcpy(h, c->d_counters + 16, sizeof h, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; ++k) out[k] = h[k];
     return CTRB_OK;
 }
 
@@ -851,6 +861,7 @@ int ctrb_static_solve_g_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, con
     CTRB_REQUIRE(!g_out || node_offsets, "g_out needs node_offsets");
     const size_t n = (size_t)B * m->mc.T, nqs = (size_t)B * m->sm.nq;
     CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 11, 0, sizeof(unsigned long long), ctx->stream));
+    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 16, 0, 6 * sizeof(unsigned long long), ctx->stream));
     if (mem == CTRB_MEM_DEVICE) {
         return launch_static_solve(ctx, m->sm, B, idx, theta, initial_guess, x0_per_config, xtol,
                                    (const long long*)node_offsets, g_out, solution_q, nfev, info, 0);
@@ -944,6 +955,7 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
     // synchronisation in CTRB_MEM_DEVICE mode.  Batches above 2^22 configurations run as consecutive launch sequences on
     // the stream so that the scratch stays bounded (C3: 2^22 x 201 nodes x 24 B = 20 GB of the 180).
     CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 11, 0, sizeof(unsigned long long), ctx->stream));
+    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 16, 0, 6 * sizeof(unsigned long long), ctx->stream));
     const int64_t CH = std::min<int64_t>(B, (int64_t)1 << 22);
     void* doff = nullptr;
     int rc = ctx_scratch(ctx, 9, ((size_t)CH * T + 1) * sizeof(long long), &doff);

@@ -95,7 +95,7 @@ struct ctrb_ctx {
     // grow-only device scratch
     void* scratch[32];        // [1..8] Stage buffers, [9..15] per-call scratch, [17..24] second set of Stage buffers
     size_t scratch_bytes[32];
-    unsigned long long* d_counters;  // [16]: [0..7] collision work counters + ticket, [8..10] static-solve tickets + fallback count, [11] fallbacks summed over the chunks of one call
+    unsigned long long* d_counters;  // [32]: [16..21] why the fast kernel handed configurations over (ctrb_static_last_fallback_reasons); [0..7] collision work counters + ticket, [8..10] static-solve tickets + fallback count, [11] fallbacks summed over the chunks of one call
     int sm_count;
     int opt[16];              // ctrb_option values (ctrb_ctx_set_option); defaults set by ctrb_ctx_create
 };

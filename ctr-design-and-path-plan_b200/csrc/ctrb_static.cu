@@ -201,10 +201,14 @@ __device__ __noinline__ double dogleg_w(int n, const double* r, double diag_l, c
 
 // The plane rotation (c, s) = (a, b) / hypot(a, b); identity when both vanish.  MINPACK stores its rotations as
 // one number (tau) and rebuilds cos / sin with a square root wherever they are applied; here they are kept as pairs.
+// b == 0 is MINPACK's "if (w[j] != 0)" guard: no rotation.  (a / |a|, 0) with a < 0 would be a rotation by pi, which r1updt's
+// "s != 0" shortcut skips on R while r1mpyq applies it to Q: the factors then disagree.  It cannot happen by rounding, but it
+// does for the decoupled unit rows of pinned unknowns (pin_mask), whose w_j is exactly zero and whose R_jj is -1.
 __device__ __forceinline__ void rot_of(double a, double b, double* c_, double* s_) {
     const double h2 = fma(a, a, b * b);
-    const double ri = h2 > 0.0 ? rsqrt(h2) : 0.0;
-    *c_ = h2 > 0.0 ? a * ri : 1.0;
+    const bool rot = b != 0.0 && h2 > 0.0;
+    const double ri = rot ? rsqrt(h2) : 0.0;
+    *c_ = rot ? a * ri : 1.0;
     *s_ = b * ri;
 }
 
@@ -307,7 +311,7 @@ __device__ __noinline__ void st_r1mpyq_row(int n, double* a, int lda, const doub
 // computed redundantly and identically by all lanes; vectors are one element per lane.
 // returns info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress)
 __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
-                                     double factor, bool reduced, int* nfev_out) {
+                                     double factor, bool reduced, unsigned pin, int* nfev_out) {
     CTRB_USE_SM;
     // with the default initial guess the decoupled linear block (3,3) is carried implicitly (block5_norm2, tabulated per design)
     const int n = reduced ? sm.nq - sm.ndof[5] : sm.nq;
@@ -325,7 +329,8 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
     const double epsmch = DBL_EPSILON, p1 = 0.1, p5 = 0.5, p001 = 1e-3, p0001 = 1e-4;
     double* fjac = M.fjac;
     int info = 0, nfev;
-    const RowMeta rm = row_meta(sm, act ? lane : 0);
+    RowMeta rm = row_meta(sm, act ? lane : 0);
+    if (pin) pin_row_meta(sm, pin, lane, rm);  // one-step sections on the reduced system, as in the fast kernel (pin_mask)
     double pa, pb;  // section shares of this lane's residual component at the accepted x (for the sparse fdjac)
     {
         const double f0 = warp_residual(sm, M.cfg, M.ybuf0, M.x, rm, act, lane, nnodes, &pa, &pb);
@@ -341,7 +346,7 @@ __device__ __noinline__ int st_hybrd(const StModel& sm_, HybrdMem& M, const Slot
     for (;;) {  // outer loop: fresh forward-difference Jacobian
         bool jeval = true;
         // fdjac1 (dense band) through the block structure of the residual: 4 (8) node evaluations per column
-        warp_fdjac(sm, M.cfg, st, rm, M.x, fjac, M.ybuf32(), act ? M.fvec[lane] : 0.0, pa, pb, n, lane);
+        warp_fdjac(sm, M.cfg, st, rm, M.x, fjac, M.ybuf32(), act ? M.fvec[lane] : 0.0, pa, pb, n, lane, pin);
         nfev += sm.nq;  // MINPACK's count: one evaluation per unknown
         __syncwarp();
         // qrfac: Householder QR without pivoting; lane k owns column k.  acnorm -> wa2, rdiag -> wa1
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(kSWarps * 32, CTRB_QR_BLOCKS)
                         double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
                         int32_t* __restrict__ info_out, unsigned long long* __restrict__ ticket,
                         const long long* __restrict__ list, const unsigned long long* __restrict__ list_count,
-                        unsigned long long* __restrict__ list_total) {
+                        unsigned long long* __restrict__ list_total, int pin_one_step) {
     if (list && list_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(list_total, *list_count);
     load_model(sm_);
     const StModel& sm = g_sm;
@@ -552,7 +557,10 @@ __global__ void __launch_bounds__(kSWarps * 32, CTRB_QR_BLOCKS)
         if (lane < n) M.x[lane] = x0 ? x0[(x0_per_config ? b * n : 0) + lane] : sm.x0[lane];
         __syncwarp();
         int nfev = 0;
-        const int info = st_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, &nfev);
+        // one-step sections under the product's rule (CTRB_OPT_STATIC_ONE_STEP = 0) keep it here too: a configuration the
+        // fast kernel hands over after a singular Jacobian re-evaluation is solved on the same reduced system
+        const unsigned pin = pin_one_step ? pin_mask(sm, M.cfg) : 0u;
+        const int info = st_hybrd(sm, M, st, lane, xtol, 200 * (n + 1), 100.0, reduced, pin, &nfev);
         __syncwarp();
         if (sol_out && lane < n) sol_out[b * n + lane] = M.x[lane];
         if (lane == 0) {
@@ -906,7 +914,8 @@ int launch_static_solve(ctrb_ctx* ctx, const StModel& sm, long long B, const int
         static_solve_kernel<<<grid, kSWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config,
                                                                       xtol > 0 ? xtol : 1.49012e-8, offsets, g_out, sol_out,
                                                                       nfev_out, info_out, ctx->d_counters + 8, fb_list,
-                                                                      ctx->d_counters + 10, ctx->d_counters + 11);
+                                                                      ctx->d_counters + 10, ctx->d_counters + 11,
+                                                                      ctx->opt[CTRB_OPT_STATIC_ONE_STEP] == 0);
         ctx->launches++;
         CTRB_CUDA(cudaGetLastError());
     }

@@ -318,8 +318,9 @@ __device__ __noinline__ bool fast_invert(FastMem& M, int n_rt, double acnorm_l, 
     return true;
 }
 
-// returns MINPACK's info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress), or -1 when the
-// configuration has to go through the QR kernel
+// returns MINPACK's info (1 = converged, 2 = maxfev, 3 = xtol too small, 4/5 = slow progress), or a negative reason when the
+// configuration has to go through the QR kernel (-1 degenerate section, -2 non-finite residual at the initial guess, -3 / -4
+// singular Jacobian at the first / a later evaluation, -5 non-finite trial point, -6 singular Broyden update)
 template <int N>
 __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const SlotTable& st, int lane, double xtol, int maxfev,
                                        double factor, bool reduced, bool allow_block, unsigned pin, int* nfev_out) {
@@ -339,7 +340,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
     double f_l = warp_residual(sm, M.cfg, M.y, M.x, rm, act, lane, nnodes, &pa, &pb);
     int nfev = 1, info = 0;
     double fnorm = wnorm(f_l);
-    if (!(fnorm < 1.7e308)) return -1;
+    if (!(fnorm < 1.7e308)) return -2;  // non-finite residual at the initial guess
     int iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0;
     double delta = 0.0, xnorm = 0.0, diag_l = 1.0;
 #pragma unroll 1
@@ -350,7 +351,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
         // three tubes from the default initial guess: block-structured inverse; anything it declines (a small pivot)
         // goes through the general Gauss-Jordan, which alone decides what is handed to the QR kernel
         const bool blocked = kBlockInvert && allow_block && reduced && n == 27 && sm.mc.T == 3 && fast_invert_block27(M, acnorm_l, lane);
-        if (!blocked && !fast_invert<N>(M, n, acnorm_l, lane)) return -1;
+        if (!blocked && !fast_invert<N>(M, n, acnorm_l, lane)) return iter == 1 && nfev <= sm.nq + 1 ? -3 : -4;  // singular Jacobian (first / later)
         if (iter == 1) {
             diag_l = acnorm_l == 0.0 ? 1.0 : acnorm_l;
             xnorm = sqrt(warp_sum(act ? (diag_l * x_l) * (diag_l * x_l) : 0.0) + c33);
@@ -404,7 +405,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
             const double fn_l = warp_residual(sm, M.cfg, M.y, M.vb, rm, act, lane, nnodes, &qa, &qb);
             nfev++;
             const double fnorm1 = wnorm(fn_l);
-            if (!(fnorm1 < 1.7e308) || !(pnorm < 1.7e308)) return -1;  // non-finite: let the QR kernel decide
+            if (!(fnorm1 < 1.7e308) || !(pnorm < 1.7e308)) return -5;  // non-finite: let the QR kernel decide
             double actred = -1.0;
             if (fnorm1 < fnorm) actred = 1 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
             const double w3 = act ? f_l + matvec_row<N>(M.J, M.va, n, lane) : 0.0;  // f + J p
@@ -466,7 +467,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
             const double Hu = act ? matvec_row<N>(M.H, M.vb, n, lane) : 0.0;
             const double vH = act ? matvec_col<N>(M.H, M.vc, n, lane) : 0.0;
             const double den = 1.0 + warp_sum(v_l * Hu);
-            if (!(fabs(den) > 1e-8) || !(fabs(den) < 1e100)) return -1;  // J+ is (numerically) singular
+            if (!(fabs(den) > 1e-8) || !(fabs(den) < 1e100)) return -6;  // J+ is (numerically) singular
             __syncwarp();
             if (act) M.vb[lane] = vH;
             __syncwarp();
@@ -502,7 +503,8 @@ __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
                        const double* __restrict__ x0, int x0_per_config, double xtol, const long long* __restrict__ offsets,
                        double* __restrict__ g_out, double* __restrict__ sol_out, int32_t* __restrict__ nfev_out,
                        int32_t* __restrict__ info_out, long long* __restrict__ fb_list,
-                       unsigned long long* __restrict__ fb_count, unsigned long long* __restrict__ ticket, int flags) {
+                       unsigned long long* __restrict__ fb_count, unsigned long long* __restrict__ ticket, int flags,
+                       unsigned long long* __restrict__ fb_reasons) {
     load_model(sm_);
     const StModel& sm = g_sm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -539,7 +541,10 @@ __global__ void __launch_bounds__(kFWarps * 32, CTRB_FAST_BLOCKS)
                                                     (flags & kFastAllowBlock) != 0, pin, &nfev);
         __syncwarp();
         if (info < 0) {
-            if (lane == 0) fb_list[atomicAdd(fb_count, 1ULL)] = b;
+            if (lane == 0) {
+                fb_list[atomicAdd(fb_count, 1ULL)] = b;
+                atomicAdd(fb_reasons + (-info - 1), 1ULL);
+            }
             continue;
         }
         if (sol_out && lane < n) sol_out[b * n + lane] = M.x[lane];
@@ -567,7 +572,7 @@ static int launch_static_fast_n(ctrb_ctx* ctx, const StModel& sm, long long B, c
     const long long blocks_needed = (B + kFWarps - 1) / kFWarps;
     const int grid = (int)std::min<long long>(blocks_needed, (long long)ctx->sm_count * std::max(per_sm, 1));
     static_fast_kernel<N><<<grid, kFWarps * 32, smem, ctx->stream>>>(sm, B, idx, theta, x0, x0_per_config, xtol, offsets, g_out,
-                                                                    sol_out, nfev_out, info_out, fb_list, fb_count, ticket, flags);
+                                                                    sol_out, nfev_out, info_out, fb_list, fb_count, ticket, flags, ctx->d_counters + 16);
     ctx->launches++;
     CTRB_CUDA(cudaGetLastError());
     return CTRB_OK;

@@ -62,6 +62,7 @@ SYMBOLS = {
     "ctrb_ctx_elapsed_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "ctrb_ctx_last_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float)]),
     "ctrb_static_last_fallbacks": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "ctrb_static_last_fallback_reasons": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "ctrb_ctx_work_counters": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "ctrb_ctx_device_status": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "ctrb_model_create": (C.c_int, [_vp, C.POINTER(ModelDesc), C.POINTER(_vp)]),
@@ -237,6 +238,12 @@ class Context:
         f = C.c_int32()
         check(lib().ctrb_ctx_device_status(self._h, C.byref(f)))
         return int(f.value)
+
+    def static_fallback_reasons(self):
+        out = (C.c_uint64 * 6)()
+        check(lib().ctrb_static_last_fallback_reasons(self._h, out))
+        return dict(zip(("degenerate_section", "nonfinite_initial_residual", "singular_first_jacobian", "singular_later_jacobian",
+                         "nonfinite_trial_point", "singular_broyden_update"), (int(v) for v in out)))
 
     def work_counters(self):
         out = (C.c_uint64 * 4)()

@@ -242,6 +242,10 @@ int ctrb_static_initial_guess(const ctrb_model* m, double* x0 /*[nq], host*/);
 /* configurations of the most recent static solve on this ctx that the explicit-inverse kernel handed to the
  * QR kernel (singular Jacobian: one-step / zero-length sections).  Synchronises. */
 int ctrb_static_last_fallbacks(ctrb_ctx* ctx, uint64_t* count);
+/* why: [0] zero-length (or, with CTRB_OPT_STATIC_ONE_STEP = 1, one-step) section, [1] non-finite residual at the
+ * initial guess, [2] / [3] singular Jacobian at the first / a later evaluation, [4] non-finite trial point,
+ * [5] singular Broyden update.  Synchronises. */
+int ctrb_static_last_fallback_reasons(ctrb_ctx* ctx, uint64_t out[6]);
 int ctrb_static_residual_batch(ctrb_ctx* ctx, const ctrb_model* m, int64_t B, const int32_t* idx /*[B][T]*/,
                                const double* theta /*[B][T]*/, const double* q /*[B][nq]*/, double* F /*[B][nq]*/,
                                int mem);

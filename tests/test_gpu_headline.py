@@ -171,6 +171,39 @@ def test_one_step_option_literal_qr_kernel():
     assert np.all(res["info"] >= 1) and np.all(res_default["info"] >= 1)
 
 
+def test_one_step_rule_in_both_solve_kernels():
+    """The reduced-system rule for one-step sections is carried by both solve kernels: the explicit-inverse kernel
+    (default) and MINPACK's QR machinery (ctx option static_solver = 1, which also receives the few configurations whose
+    Jacobian turns out singular at a re-evaluation).  Same rule, two factorizations: against the oracle's hybrd on the
+    reduced system each lands on the same root as often as the oracle does under a 1e-13 perturbation of itself."""
+    bench, orc, ms, cc, s, oenv = _objects()
+    idx, theta = bench.make_inputs(12_000, 1003, 1, 8)
+    short = sp.one_step(idx, np.asarray(bench.NPTS))
+    idx, theta = idx[short], theta[short]
+    n = idx.shape[0]
+    fast = ms.solve_g_batch(idx, theta, want_g=False)
+    reasons = ms.ctx.static_fallback_reasons()
+    assert sum(reasons.values()) == ms.ctx.static_fallbacks() and reasons["degenerate_section"] == 0
+    with ms.ctx.options(static_solver=1):
+        qr = ms.solve_g_batch(idx, theta, want_g=False)
+    o1 = orc.static_batch(s, idx, theta, one_step_rule=1)
+    x0 = orc.static_init_guess(s)
+    o1p = orc.static_batch(s, idx, theta, one_step_rule=1,
+                           x0=x0[None, :] * (1.0 + 1e-13 * np.random.default_rng(3).standard_normal((n, x0.size))))
+    all_ = np.ones(n, bool)
+    ro = sp.rates(sp.buckets(o1p["solution"], o1p["info"], o1["solution"], o1["info"]), all_)
+    for name, res in (("fast", fast), ("qr", qr)):
+        rg = sp.rates(sp.buckets(res["solution"], res["info"], o1["solution"], o1["info"]), all_)
+        print("ONE_STEP_RULE", name, json.dumps(rg), "oracle vs itself", json.dumps(ro))
+        assert 1.0 - rg["A"] - rg["N"] <= 2.0 * (1.0 - ro["A"] - ro["N"]) + 0.005, (name, rg, ro)
+        # the pinned x^2 coefficients keep their initial value exactly
+        pins = [2, 5, 8, 17, 20, 23]
+        e = np.asarray(bench.NPTS)[None, :] - 1 - idx
+        for sec, cols in ((0, pins[:3]), (1, pins[3:])):
+            sel = e[:, sec] == 1
+            assert np.all(res["solution"][sel][:, cols] == x0[cols])
+
+
 def test_position_curve_kernels_agree():
     """ctrb_static_eval_batch integrates node positions with one thread per configuration (static_curves_pos_kernel);
     the warp-per-configuration scan kernel (ctx option static_curves_scan) multiplies the same Magnus steps in another

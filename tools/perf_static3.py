@@ -34,5 +34,5 @@ for case in cases:
                "nfev": {"mean": round(float(nf.mean()), 1), "p50": int(np.median(nf)), "p99": int(np.quantile(nf, 0.99)), "max": int(nf.max()),
                         "mean_one_step": round(float(nf[short].mean()), 1) if short.any() else None,
                         "mean_other": round(float(nf[~short].mean()), 1)},
-               "info_hist": np.bincount(res["info"], minlength=6).tolist()}
+               "info_hist": np.bincount(res["info"], minlength=6).tolist(), "fallback_reasons": m.ctx.static_fallback_reasons()}
         print(json.dumps(out), flush=True)
