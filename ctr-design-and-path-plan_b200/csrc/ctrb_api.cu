@@ -969,7 +969,10 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
         if (rc) return rc;
         rc = launch_static_solve(ctx, m->sm, nb, di + b0 * T, dt + b0 * T, nullptr, 0, 0.0, (const long long*)doff, (double*)dg,
                                  nullptr, dnf ? dnf + b0 : nullptr, dinf ? dinf + b0 : nullptr,
-                                 ctx->opt[CTRB_OPT_STATIC_CURVES_SCAN] ? 2 : 1);
+                                 // node positions: one thread per configuration when there are enough configurations to fill
+                                 // the machine with threads, the warp-per-configuration scan otherwise (a thread walks up to
+                                 // total_nodes Magnus steps serially: 0.5 ms of latency on a 1024-configuration batch)
+                                 (ctx->opt[CTRB_OPT_STATIC_CURVES_SCAN] || nb < 65536) ? 2 : 1);
         if (rc) return rc;
         rc = launch_eval_curves_cost(ctx, env, cd, nb, T, (const double*)dg, (const long long*)doff, m->mc.total_nodes, rad,
                                      dob + b0, dgo + b0, dco ? dco + b0 : nullptr, dcl ? dcl + b0 : nullptr, 1);
