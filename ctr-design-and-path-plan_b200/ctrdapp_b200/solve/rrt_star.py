@@ -13,7 +13,13 @@ one k-NN launch finds the neighbours of every surviving candidate, ONE eta/FTL b
 alternative parent) pairs, the survivors are inserted, and ONE more batch evaluates all (new node, neighbour) rewiring
 offers, which are then applied in candidate order (cycle check and cost comparison at that moment, so a neighbour that an
 earlier candidate of the round has already re-parented is judged by its new cost).  New nodes of the same round are not
-each other's neighbours.  `batch_size` = 1 is the reference's sequence operation for operation.
+each other's neighbours.  `batch_size` = 1 follows the reference's sequence of operations, with two deliberate deviations
+(so trees are not asserted node for node against the reference's under a seeded generator):
+  * the reference sets `single_tube_control = False` only AFTER `super().__init__` has already run the search
+    (rrt_star.py:9-11), so the configured value is in effect during its search; here it is off during the search, which is
+    what its comment ("impossible to maintain with the rewire operation") asks for;
+  * the reference's choose-parent loop reuses the previous neighbour's FTL array for the original neighbour when that
+    neighbour is not first in the list (rrt_star.py:43-61); here the original solve's FTL is always used.
 """
 import numpy as np
 
@@ -24,7 +30,7 @@ from .step import delta_rotation_batch
 class RRTStar(RRT):
     def __init__(self, model, heuristic_factory, collision_detector, configuration):
         configuration = dict(configuration)
-        configuration["single_tube_control"] = False  # impossible to maintain with the rewire operation (rrt_star.py:11)
+        configuration["single_tube_control"] = False  # impossible to maintain with the rewire operation (rrt_star.py:11; see above)
         super().__init__(model, heuristic_factory, collision_detector, configuration)
         self.single_tube_control = False
 

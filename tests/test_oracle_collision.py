@@ -224,3 +224,45 @@ def test_reference_cylinder_fixture_loads():
     # inside the z-aligned one
     obs, _ = env.check_collision([[se3([0.2, 0.3, 3.0]), se3([1.2, 0.3, 3.0])]], [0.5])
     assert obs == -1.0
+
+
+@pytest.mark.parametrize("env_name", ["env_c3_colon_straight.json", "env_colon_straight_new.json", "env_colon_angled.json"])
+def test_c_and_numpy_agree_on_the_colon_meshes(env_name):
+    """The two independent implementations (the C case analysis and the NumPy nested convex search) on the REAL meshes:
+    tube cylinders of random C3 configurations against the triangles of the posed colon files -- the triangles nearest to
+    each cylinder (where the minimum is decided, contacts included) and random far ones.  With python-fcl unobtainable this
+    agreement is what arbitrates the restated cylinder-triangle distance."""
+    import json
+    from conftest import FIXTURES
+    spec = json.loads((FIXTURES / env_name).read_text())
+    mesh = next(o for o in spec["obstacles"] if o.get("mesh"))
+    tris = orc.read_stl(FIXTURES / mesh["filename"]).astype(np.float64) + np.asarray(mesh["transform"], np.float64)
+    cent = tris.mean(1)
+    from util import orc_model
+    om = orc_model("c3_three_tube")
+    rng = np.random.default_rng(2025)
+    N = np.array([34, 67, 100])
+    rad = [1.2, 0.9, 0.6]
+    cs, as_, hs, rs, t0, t1, t2 = [], [], [], [], [], [], []
+    for _ in range(40):
+        e = rng.integers(2, 20, 3)
+        g = orc.solve_g(om, (N - 1 - e).tolist(), rng.uniform(0, 2 * np.pi, 3).tolist(), full=False)
+        for n, curve in enumerate(g):
+            p = curve[:, 0:3, 3]
+            k = int(rng.integers(0, len(p) - 1))
+            f, t = p[k], p[k + 1]
+            c, vec = (f + t) / 2, t - f
+            h = np.linalg.norm(vec) / 2
+            near = np.argsort(np.linalg.norm(cent - c, axis=1))[:6]
+            far = rng.integers(0, len(tris), 2)
+            for j in list(near) + list(far):
+                cs.append(c); as_.append(vec / (2 * h)); hs.append(h); rs.append(rad[n])
+                t0.append(tris[j, 0]); t1.append(tris[j, 1]); t2.append(tris[j, 2])
+    cs, as_, hs, rs, t0, t1, t2 = (np.asarray(v) for v in (cs, as_, hs, rs, t0, t1, t2))
+    want = npc.cylinder_triangle(cs, as_, hs, rs, t0, t1, t2)
+    got = np.array([orc.cylinder_triangle(cs[i], as_[i], hs[i], rs[i], t0[i], t1[i], t2[i]) for i in range(len(cs))])
+    pos = got > 0
+    assert len(cs) == 960 and pos.sum() > 200
+    assert np.max(np.abs(got[pos] - want[pos])) < 1e-7          # the search's own accuracy
+    assert np.all(want[~pos] < 1e-6)                             # contacts are contacts for both
+    assert np.all(got <= want + 1e-12)                           # a search can only over-estimate a minimum
