@@ -14,6 +14,15 @@ namespace ctrb {
 namespace {  // internal linkage: two translation units include this header
 
 constexpr int kMaxNq = kStaticMaxNq;
+// unroll factors of two loops, for the compile-time sweeps (tools/build_variant.sh)
+#ifndef CTRB_FDJ_NORM_UNROLL
+#define CTRB_FDJ_NORM_UNROLL 2
+#endif
+constexpr int kFdjNormUnroll = CTRB_FDJ_NORM_UNROLL;  // column-norm loop of warp_fdjac
+#ifndef CTRB_NODE_OUT_UNROLL
+#define CTRB_NODE_OUT_UNROLL 3
+#endif
+constexpr int kNodeOutUnroll = CTRB_NODE_OUT_UNROLL;  // node_sec12's loop over the three powers of x
 
 // The model constants as every device function below reads them: a block-wide shared-memory copy that each kernel
 // fills first (load_model).  Through the kernel parameter (a generic pointer once it crosses an out-of-line call)
@@ -68,12 +77,22 @@ __device__ __noinline__ SinCos sincos_ni(double a) {
 struct SinCos2 {
     double s0, c0, s1, c1;
 };
+#ifndef CTRB_SINCOS_PAIR
+#define CTRB_SINCOS_PAIR 1
+#endif
+#if CTRB_SINCOS_PAIR
 __device__ __noinline__ SinCos2 sincos2_ni(double a, double b) {
     SinCos2 r;
     sincos(a, &r.s0, &r.c0);
     sincos(b, &r.s1, &r.c1);
     return r;
 }
+#else
+__device__ __forceinline__ SinCos2 sincos2_ni(double a, double b) {  // two calls of the one out-of-line copy: half the code
+    const SinCos x = sincos_ni(a), y = sincos_ni(b);
+    return SinCos2{x.s, x.c, y.s, y.c};
+}
+#endif
 
 // one non-zero per column of a strain base (strain_bases.py:7-224): its row (0..2) and its value at x
 __host__ __device__ __forceinline__ void strain_base_col(int kind, int dof, int k, double x, int* row, double* val) {
@@ -259,7 +278,7 @@ __device__ __noinline__ void node_sec12(const StModel& sm_, const StCfg& c, QV q
     const double P[3] = {1.0, X, X * X};
     const double S[3] = {X, 0.5 * X * X, X * X * X * (1.0 / 3.0)};            // sg (row 0) = int of the basis
     const double Se[3] = {Xe, 0.5 * Xe * Xe, Xe * Xe * Xe * (1.0 / 3.0)};     // sg31 at the end of section 1
-#pragma unroll
+#pragma unroll(kNodeOutUnroll)
     for (int k = 0; k < 3; ++k) {
         y[k] = P[k] * wsum.x;
         y[3 + k] = P[k] * wsum.y;
@@ -620,7 +639,7 @@ __device__ __noinline__ double warp_fdjac(const StModel& sm_, const StCfg& cfg, 
     double s2 = 0.0;
     if (act) {
         const double* m = J + lane * kJLD;
-#pragma unroll 2
+#pragma unroll(kFdjNormUnroll)
         for (int i = 0; i < n; ++i) s2 = fma(m[i], m[i], s2);
     }
     return sqrt(s2);

@@ -61,6 +61,14 @@ constexpr int kFastAllowBlock = 1, kFastPinOneStep = 2;  // kernel flags
 #ifndef CTRB_BLOCK_INVERT
 #define CTRB_BLOCK_INVERT 1
 #endif
+#ifndef CTRB_B27_UNROLL
+#define CTRB_B27_UNROLL 1   // 3 / 2 / 1: 95.4 / 94.0 / 92.1 ms per 2^20 shallow configurations
+#endif
+#ifndef CTRB_COPY_UNROLL
+#define CTRB_COPY_UNROLL 4
+#endif
+constexpr int kCopyUnroll = CTRB_COPY_UNROLL;
+constexpr int kB27Unroll = CTRB_B27_UNROLL;  // the three j-loops of fast_invert_block27
 constexpr bool kBlockInvert = CTRB_BLOCK_INVERT != 0;
 constexpr int kMvUnroll = CTRB_MV_UNROLL, kR1Unroll = CTRB_R1_UNROLL, kInvUnroll = CTRB_INV_UNROLL;
 
@@ -133,6 +141,7 @@ __device__ __noinline__ bool fast_invert_block27(FastMem& M, double acnorm_l, in
     constexpr int n = 27, nb = 12, c2 = 12;  // c2: first row / column of the middle block
     double* Tm = M.H;
     const double* Jm = M.J;
+#pragma unroll(kCopyUnroll)
     for (int e = lane; e < kLD * n; e += 32) Tm[e] = Jm[e];
     __syncwarp();
     const int half = lane >> 4, li = lane & 15;
@@ -160,7 +169,7 @@ __device__ __noinline__ bool fast_invert_block27(FastMem& M, double acnorm_l, in
         if (act && lane != r) {
             const double* pr = Tm + rrow + cb * kLD;
             double* tr = Tm + row + cb * kLD;
-#pragma unroll 3
+#pragma unroll(kB27Unroll)
             for (int j = 0; j < nb; ++j) tr[j * kLD] = fma(-m, pr[j * kLD], tr[j * kLD]);
         }
         __syncwarp();
@@ -193,7 +202,7 @@ __device__ __noinline__ bool fast_invert_block27(FastMem& M, double acnorm_l, in
         const double* pc = Tm + cb + row * kLD;           // column of P / Q
         const double* a12 = Jm + cb + c2 * kLD;           // A12 / A32: rows cb.., columns 12..14
         const double* a21 = Jm + c2 + cb * kLD;           // A21 / A23: rows 12..14, columns cb..
-#pragma unroll 3
+#pragma unroll(kB27Unroll)
         for (int j = 0; j < nb; ++j) {
             const double p = pr[j * kLD], q = pc[j];
             u0 = fma(p, a12[j], u0);
@@ -251,7 +260,7 @@ __device__ __noinline__ bool fast_invert_block27(FastMem& M, double acnorm_l, in
         const double t2 = fma(w0, G[0][2], fma(w1, G[1][2], w2 * G[2][2]));
         double* hr = Tm + lane;
         const bool top = lane < nb, bot = lane >= 15;
-#pragma unroll 3
+#pragma unroll(kB27Unroll)
         for (int j = 0; j < n; ++j) {
             const bool diag = (top && j < nb) || (bot && j >= 15);
             const double d = diag ? hr[j * kLD] : 0.0;
