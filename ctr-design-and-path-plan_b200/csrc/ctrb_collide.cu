@@ -523,7 +523,7 @@ constexpr int kGStack = 24;    // traversal stack entries per lane, in SHARED me
                                // chain_eval_kernel): with 32 busy lanes per warp a local-memory stack thrashed the ~40 KB
                                // of L1 that the shared-memory carve-out leaves (ncu: L1 hit rate 50 %, long-scoreboard 8.4)
 #ifndef CTRB_GROUP_MIN
-#define CTRB_GROUP_MIN 8
+#define CTRB_GROUP_MIN 6
 #endif
 // No BVH levels are staged in shared memory here: the staged-or-global branch in load_node diverges between lanes that
 // are at different depths, and the staging takes L1 capacity away from the nodes below (measured: 45.6 -> 63 M configs/s
