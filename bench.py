@@ -40,7 +40,7 @@ ENV_FILE = ROOT / "tests" / "fixtures" / "env_c3_colon_straight.json"
 ENV_NEW_FILE = ROOT / "tests" / "fixtures" / "env_colon_straight_new.json"
 RIN = [1.0, 0.7, 0.4]
 WORKLOADS = {  # name -> (model, exposure lo, hi, default configs per step per GPU); SURVEY 8d "shallow" / "uniform"
-    "c3_static_colon_straight_shallow": ("static", 1, 8, 1 << 20),
+    "c3_static_colon_straight_shallow": ("static", 1, 8, 10_000_000),
     "c3_static_colon_straight_uniform": ("static", 1, 33, 1 << 18),
     "c3_kinematic_colon_straight_shallow": ("kinematic", 1, 8, 10_000_000),
     "c3_kinematic_colon_straight_uniform": ("kinematic", 1, 33, 10_000_000),
@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="configs per step of the CPU arm (0 = workload default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / kernels report")
+    ap.add_argument("--timed-only", action="store_true", help="profiling runs: warm-up + timed steps only (no anatomy / e2e / extras)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -302,6 +303,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = world * B / (ms_per_step * 1e-3)
+
+    if args.timed_only:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_per_step, "timed_only": True}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- step anatomy: the library's CUDA events around each hot kernel, on its stream (three more steps, each
     # read back before the next; the timed region above never waits for the device)
@@ -541,10 +549,11 @@ def run_extra(args, ctx, dev, ms, mk, cc, eval_any, dev_outs, B, peak, lib, C, L
     for tag, l2, h2, Bx in (("shallow", 1, 8, 1 << 18), ("uniform", 1, 33, 1 << 17)):
         extra[f"c3_static_colon_straight_new_{tag}"] = timed_eval(ms, cc_new, Bx, l2, h2)[0]
         extra[f"c3_kinematic_colon_straight_new_{tag}"] = timed_eval(mk, cc_new, 2_000_000, l2, h2)[0]
-    # BASELINE configs[2] is quoted on 10^7 configurations: one static step of that size (three launch sequences of at
-    # most 2^22 configurations inside the library)
-    r, _, _ = timed_eval(ms, cc, 10_000_000, 1, 8, reps=1)
-    extra["c3_static_colon_straight_shallow_1e7_one_step"] = r
+    # the headline at smaller steps (round 1 and the first half of round 2 stepped 2^20 configurations)
+    if args.workload != "c3_static_colon_straight_shallow" or B != 1 << 20:
+        extra["c3_static_colon_straight_shallow_2^20"] = timed_eval(ms, cc, 1 << 20, 1, 8)[0]
+    if args.workload != "c3_static_colon_straight_shallow" or B != 1 << 22:
+        extra["c3_static_colon_straight_shallow_2^22"] = timed_eval(ms, cc, 1 << 22, 1, 8)[0]
     # BASELINE configs[0] (C1): configuration/config.yaml as a STATIC model, 1024 random configurations against the
     # translated box of SURVEY 8d's C1b variant (against in_simple.STL itself every configuration collides at the base)
     q1 = [np.array([0.02, 0.001]), np.array([0.05, 0.0001, 0.002])]

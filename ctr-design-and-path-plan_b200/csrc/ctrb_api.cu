@@ -952,11 +952,13 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
     // The ragged offsets and the curves live on the device only.  The collision kernel reads node positions, so the curves
     // kernel writes positions (24 B per node, not 128).  Their scratch is sized for the longest possible curves
     // (every tube fully exposed), not from the batch's own node count: reading that count back would be a hidden
-    // synchronisation in CTRB_MEM_DEVICE mode.  Batches above 2^22 configurations run as consecutive launch sequences on
-    // the stream so that the scratch stays bounded (C3: 2^22 x 201 nodes x 24 B = 20 GB of the 180).
+    // synchronisation in CTRB_MEM_DEVICE mode.  The scratch is bounded at 64 GiB of the 180: larger batches run as
+    // consecutive launch sequences on the stream (C3: 201 nodes x 24 B per configuration -> up to 14.2 M configurations
+    // per sequence, so BASELINE's 10^7 is one).
     CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 11, 0, sizeof(unsigned long long), ctx->stream));
     CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 16, 0, 6 * sizeof(unsigned long long), ctx->stream));
-    const int64_t CH = std::min<int64_t>(B, (int64_t)1 << 22);
+    const int64_t per_cfg = (int64_t)m->mc.total_nodes * 3 * (int64_t)sizeof(double);
+    const int64_t CH = std::min<int64_t>(B, std::max<int64_t>(((int64_t)64 << 30) / per_cfg, 1 << 16));
     void* doff = nullptr;
     int rc = ctx_scratch(ctx, 9, ((size_t)CH * T + 1) * sizeof(long long), &doff);
     if (rc) return rc;

@@ -645,7 +645,7 @@ __device__ __forceinline__ SE3 chain_section_pos(const StModel& sm_, const doubl
             omega_poly(qs, (si + cg1 - 1) * dx, wA);
             omega_poly(qs, (si + cg2 - 1) * dx, wB);
         }
-        g = se3_mul(g, magnus_step(wA, wB, dx));
+        g = se3_mul(g, magnus_step_inl(wA, wB, dx));
         out[3 * k + 0] = g.p[0]; out[3 * k + 1] = g.p[1]; out[3 * k + 2] = g.p[2];
     }
     return g;

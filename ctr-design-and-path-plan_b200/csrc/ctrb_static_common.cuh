@@ -651,7 +651,7 @@ __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_
 
 // half_step_integral for a tube==section basis (with bias): the Magnus exponential of one step.
 // wA, wB = omega at the two Gauss points; v = e_x at both.
-__device__ __noinline__ SE3 magnus_step(const double wA[3], const double wB[3], double dx) {
+__device__ __forceinline__ SE3 magnus_step_body(const double wA[3], const double wB[3], double dx) {
     const double cf = (sqrt(3.0) * dx * dx) / 12;
     // Gamma = dx/2 (xi1^ + xi2^) + cf [xi2^, xi1^];  [.,.] = (w2 x w1, w2 x v1 - w1 x v2), v1 = v2 = e_x
     V3 a = {wA[0], wA[1], wA[2]}, b = {wB[0], wB[1], wB[2]};
@@ -662,6 +662,10 @@ __device__ __noinline__ SE3 magnus_step(const double wA[3], const double wB[3], 
     double v[3] = {(dx / 2) * 2.0 + cf * cv.x, cf * cv.y, cf * cv.z};
     return se3_exp(w, v, 1.0);
 }
+// out of line for the warp-per-configuration scan (its code size matters there), inline for the thread-per-configuration
+// kernel (a call passes the 12 doubles of the result through the stack: 2.92 -> 2.63 ms per 2^22 configurations)
+__device__ __noinline__ SE3 magnus_step(const double wA[3], const double wB[3], double dx) { return magnus_step_body(wA, wB, dx); }
+__device__ __forceinline__ SE3 magnus_step_inl(const double wA[3], const double wB[3], double dx) { return magnus_step_body(wA, wB, dx); }
 
 // omega of the (tube==section) basis at absolute section coordinate `sidx` (static_bases.py:61-81)
 __device__ __noinline__ void sect_omega(const StModel& sm_, const StCfg& c, const double* qs, int sect, double sidx,
