@@ -46,8 +46,11 @@ constexpr int kFastAllowBlock = 1, kFastPinOneStep = 2;  // kernel flags
 // fallbacks), M cfg/s: everything complete 11.19; update 3 -> 11.79; + Gauss-Jordan 3 -> 12.10; (2, 2) 12.07; (1, 1) 11.84;
 // matrix-vector products by 5 or 8 instead of complete: 12.2 / 12.1 with the two-tube model slower.  The kernel runs on
 // instruction fetch: ncu's stall_no_instruction went from 1.3 to 2.4 per issue with everything unrolled.
+// Round 2 (one-step configurations inside): matrix-vector products 3 / 5 / 6 / 7 / 12 / complete: 90.9 / 91.7 / 91.1 / 93.3 /
+// 93.7 / 91.9 ms per 2^20 shallow configurations, the same order on the uniform and the well-posed workloads.  The curve is not
+// monotone: the kernel's speed follows its code layout as much as its instruction count.
 #ifndef CTRB_MV_UNROLL
-#define CTRB_MV_UNROLL 16
+#define CTRB_MV_UNROLL 3
 #endif
 // Round 2, with the one-step configurations in this kernel (more Jacobian evaluations per configuration, so more of the
 // code is live at once): the same sweep now favours the rolled loops -- rank-one update 3 / 2 / 1: 98.1 / 97.2 / 95.8 ms per
