@@ -35,3 +35,30 @@ def test_product_does_not_import_oracle():
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         txt = p.read_text()
         assert "oracle" not in txt.lower(), p
+
+
+def test_library_reads_nothing_from_the_environment():
+    """include/ctrb200.h promises immutable handles and per-ctx options: no kernel-selection switch may be read from the
+    process environment (round 1 had five getenv calls on the launch paths)."""
+    csrc = ROOT / "ctr-design-and-path-plan_b200" / "csrc"
+    for p in list(csrc.glob("*.cu")) + list(csrc.glob("*.cuh")):
+        assert "getenv" not in p.read_text(), p
+
+
+@pytest.mark.gpu
+def test_ctx_options_round_trip():
+    """ctrb_ctx_set_option / ctrb_ctx_get_option: defaults, round trip, range checks (ValueError), restore on exit."""
+    from ctrdapp_b200 import _lib
+    ctx = _lib.Context(0)
+    defaults = {"static_solver": 0, "static_one_step": 0, "fast_generic_n": 0, "fast_block_invert": 1, "eval_group": 1,
+                "gcurve_blocks": 3, "max_nodes_hint": 0, "static_curves_scan": 0}
+    assert {k: ctx.get_option(k) for k in defaults} == defaults
+    with ctx.options(static_one_step=1, gcurve_blocks=5):
+        assert ctx.get_option("static_one_step") == 1 and ctx.get_option("gcurve_blocks") == 5
+    assert {k: ctx.get_option(k) for k in defaults} == defaults
+    with pytest.raises(ValueError):
+        ctx.set_option("eval_group", 2)
+    with pytest.raises(ValueError):
+        ctx.set_option("gcurve_blocks", 0)
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib().ctrb_ctx_set_option(ctx.handle, 99, 0))

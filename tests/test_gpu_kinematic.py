@@ -174,3 +174,38 @@ def test_bad_arguments_raise():
         m.solve_g_batch([[121, 0]], [[0.0, 0.0]])  # index beyond num_discrete_points - 1
     g, off = m.solve_g_batch(np.zeros((0, 2), np.int32), np.zeros((0, 2)))
     assert g.shape == (0, 4, 4) and off.tolist() == [0]
+
+
+def test_eta_ftl_device_buffers_report_short_parents_through_the_status_flag():
+    """ctrb_eta_ftl_batch with device buffers does not synchronise, so "parent curve shorter than npts - prev_idx" (an
+    IndexError in the reference, CTRB_ERR_INVALID for host buffers) is reported through ctrb_ctx_device_status; the rows the
+    kernel does not reach stay untouched (the Python mirror zero-fills them)."""
+    import ctypes as C
+    import torch
+    from ctrdapp_b200 import _lib as L
+    m = gpu_model("config_yaml")
+    dev = torch.device("cuda", 0)
+    B = 64
+    prev_idx = np.full((B, 2), 100, np.int32)
+    g, off = m.solve_g_batch(prev_idx, np.zeros((B, 2)), full=False)          # 21 nodes per tube
+    new_idx = prev_idx - 1
+    dth = np.full((B, 2), 0.05)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)          # noqa: E731
+    gd, offd, pid, nid, dthd = t(g), t(off), t(prev_idx), t(new_idx), t(dth)
+    eta = torch.zeros((B, 2, 6), dtype=torch.float64, device=dev)
+    mag = torch.zeros((B, 4), dtype=torch.float64, device=dev)
+
+    def call(pi):
+        L.check(L.lib().ctrb_eta_ftl_batch(m.ctx.handle, m.handle, B, L.ptr(pi), L.ptr(nid), None, L.ptr(dthd), L.ptr(gd),
+                                           L.ptr(offd), L.ptr(eta), None, L.ptr(mag), L.MEM_DEVICE))
+        return m.ctx.device_status()
+    assert call(pid) == 0
+    ref = eta.clone()
+    host_eta, _, host_mag = m.eta_ftl_batch(prev_idx, new_idx, dth, g, off, want_ftl=False)
+    assert np.array_equal(ref.cpu().numpy(), host_eta) and np.array_equal(mag.cpu().numpy(), host_mag)
+    bad = prev_idx.copy()
+    bad[7, 1] = 90                                                            # needs 31 nodes, the parent curve has 21
+    assert call(t(bad)) == 1
+    with pytest.raises(ValueError, match="fewer nodes"):
+        m.eta_ftl_batch(bad, new_idx, dth, g, off, want_ftl=False)           # host buffers: the call itself fails
+    assert call(pid) == 0                                                     # the flag is per call
