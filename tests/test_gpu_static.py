@@ -80,8 +80,37 @@ def test_solve_g_golden(gs, name):
     assert m.last_solution["success"]
 
 
+def _bucket_check(m, s, idx, th, one_step_rule, seed, label):
+    """GPU solve vs the oracle's hybrd, per bucket (tests/static_parity.py), bounded by the oracle's OWN sensitivity: the
+    same comparison of the oracle with itself from an initial guess perturbed by 1e-13, measured here.  No fixed
+    threshold below 1: where the oracle is insensitive, every configuration has to land on its root."""
+    import static_parity as sp
+    from oracle import oracle as orc
+    B = idx.shape[0]
+    res = m.solve_g_batch(idx, th)
+    o = orc.static_batch(s, idx, th, one_step_rule=one_step_rule, want_residual=True)
+    x0 = orc.static_init_guess(s)
+    x0p = x0[None, :] * (1.0 + 1e-13 * np.random.default_rng(seed).standard_normal((B, x0.size)))
+    op = orc.static_batch(s, idx, th, one_step_rule=one_step_rule, x0=x0p)
+    allc = np.ones(B, bool)
+    rg = sp.rates(sp.buckets(res["solution"], res["info"], o["solution"], o["info"]), allc)
+    ro = sp.rates(sp.buckets(op["solution"], op["info"], o["solution"], o["info"]), allc)
+    print(f"{label}: gpu vs oracle {rg}; oracle vs itself (1e-13) {ro}")
+    assert 1.0 - rg["A"] - rg["N"] <= 2.0 * (1.0 - ro["A"] - ro["N"]) + 0.005, (label, rg, ro)
+    assert rg["F"] <= 2.0 * ro["F"] + 0.005, (label, rg, ro)
+    # whatever the bucket: a converged GPU solve is a root of the oracle's marched residual
+    conv = res["converged"] & np.all(np.isfinite(res["solution"]), axis=1)
+    f_gpu = sp.residual_norms(orc, s, idx[conv], th[conv], res["solution"][conv])
+    f_orc = np.linalg.norm(o["residual"], axis=1)[o["info"] == 1]
+    assert np.quantile(f_gpu, 0.99) <= 10.0 * np.quantile(f_orc, 0.99) and np.median(f_gpu) <= 2.0 * np.median(f_orc)
+    # same root => same curves to the solver tolerance, same evaluation count
+    same = sp.buckets(res["solution"], res["info"], o["solution"], o["info"])["A"]
+    assert np.median(np.abs(res["nfev"][same] - o["nfev"][same])) <= 1
+    return res, o, same
+
+
 def test_random_batch_vs_oracle():
-    """300 random C1 configurations: converged flags and roots vs the CPU oracle's literal hybrd."""
+    """300 random C1 configurations (two tubes, configuration/config.yaml as a static model), >= 3 nodes per section."""
     from oracle import oracle as orc
     name = "c1_two_tube"
     m, s = gpu_static(name), orc_static(name)
@@ -89,31 +118,20 @@ def test_random_batch_vs_oracle():
     B = 300
     idx = rng.integers(0, 118, (B, 2)).astype(np.int32)   # >= 3 nodes per section
     th = rng.uniform(0, 2 * np.pi, (B, 2))
-    res = m.solve_g_batch(idx, th)
-    agree_flag, agree_root, worst_g = 0, 0, 0.0
-    for b in range(B):
-        g, sol, nfev, info = orc.static_solve_g(s, idx[b], th[b])
-        agree_flag += (info == 1) == bool(res["converged"][b])
-        if info == 1 and res["converged"][b]:
-            same = np.max(np.abs(sol - res["solution"][b])) <= 1e-5 * max(1.0, np.max(np.abs(sol)))
-            agree_root += same
-            if same:
-                lo, hi = res["offsets"][b * 2], res["offsets"][b * 2 + 2]
-                worst_g = max(worst_g, rel_err(res["g"][lo:hi], np.concatenate(g, 0)))
-    assert agree_flag >= 0.98 * B, agree_flag
-    # The equilibrium is multi-stable and hybrd's path is chaotic in its input: perturbing the initial guess by
-    # 1e-13 (relative) moves the ORACLE itself to a different equilibrium in 13 of these 292 configurations
-    # (DESIGN.md section 8).  The closed-form residual differs from the marched one by ~1e-13, so the same
-    # fraction (measured: 15 of 292) lands on another equilibrium here; everything else must be the same root.
-    assert agree_root >= 0.90 * res["converged"].sum(), (agree_root, res["converged"].sum())
+    res, o, same = _bucket_check(m, s, idx, th, 0, 1, "C1 well-posed")
+    worst_g = 0.0
+    for b in np.flatnonzero(same)[::3]:
+        g = orc.static_curves(s, idx[b], th[b], o["solution"][b])
+        lo, hi = res["offsets"][b * 2], res["offsets"][b * 2 + 2]
+        worst_g = max(worst_g, rel_err(res["g"][lo:hi], np.concatenate(g, 0)))
     assert worst_g < 1e-4, worst_g  # both stopped at xtol = 1.49e-8: curves agree to the solver tolerance
 
 
 def test_random_three_tube_batch_vs_oracle():
-    """600 random C3 configurations (BASELINE configs[2]'s model), exposure 2-12 nodes per tube, i.e. the
-    configurations the explicit-inverse kernel solves itself: converged flag, root and evaluation count against the
-    CPU oracle's literal hybrd; then the same batch with one-step sections mixed in, which must come back through the
-    QR kernel with the flag the oracle reports in all but the chaotic cases."""
+    """600 random C3 configurations (BASELINE configs[2]'s model), exposure 2-12 nodes per tube, then the same batch with
+    one-step sections mixed in: by default those are solved on the reduced system (against the oracle's hybrd on that
+    system), with ctx option static_one_step = 1 they go to the QR kernel, MINPACK's literal treatment (against the
+    oracle's literal hybrd, where only the converged flag can be compared: its null-space component is rounding noise)."""
     from oracle import oracle as orc
     name = "c3_three_tube"
     m, s = gpu_static(name), orc_static(name)
@@ -123,38 +141,24 @@ def test_random_three_tube_batch_vs_oracle():
     e = rng.integers(2, 13, (B, 3))
     idx = (N[None, :] - 1 - e).astype(np.int32)
     th = rng.uniform(0, 2 * np.pi, (B, 3))
-    res = m.solve_g_batch(idx, th)
+    _bucket_check(m, s, idx, th, 0, 2, "C3 well-posed")
     assert m.ctx.static_fallbacks() <= 0.02 * B          # a numerically singular Jacobian is the exception here
-    flag = root = 0
-    nfev_gap = []
-    for b in range(B):
-        _, sol, nfev, info = orc.static_solve_g(s, idx[b], th[b])
-        flag += (info == 1) == bool(res["converged"][b])
-        if info == 1 and res["converged"][b]:
-            root += np.max(np.abs(sol - res["solution"][b])) <= 1e-5 * max(1.0, np.max(np.abs(sol)))
-            nfev_gap.append(abs(int(res["nfev"][b]) - nfev))
-    assert flag >= 0.98 * B, flag
-    assert root >= 0.97 * res["converged"].sum(), (root, res["converged"].sum())
-    assert np.median(nfev_gap) <= 1, np.median(nfev_gap)  # same path: same number of residual evaluations
-    # one-step sections.  Default: solved by the explicit-inverse kernel on the reduced system -- same root as the oracle's
-    # hybrd on that system; ctx option static_one_step = 1: handed to the QR kernel, MINPACK's literal treatment, where only
-    # the converged flag can be compared (the null-space component is decided by rounding)
     e[::3, rng.integers(0, 2)] = 1
     idx = (N[None, :] - 1 - e).astype(np.int32)
-    sub = np.arange(0, B, 3)
-    res = m.solve_g_batch(idx, th)
+    _bucket_check(m, s, idx, th, 1, 3, "C3 with one-step sections, reduced-system rule")
     assert m.ctx.static_fallbacks() <= 0.02 * B
-    o1 = orc.static_batch(s, idx[sub], th[sub], one_step_rule=1)
-    both = (o1["info"] == 1) & res["converged"][sub]
-    same = np.abs(o1["solution"] - res["solution"][sub]).max(1) <= 1e-5 * np.maximum(1.0, np.abs(o1["solution"]).max(1))
-    assert ((o1["info"] == 1) == res["converged"][sub]).mean() >= 0.97
-    assert same[both].mean() >= 0.93, same[both].mean()
     with m.ctx.options(static_one_step=1):
         res = m.solve_g_batch(idx, th)
         assert m.ctx.static_fallbacks() >= B // 3
     assert np.all(res["info"] >= 1) and np.all(res["nfev"] >= 31) and np.all(np.isfinite(res["solution"]))
-    agree = sum((orc.static_solve_g(s, idx[b], th[b])[3] == 1) == bool(res["converged"][b]) for b in range(0, B, 3))
-    assert agree >= 0.9 * (B // 3), agree
+    sub = np.arange(0, B, 3)
+    o0 = orc.static_batch(s, idx[sub], th[sub], one_step_rule=0)
+    x0 = orc.static_init_guess(s)
+    o0p = orc.static_batch(s, idx[sub], th[sub], one_step_rule=0,
+                           x0=x0[None, :] * (1.0 + 1e-13 * np.random.default_rng(4).standard_normal((sub.size, x0.size))))
+    flag_gpu = np.mean((o0["info"] == 1) != res["converged"][sub])
+    flag_self = np.mean((o0["info"] == 1) != (o0p["info"] == 1))
+    assert flag_gpu <= 2.0 * flag_self + 0.02, (flag_gpu, flag_self)
 
 
 def test_static_fused_eval():

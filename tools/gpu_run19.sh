@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-(timeout 900 python -m pytest tests/test_gpu_kinematic.py tests/test_abi.py -m gpu -q -x 2>&1 | tail -5)
+(timeout 900 python -m pytest tests/test_gpu_static.py -q -x -s 2>&1 | grep "gpu vs oracle\|passed\|failed\|Error\|assert" | cut -c1-700)
