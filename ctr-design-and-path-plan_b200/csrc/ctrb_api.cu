@@ -932,10 +932,83 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
     CTRB_REQUIRE(idx && theta && rad && obstacle_min && goal_dist, "NULL buffer");
     const int T = m->mc.T;
     const size_t n = (size_t)B * T;
-    // (no chunk pipeline here: the solve is ~200 ns per configuration against ~1 ns of copies, and launches over
-    // fewer configurations lose more to the tails of the fast / QR / curves / collision kernels than the overlap gains;
-    // measured 3.2 M instead of 4.7 M configs/s end to end with eight chunks)
-    if (mem == CTRB_MEM_HOST) {
+    // The ragged offsets and the curves live on the device only.  The collision kernel reads node positions, so the curves
+    // kernel writes positions (24 B per node, not 128).  Their scratch is sized for the longest possible curves
+    // (every tube fully exposed), not from the batch's own node count: reading that count back would be a hidden
+    // synchronisation in CTRB_MEM_DEVICE mode.  The scratch is bounded at 64 GiB of the 180: larger batches run as
+    // consecutive launch sequences on the stream (C3: 201 nodes x 24 B per configuration -> up to 14.2 M configurations
+    // per sequence, so BASELINE's 10^7 is one).
+    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 11, 0, sizeof(unsigned long long), ctx->stream));
+    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 16, 0, 6 * sizeof(unsigned long long), ctx->stream));
+    const int64_t per_cfg = (int64_t)m->mc.total_nodes * 3 * (int64_t)sizeof(double);
+    const int64_t seq_max = std::max<int64_t>(((int64_t)64 << 30) / per_cfg, 1 << 16);
+    // one launch sequence (offset scan, solve, curves, collision + cost) over nb configurations in device memory
+    auto run = [&](int64_t nb, const int32_t* di, const double* dt, double* dob, double* dgo, double* dco, uint8_t* dcl,
+                   int32_t* dinf, int32_t* dnf) -> int {
+        const int64_t CH = std::min<int64_t>(nb, seq_max);
+        void* doff = nullptr;
+        int rc = ctx_scratch(ctx, 9, ((size_t)CH * T + 1) * sizeof(long long), &doff);
+        if (rc) return rc;
+        void* dg = nullptr;
+        rc = ctx_scratch(ctx, 10, (size_t)CH * m->mc.total_nodes * 3 * sizeof(double), &dg);
+        if (rc) return rc;
+        for (int64_t b0 = 0; b0 < nb; b0 += CH) {
+            const int64_t k = std::min(CH, nb - b0);
+            rc = launch_offsets(ctx, m, k, di + b0 * T, 0, (long long*)doff);
+            if (rc) return rc;
+            rc = launch_static_solve(ctx, m->sm, k, di + b0 * T, dt + b0 * T, nullptr, 0, 0.0, (const long long*)doff, (double*)dg,
+                                     nullptr, dnf ? dnf + b0 : nullptr, dinf ? dinf + b0 : nullptr,
+                                     // node positions: one thread per configuration when there are enough configurations to
+                                     // fill the machine with threads, the warp-per-configuration scan otherwise (a thread walks
+                                     // up to total_nodes Magnus steps serially: 0.5 ms of latency on a 1024-configuration batch)
+                                     (ctx->opt[CTRB_OPT_STATIC_CURVES_SCAN] || k < 65536) ? 2 : 1);
+            if (rc) return rc;
+            rc = launch_eval_curves_cost(ctx, env, cd, k, T, (const double*)dg, (const long long*)doff, m->mc.total_nodes, rad,
+                                         dob + b0, dgo + b0, dco ? dco + b0 : nullptr, dcl ? dcl + b0 : nullptr, 1);
+            if (rc) return rc;
+        }
+        return (int)CTRB_OK;
+    };
+    if (mem == CTRB_MEM_DEVICE) return run(B, idx, theta, obstacle_min, goal_dist, cost, collide, info, nfev);
+    // Host buffers, large batch: a copy / compute pipeline over a few chunks (the copies are 2.7 % of the call at 10^7
+    // configurations; chunks stay at 2^21 or more, so that the kernels' tails -- ~1.5 ms per sequence -- cost less than the
+    // overlap gains).  Smaller batches: one sequence (eight chunks of 2^17 measured 3.2 M instead of 4.7 M configs/s in round 1).
+    if (B >= ((int64_t)1 << 22)) {
+        const int64_t CH = std::min<int64_t>(std::max<int64_t>((B + 3) / 4, (int64_t)1 << 21), seq_max);
+        void* d[2][8];
+        const size_t sz[8] = {(size_t)CH * T * sizeof(int32_t), (size_t)CH * T * sizeof(double), (size_t)CH * sizeof(double),
+                              (size_t)CH * sizeof(double), (size_t)CH * sizeof(double), (size_t)CH, (size_t)CH * sizeof(int32_t),
+                              (size_t)CH * sizeof(int32_t)};
+        for (int p = 0; p < 2; ++p)
+            for (int k = 0; k < 8; ++k) {
+                int rc = ctx_scratch(ctx, (p ? 17 : 1) + k, sz[k], &d[p][k]);
+                if (rc) return rc;
+            }
+        return host_pipeline(
+            ctx, B, CH,
+            [&](int64_t b0, int64_t nb, int p, cudaStream_t s) -> int {
+                int rc = check_idx_host(m, nb, idx + b0 * T, b0);
+                if (rc) return rc;
+                CTRB_COPY(d[p][0], idx + b0 * T, (size_t)nb * T * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+                CTRB_COPY(d[p][1], theta + b0 * T, (size_t)nb * T * sizeof(double), cudaMemcpyHostToDevice, s);
+                return (int)CTRB_OK;
+            },
+            [&](int64_t, int64_t nb, int p) -> int {
+                return run(nb, (const int32_t*)d[p][0], (const double*)d[p][1], (double*)d[p][2], (double*)d[p][3],
+                           cost ? (double*)d[p][4] : nullptr, collide ? (uint8_t*)d[p][5] : nullptr,
+                           info ? (int32_t*)d[p][6] : nullptr, nfev ? (int32_t*)d[p][7] : nullptr);
+            },
+            [&](int64_t b0, int64_t nb, int p, cudaStream_t s) -> int {
+                CTRB_COPY(obstacle_min + b0, d[p][2], (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, s);
+                CTRB_COPY(goal_dist + b0, d[p][3], (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, s);
+                if (cost) CTRB_COPY(cost + b0, d[p][4], (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, s);
+                if (collide) CTRB_COPY(collide + b0, d[p][5], (size_t)nb, cudaMemcpyDeviceToHost, s);
+                if (info) CTRB_COPY(info + b0, d[p][6], (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+                if (nfev) CTRB_COPY(nfev + b0, d[p][7], (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+                return (int)CTRB_OK;
+            });
+    }
+    {
         int rc = check_idx_host(m, B, idx);
         if (rc) return rc;
     }
@@ -949,37 +1022,8 @@ int ctrb_static_eval_batch(ctrb_ctx* ctx, const ctrb_model* m, const ctrb_env* e
     int32_t* dinf = st.out(info, (size_t)B, mem);
     int32_t* dnf = st.out(nfev, (size_t)B, mem);
     if (st.rc) return st.rc;
-    // The ragged offsets and the curves live on the device only.  The collision kernel reads node positions, so the curves
-    // kernel writes positions (24 B per node, not 128).  Their scratch is sized for the longest possible curves
-    // (every tube fully exposed), not from the batch's own node count: reading that count back would be a hidden
-    // synchronisation in CTRB_MEM_DEVICE mode.  The scratch is bounded at 64 GiB of the 180: larger batches run as
-    // consecutive launch sequences on the stream (C3: 201 nodes x 24 B per configuration -> up to 14.2 M configurations
-    // per sequence, so BASELINE's 10^7 is one).
-    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 11, 0, sizeof(unsigned long long), ctx->stream));
-    CTRB_CUDA(cudaMemsetAsync(ctx->d_counters + 16, 0, 6 * sizeof(unsigned long long), ctx->stream));
-    const int64_t per_cfg = (int64_t)m->mc.total_nodes * 3 * (int64_t)sizeof(double);
-    const int64_t CH = std::min<int64_t>(B, std::max<int64_t>(((int64_t)64 << 30) / per_cfg, 1 << 16));
-    void* doff = nullptr;
-    int rc = ctx_scratch(ctx, 9, ((size_t)CH * T + 1) * sizeof(long long), &doff);
+    int rc = run(B, di, dt, dob, dgo, dco, dcl, dinf, dnf);
     if (rc) return rc;
-    void* dg = nullptr;
-    rc = ctx_scratch(ctx, 10, (size_t)CH * m->mc.total_nodes * 3 * sizeof(double), &dg);
-    if (rc) return rc;
-    for (int64_t b0 = 0; b0 < B; b0 += CH) {
-        const int64_t nb = std::min(CH, B - b0);
-        rc = launch_offsets(ctx, m, nb, di + b0 * T, 0, (long long*)doff);
-        if (rc) return rc;
-        rc = launch_static_solve(ctx, m->sm, nb, di + b0 * T, dt + b0 * T, nullptr, 0, 0.0, (const long long*)doff, (double*)dg,
-                                 nullptr, dnf ? dnf + b0 : nullptr, dinf ? dinf + b0 : nullptr,
-                                 // node positions: one thread per configuration when there are enough configurations to fill
-                                 // the machine with threads, the warp-per-configuration scan otherwise (a thread walks up to
-                                 // total_nodes Magnus steps serially: 0.5 ms of latency on a 1024-configuration batch)
-                                 (ctx->opt[CTRB_OPT_STATIC_CURVES_SCAN] || nb < 65536) ? 2 : 1);
-        if (rc) return rc;
-        rc = launch_eval_curves_cost(ctx, env, cd, nb, T, (const double*)dg, (const long long*)doff, m->mc.total_nodes, rad,
-                                     dob + b0, dgo + b0, dco ? dco + b0 : nullptr, dcl ? dcl + b0 : nullptr, 1);
-        if (rc) return rc;
-    }
     st.back(obstacle_min, dob, (size_t)B, mem);
     st.back(goal_dist, dgo, (size_t)B, mem);
     st.back(cost, dco, (size_t)B, mem);

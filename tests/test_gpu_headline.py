@@ -304,3 +304,35 @@ def test_static_eval_device_mode_does_not_synchronise():
             assert torch.equal(a, b) or torch.allclose(a, b, equal_nan=True)
     finally:
         ctx.set_stream(None)
+
+
+def test_static_host_memory_pipeline_equals_device_path():
+    """ctrb_static_eval_batch(CTRB_MEM_HOST) on 2^22 or more configurations runs as a copy / compute pipeline over chunks
+    (two streams, two sets of staging buffers): identical outputs to the single-sequence device path; a bad index in a late
+    chunk is still a ValueError that leaves the context usable."""
+    import ctypes as C
+    import torch
+    from ctrdapp_b200 import _lib as L
+    bench, orc, ms, cc, s, oenv = _objects()
+    dev = torch.device("cuda", 0)
+    B = (1 << 22) + 100_000                    # three chunks of 2^21, 2^21 and 100 000 (>= 65 536: the same curves kernel)
+    idx, theta = bench.make_inputs(B, 77, 1, 8)
+    a = cc.evaluate_batch(ms, idx, theta, RAD, goal_weight=GOAL_WEIGHT)          # host buffers: pipelined
+    info_a, nfev_a = cc.last_static["info"].copy(), cc.last_static["nfev"].copy()
+    idx_d, th_d = torch.from_numpy(idx).to(dev), torch.from_numpy(theta).to(dev)
+    outs = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(3)] + [torch.empty(B, dtype=torch.uint8, device=dev)] \
+        + [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)]
+    cd = L.CostDesc(L.COST_TYPES["square_obstacle_avg_plus_weighted_goal"], GOAL_WEIGHT, 1, 0.0)
+    rad = np.ascontiguousarray(RAD, np.float64)
+    L.check(L.lib().ctrb_static_eval_batch(ms.ctx.handle, ms.handle, cc.handle, C.byref(cd), B, L.ptr(idx_d), L.ptr(th_d),
+                                           L.ptr(rad), *[L.ptr(o) for o in outs], L.MEM_DEVICE))
+    ms.ctx.synchronize()
+    for host, d in zip(list(a) + [info_a, nfev_a], outs):
+        assert np.array_equal(host, d.cpu().numpy(), equal_nan=True)
+    bad = idx.copy()
+    bad[B - 5, 1] = 10_000
+    with pytest.raises(ValueError, match="outside"):
+        cc.evaluate_batch(ms, bad, theta, RAD, goal_weight=GOAL_WEIGHT)
+    small = cc.evaluate_batch(ms, idx[:1000], theta[:1000], RAD, goal_weight=GOAL_WEIGHT)   # the context still works
+    assert np.array_equal(small[3], a[3][:1000])         # (a batch this small takes the scan curves kernel: last-bit differences)
+    np.testing.assert_allclose(small[0], a[0][:1000], rtol=1e-9)
