@@ -183,8 +183,24 @@ def test_batched_search_invariants(solver, tmp_path):
     s.save_tree(tmp_path)
     lines = (tmp_path / "tree.txt").read_text().splitlines()
     assert len(lines) == len(s.tree.nodes) and lines[0].startswith("0 | 0, 0, 0 | 0, 0, 0 | None | ")
+    # every line in the reference's format (dynamic_tree.py:328-355): "i | ins, .. | rot, .. | parent | cost | at_goal"
+    import re
+    num = r"-?\d+(?:\.\d+)?(?:e[+-]?\d+)?"
+    line_re = re.compile(rf"^(\d+) \| {num}(?:, {num}){{2}} \| {num}(?:, {num}){{2}} \| (None|\d+) \| ({num}|inf|nan) \| (True|False)$")
+    for k, ln in enumerate(lines):
+        mt = line_re.match(ln)
+        assert mt and int(mt.group(1)) == k, ln
+        assert (mt.group(2) == "None") == (k == 0)       # (RRT* rewiring can hang a node under a later one)
+        assert mt.group(2) == "None" or int(mt.group(2)) == s.tree.nodes[k].parent
+        assert float(mt.group(3)) == pytest.approx(s.tree.nodes[k].heuristic.get_cost(), rel=1e-12, nan_ok=True)
+        assert (mt.group(4) == "True") == (k in s.tree.at_goal)
     s.save_best_solution(tmp_path)
-    assert (tmp_path / "solution_path.txt").read_text().startswith("Q: ")
+    sol = (tmp_path / "solution_path.txt").read_text().split("\n")   # rrt.py:184-198: "Q: ..", "Cost: ..", the index chain
+    assert len(sol) == 3 and sol[0] == f"Q: {m.q}" and sol[1].startswith("Cost: ")
+    cost, best = s.get_best_cost()
+    assert float(sol[1][6:]) == pytest.approx(cost)
+    chain = [int(v) for v in sol[2].split(", ")]
+    assert chain[0] == 0 and chain[-1] == best and all(s.tree.nodes[b].parent == a for a, b in zip(chain, chain[1:]))
     # the reference's writer -> the reference's reader: integer tube lengths and delta_x give integer insertions
     # ("3, 6, 9", kinematic.py:74-78), which TreeFromFile parses back (tree_from_file.py:28) and re-solves
     import os
