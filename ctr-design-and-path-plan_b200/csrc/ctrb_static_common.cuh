@@ -23,6 +23,14 @@ constexpr int kFdjNormUnroll = CTRB_FDJ_NORM_UNROLL;  // column-norm loop of war
 #define CTRB_NODE_OUT_UNROLL 3
 #endif
 constexpr int kNodeOutUnroll = CTRB_NODE_OUT_UNROLL;  // node_sec12's loop over the three powers of x
+#ifndef CTRB_WARP_SUM_UNROLL
+#define CTRB_WARP_SUM_UNROLL 5
+#endif
+constexpr int kWarpSumUnroll = CTRB_WARP_SUM_UNROLL;  // the butterfly of warp_sum
+#ifndef CTRB_ASM_UNROLL
+#define CTRB_ASM_UNROLL 2
+#endif
+constexpr int kAsmUnroll = CTRB_ASM_UNROLL;  // asm_part's loop over the two Gauss abscissae
 
 // The model constants as every device function below reads them: a block-wide shared-memory copy that each kernel
 // fills first (load_model).  Through the kernel parameter (a generic pointer once it crosses an out-of-line call)
@@ -325,7 +333,7 @@ __device__ __noinline__ void node_sec3(const StModel& sm_, const StCfg& c, QV q,
 }
 
 __device__ __noinline__ double warp_sum(double v) {
-#pragma unroll
+#pragma unroll(kWarpSumUnroll)
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
 }
@@ -493,7 +501,7 @@ __device__ __forceinline__ void pin_row_meta(const StModel& sm_, unsigned pin, i
 __device__ __forceinline__ double asm_part(const StCfg& c, const double (*yb)[16], int base, int sec, int off) {
     if (!(c.len[sec] > 0.0)) return 0.0;
     double acc = 0.0;
-#pragma unroll
+#pragma unroll(kAsmUnroll)
     for (int a = 0; a < 2; ++a) {
         const double ylo = yb[base + a * 2 + 0][off], yhi = yb[base + a * 2 + 1][off];
         acc += 0.5 * ((yhi - ylo) * c.wq[sec][a] + ylo);

@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 for v in default $(ls build/variants/ 2>/dev/null); do
   if [ "$v" == "default" ]; then unset CTRB200_LIB; else export CTRB200_LIB=$GRAFT_REPO_ROOT/build/variants/$v; fi
   echo "== $v"
-  python tools/perf_static3.py 1048576 1:8 2:8 1:33 2>&1 | grep -v "one_step_option\": 1" | python -c "
+  python tools/perf_static3.py 1048576 1:8 2:8 2>&1 | grep -v "one_step_option\": 1" | python -c "
 import sys, json
 for l in sys.stdin:
     try: d=json.loads(l)
