@@ -13,10 +13,13 @@
 // variant follows the literal hybrd as closely as hybrd follows itself under a 1e-13 perturbation of its
 // initial guess.
 //
-// What it cannot do is MINPACK's treatment of a singular R (a zero diagonal is replaced by eps * |column|):
-// a one-step section makes two Jacobian columns identical.  The Gauss-Jordan inversion
-// detects that (pivot below 1e-12 of the column norm) and the configuration is appended to a fallback list
-// that static_solve_kernel -- the literal QR algorithm -- solves in the same launch sequence.
+// What it cannot do is MINPACK's treatment of a singular R (a zero diagonal is replaced by eps * |column|).  A
+// configuration whose Jacobian the Gauss-Jordan inversion finds singular (pivot below 1e-12 of the column norm: in
+// practice a forward-difference column that vanished because hybrd's step h = eps |x_j| underflowed against the other
+// terms) is appended to a fallback list that static_solve_kernel -- the literal QR algorithm -- solves in the same launch
+// sequence; so is one with a zero-length section.  One-step sections, whose x and x^2 curvature columns are proportional
+// (SURVEY App. B#5), are solved HERE on the reduced system (pin_mask in ctrb_static_common.cuh) unless the caller asks for
+// MINPACK's literal treatment of them (CTRB_OPT_STATIC_ONE_STEP = 1: they then go to the QR kernel).
 //
 // The forward-difference Jacobian uses the block structure of the residual: perturbing an unknown of block
 // (tube, section) only changes the node integrands of that section (and of section 2 for the (3,1) torsion,
