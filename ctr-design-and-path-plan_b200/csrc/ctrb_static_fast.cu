@@ -409,7 +409,9 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
             }
             const double p_l = act ? -step : 0.0;
             const double xt_l = x_l + p_l;
-            const double pnorm = wnorm(diag_l * p_l);
+            // inside the trust region p = -(H f), so |D p| is |D (H f)| = qnorm to the bit: one warp reduction less
+            // (measured: 92.0 -> 89.3 ms per 2^20 shallow configurations)
+            const double pnorm = (qnorm <= delta) ? qnorm : wnorm(diag_l * p_l);
             if (iter == 1) delta = fmin(delta, pnorm);
             if (act) {
                 M.va[lane] = p_l;
@@ -418,13 +420,30 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
             __syncwarp();
             double qa, qb;
             const double fn_l = warp_residual(sm, M.cfg, M.y, M.vb, rm, act, lane, nnodes, &qa, &qb);
+            // Everything the rest of the iteration reduces over the warp is known here: |f+|, |f + J p|, |D x+| and v.(H u) of the
+            // Sherman-Morrison denominator (the Broyden vectors only need f+, J p and |D p|).  One four-value butterfly instead of
+            // four chains of five dependent shuffle-add steps; the two products with H move ahead of the acceptance test (wasted
+            // in the last iteration and when the Jacobian is re-evaluated).  Same sums, same order: bit-identical results (checked on
+            // 2^20 configurations), 89.3 -> 88.2 ms.
             nfev++;
-            const double fnorm1 = wnorm(fn_l);
+            const double w3 = act ? f_l + matvec_row<N>(M.J, M.va, n, lane) : 0.0;  // f + J p
+            // Broyden vectors (hybrd: wa2 = (Q^T f+ - (Q^T f + R p)) / pnorm, wa1 = D ((D p) / pnorm))
+            const double ipn = 1.0 / pnorm;
+            const double u_l = act ? (fn_l - w3) * ipn : 0.0;
+            const double v_l = act ? diag_l * ((diag_l * p_l) * ipn) : 0.0;
+            if (act) {
+                M.vb[lane] = u_l;
+                M.vc[lane] = v_l;
+            }
+            __syncwarp();
+            const double Hu = act ? matvec_row<N>(M.H, M.vb, n, lane) : 0.0;
+            const double vH = act ? matvec_col<N>(M.H, M.vc, n, lane) : 0.0;
+            const D4 red = warp_sum4(fn_l * fn_l, w3 * w3, act ? (diag_l * xt_l) * (diag_l * xt_l) : 0.0, v_l * Hu);
+            const double fnorm1 = sqrt(red.a);
             if (!(fnorm1 < 1.7e308) || !(pnorm < 1.7e308)) return -5;  // non-finite: let the QR kernel decide
             double actred = -1.0;
             if (fnorm1 < fnorm) actred = 1 - (fnorm1 / fnorm) * (fnorm1 / fnorm);
-            const double w3 = act ? f_l + matvec_row<N>(M.J, M.va, n, lane) : 0.0;  // f + J p
-            const double temp = wnorm(w3);
+            const double temp = sqrt(red.b);
             double prered = 0.0;
             if (temp < fnorm) prered = 1 - (temp / fnorm) * (temp / fnorm);
             double ratio = 0.0;
@@ -439,10 +458,6 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
                 if (ratio >= p5 || ncsuc > 1) delta = fmax(delta, pnorm / p5);
                 if (fabs(ratio - 1) <= p1c) delta = pnorm / p5;
             }
-            // Broyden vectors (hybrd: wa2 = (Q^T f+ - (Q^T f + R p)) / pnorm, wa1 = D ((D p) / pnorm))
-            const double ipn = 1.0 / pnorm;
-            const double u_l = act ? (fn_l - w3) * ipn : 0.0;
-            const double v_l = act ? diag_l * ((diag_l * p_l) * ipn) : 0.0;
             if (ratio >= p0001) {  // successful iteration
                 x_l = xt_l;
                 f_l = fn_l;
@@ -452,7 +467,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
                     M.x[lane] = x_l;
                     M.f[lane] = f_l;
                 }
-                xnorm = sqrt(warp_sum(act ? (diag_l * x_l) * (diag_l * x_l) : 0.0) + c33);
+                xnorm = sqrt(red.c + c33);
                 fnorm = fnorm1;
                 iter++;
             }
@@ -474,14 +489,7 @@ __device__ __noinline__ int fast_hybrd(const StModel& sm_, FastMem& M, const Slo
             }
             if (ncfail == 2) break;  // recompute the Jacobian
             // ---- rank-one update of J and, by Sherman-Morrison, of H
-            if (act) {
-                M.vb[lane] = u_l;
-                M.vc[lane] = v_l;
-            }
-            __syncwarp();
-            const double Hu = act ? matvec_row<N>(M.H, M.vb, n, lane) : 0.0;
-            const double vH = act ? matvec_col<N>(M.H, M.vc, n, lane) : 0.0;
-            const double den = 1.0 + warp_sum(v_l * Hu);
+            const double den = 1.0 + red.d;
             if (!(fabs(den) > 1e-8) || !(fabs(den) < 1e100)) return -6;  // J+ is (numerically) singular
             __syncwarp();
             if (act) M.vb[lane] = vH;

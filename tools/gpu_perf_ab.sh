@@ -8,13 +8,13 @@ import sys, json
 for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: print(l.strip()[:300]); continue
-    print(d['case'], d['ms'], d['Mcfg_per_s'], 'fb', d['fallbacks'], 'conv', d['converged'], 'nfev', d['nfev']['mean'])
+    print(d['case'], d['ms'], d['Mcfg_per_s'], 'fb', d['fallbacks'], 'conv', d['converged'], 'nfev', d['nfev']['mean'], d.get('md5'))
 "
   true 2>&1 | grep -v "one_step_option\": 1" | python -c "
 import sys, json
 for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: print(l.strip()[:300]); continue
-    print(d['case'], d['ms'], d['Mcfg_per_s'], 'fb', d['fallbacks'], 'conv', d['converged'], 'nfev', d['nfev']['mean'])
+    print(d['case'], d['ms'], d['Mcfg_per_s'], 'fb', d['fallbacks'], 'conv', d['converged'], 'nfev', d['nfev']['mean'], d.get('md5'))
 "
 done

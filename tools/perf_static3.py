@@ -1,5 +1,6 @@
 """Device timing of the static solve per kernel (CUDA events inside the library) for both treatments of one-step
 sections, with the distribution of the evaluation counts.  usage: perf_static3.py [B] [case ...]   case = lo:hi"""
+import hashlib
 import json
 import pathlib
 import sys
@@ -34,5 +35,7 @@ for case in cases:
                "nfev": {"mean": round(float(nf.mean()), 1), "p50": int(np.median(nf)), "p99": int(np.quantile(nf, 0.99)), "max": int(nf.max()),
                         "mean_one_step": round(float(nf[short].mean()), 1) if short.any() else None,
                         "mean_other": round(float(nf[~short].mean()), 1)},
-               "info_hist": np.bincount(res["info"], minlength=6).tolist(), "fallback_reasons": m.ctx.static_fallback_reasons()}
+               "info_hist": np.bincount(res["info"], minlength=6).tolist(), "fallback_reasons": m.ctx.static_fallback_reasons(),
+               # bit-level fingerprint of the whole batch: kernel variants that only re-schedule the same arithmetic must agree
+               "md5": hashlib.md5(res["solution"].tobytes() + nf.tobytes() + res["info"].tobytes()).hexdigest()[:12]}
         print(json.dumps(out), flush=True)
