@@ -254,3 +254,24 @@ def test_block_structured_inverse_vs_gauss_jordan():
     assert same_flag >= 0.98 and same_nfev >= 0.95 and close >= 0.98, (same_flag, same_nfev, close)
     print("block vs Gauss-Jordan: same info %.4f, same nfev %.4f, same root %.4f" % (same_flag, same_nfev, close))
     assert a["converged"].mean() > 0.95 and abs(a["converged"].mean() - b["converged"].mean()) < 0.01
+
+
+def test_static_empty_and_invalid_batches():
+    """B = 0 through every static entry point (the reference has no batch; an empty list of candidates is what a
+    planner round without survivors hands over), and indices outside the tubes raise like the reference's IndexError path."""
+    from ctrdapp_b200.collision import CollisionChecker
+    m = gpu_static("c3_three_tube")
+    nq = m.num_unknowns
+    idx0, th0 = np.zeros((0, 3), np.int32), np.zeros((0, 3))
+    res = m.solve_g_batch(idx0, th0)
+    assert res["g"].shape == (0, 4, 4) and res["offsets"].tolist() == [0]
+    assert res["solution"].shape == (0, nq) and res["nfev"].shape == (0,) and res["info"].shape == (0,)
+    assert m.curves_batch(idx0, th0, np.zeros((0, nq)))["g"].shape == (0, 4, 4)
+    assert m.static_equilibrium_batch(idx0, th0, np.zeros((0, nq))).shape == (0, nq)
+    cc = CollisionChecker(FIXTURES / "env_c3_colon_straight.json", ctx=m.ctx)
+    out = cc.evaluate_batch(m, idx0, th0, [1.2, 0.9, 0.6])
+    assert all(len(o) == 0 for o in out) and cc.last_static["info"].shape == (0,)
+    with pytest.raises(ValueError):
+        m.solve_g_batch([[0, 0, 500]], [[0.0, 0.0, 0.0]])
+    with pytest.raises(ValueError):
+        cc.evaluate_batch(m, [[-1, 0, 0]], [[0.0, 0.0, 0.0]], [1.2, 0.9, 0.6])
