@@ -215,34 +215,10 @@ struct QV {
     double hp;
     __device__ __forceinline__ double operator()(int k) const { return k == jp ? q[k] + hp : q[k]; }
 };
-// the same vector for a caller that knows at compile time that nothing is displaced (kPert = false: plain reads)
-template <bool kPert>
-struct QVT {
-    const double* q;
-    int jp;
-    double hp;
-    __device__ __forceinline__ double operator()(int k) const { return (kPert && k == jp) ? q[k] + hp : q[k]; }
-};
-template <class Q>
-__device__ __forceinline__ double poly3v(Q q, int o, double x) { return q(o) + q(o + 1) * x + q(o + 2) * (x * x); }
-template <class Q>
-__device__ __forceinline__ double ipoly3v(Q q, int o, double X) {
+__device__ __forceinline__ double poly3v(QV q, int o, double x) { return q(o) + q(o + 1) * x + q(o + 2) * (x * x); }
+__device__ __forceinline__ double ipoly3v(QV q, int o, double X) {
     return q(o) * X + q(o + 1) * (0.5 * X * X) + q(o + 2) * (X * X * X * (1.0 / 3.0));
 }
-// CTRB_NODE_SPLIT = 1: the residual at an iterate (nothing displaced) runs its own copy of the node routines without the
-// per-read select; 0: one copy serves both (less code in a kernel that runs on instruction fetch)
-#ifndef CTRB_NODE_SPLIT
-#define CTRB_NODE_SPLIT 0
-#endif
-constexpr bool kNodeSplit = CTRB_NODE_SPLIT != 0;
-// CTRB_FDJ_RECIP = 1: the forward-difference quotient multiplies by 1 / h (one division per column, taken by the lane that
-// owns the column and broadcast) instead of dividing in every lane for every column: ~30 instructions less per Jacobian
-// entry, at most one ulp away from the quotient.  Measured per 2^20 shallow / well-posed configurations: 93.6 -> 91.7 ms /
-// 72.2 -> 70.6 ms.  (CTRB_NODE_SPLIT = 1 in the same run: 101.3 / 75.8 ms -- the second copy of the node routine costs more
-// in instruction fetch than the selects it saves.)
-#ifndef CTRB_FDJ_RECIP
-#define CTRB_FDJ_RECIP 1
-#endif
 // section 1 (static.py:261-345), three tubes; y = [intc1 (9), intg21 (3), intg31 (3)]
 // omega of tube n's own pre-curvature at absolute node `node` (get_ksi_star, static.py:618-634): per-design table,
 // or the formula when a derived section index runs outside the tube (negative idx21 / idx31 / idx32)
@@ -266,10 +242,9 @@ __device__ __forceinline__ V3 ksi_star_w(const StModel& sm_, int n, int node) {
 // same chain without a middle tube (zero stiffness, no torsion) whose rotation is the relative frame gg31 reached
 // at the end of section 1 (equilibrium_three's return value; identity for two tubes).
 //   sec 0: y = [intc1 (9), intg21 (3), intg31 (3)]      sec 1: y = [intc2 (9), intg32 (3), intg312 (3)]
-template <bool kShared = true, bool kPert = true>  // kShared: c, q and y live in shared memory (all callers but the scalar parity kernel)
-__device__ __noinline__ void node_sec12(const StModel& sm_, const StCfg& c, QV q_, int sec, int i, double y[15]) {
+template <bool kShared = true>  // kShared: c, q and y live in shared memory (all callers but the scalar parity kernel)
+__device__ __noinline__ void node_sec12(const StModel& sm_, const StCfg& c, QV q, int sec, int i, double y[15]) {
     CTRB_USE_SM;
-    const QVT<kPert> q{q_.q, q_.jp, q_.hp};
     if (kShared) {
         CTRB_IN_SHARED(&c);
         CTRB_IN_SHARED(q.q);
@@ -323,10 +298,9 @@ __device__ __noinline__ void node_sec12(const StModel& sm_, const StCfg& c, QV q
 
 // section 3 (static.py:438-452); y = intc3 (dof of the last tube): B^T K (B q33 - B q*) with the base's single
 // non-zero per column taken from the per-design table
-template <bool kShared = true, bool kPert = true>
-__device__ __noinline__ void node_sec3(const StModel& sm_, const StCfg& c, QV q_, int i, double y[CTRB_MAX_DOF]) {
+template <bool kShared = true>
+__device__ __noinline__ void node_sec3(const StModel& sm_, const StCfg& c, QV q, int i, double y[CTRB_MAX_DOF]) {
     CTRB_USE_SM;
-    const QVT<kPert> q{q_.q, q_.jp, q_.hp};
     if (kShared) {
         CTRB_IN_SHARED(&c);
         CTRB_IN_SHARED(q.q);
@@ -432,7 +406,6 @@ __device__ __noinline__ double enorm_w(int n, double v, const double* x_smem_or_
 
 // Cooperative residual, phase 1: work item t in 0..11 = (section, abscissa, bracket end) evaluates one node
 // integrand vector into y (shared memory).  q is a shared-memory vector of the unknowns.
-template <bool kPert = true>
 __device__ __noinline__ void res_node(const StModel& sm_, const StCfg& c, QV q, int t, double* y) {
     CTRB_USE_SM;
     CTRB_IN_SHARED(&c);
@@ -443,9 +416,9 @@ __device__ __noinline__ void res_node(const StModel& sm_, const StCfg& c, QV q, 
     if (c.len[sec] > 0.0 && (sec != 0 || T == 3)) {
         const int node = e ? c.hi[sec][a] : c.lo[sec][a];
         if (sec < 2) {
-            node_sec12<true, kPert>(sm, c, q, sec, node, y);
+            node_sec12(sm, c, q, sec, node, y);
         } else {
-            node_sec3<true, kPert>(sm, c, q, node, y);
+            node_sec3(sm, c, q, node, y);
         }
     } else {
 #pragma unroll 1
@@ -557,7 +530,7 @@ __device__ __forceinline__ double asm_part(const StCfg& c, const double (*yb)[16
 __device__ __forceinline__ double warp_residual(const StModel& sm_, const StCfg& cfg, double (*y)[16], const double* q,
                                                 const RowMeta& rm, bool act, int lane, int nnodes, double* p1, double* p2) {
     CTRB_USE_SM;
-    if (lane < nnodes) res_node<!kNodeSplit>(sm, cfg, QV{q, -1, 0.0}, lane, y[lane]);
+    if (lane < nnodes) res_node(sm, cfg, QV{q, -1, 0.0}, lane, y[lane]);
     __syncwarp();
     double a = 0.0, b = 0.0;
     if (act) {
@@ -642,14 +615,15 @@ __device__ __noinline__ double warp_fdjac(const StModel& sm_, const StCfg& cfg, 
     CTRB_USE_SM;
     const bool act = lane < n;
     const double eps = sqrt(DBL_EPSILON);
-#if CTRB_FDJ_RECIP
-    double rh_l = 0.0;  // 1 / h of column `lane`: one division per lane instead of one per column in every lane
+    // The quotient (F(x + h e_j) - F(x)) / h is taken as a product with 1 / h: one division per COLUMN (by the lane that owns
+    // it, broadcast below) instead of one per entry, at most one ulp away from the quotient.  The block structure makes most
+    // numerators exactly zero, and a zero numerator sends the IEEE division through its slow path.
+    double rh_l = 0.0;
     {
         double h = eps * fabs(act ? x[lane] : 0.0);
         if (h == 0.0) h = eps;
         rh_l = 1.0 / h;
     }
-#endif
     for (int base = 0; base < st.nslots; base += 8) {
         {
             const int slot = base + (lane >> 2);
@@ -669,9 +643,7 @@ __device__ __noinline__ double warp_fdjac(const StModel& sm_, const StCfg& cfg, 
             const int j = st.j[slot], sec = st.sec[slot];
             const bool pair = st.col_blk[j] == 2;  // (3,1) torsion: sections 1 and 2 both move; slots (s, s + 1)
             if (pair && sec == 1) continue;
-#if CTRB_FDJ_RECIP
             const double rh = __shfl_sync(0xffffffffu, rh_l, j);
-#endif
             if (act) {
                 const bool hit1 = rm.sec == sec || (pair && rm.sec == 1);
                 const bool hit2 = rm.blk == 2 && (sec == 1 || pair);
@@ -685,14 +657,7 @@ __device__ __noinline__ double warp_fdjac(const StModel& sm_, const StCfg& cfg, 
                         const double p2 = hit2 ? asm_part(cfg, yb, b2, 1, 12 + rm.k) : p2b;
                         Fp = p1 - p2;
                     }
-#if CTRB_FDJ_RECIP
                     val = (Fp - f_l) * rh;
-#else
-                    const double xv = x[j];
-                    double h = eps * fabs(xv);
-                    if (h == 0.0) h = eps;
-                    val = (Fp - f_l) / h;
-#endif
                 }
                 if ((pin >> j) & 1u) val = lane == j ? 1.0 : 0.0;  // pinned unknown: column e_j (its row is zero: scale 0)
                 J[lane + j * kJLD] = val;
