@@ -18,6 +18,7 @@ What is asserted (tests/static_parity.py has the bucket definitions):
      self-perturbation rate is measured and printed), so the statement is 3. plus the converged flag.
 """
 import json
+import os
 
 import numpy as np
 import pytest
@@ -45,6 +46,7 @@ def _objects():
 
 @pytest.mark.parametrize("lo,hi,B", [(1, 8, 50_000), (1, 33, 12_000)])
 def test_headline_static_parity(lo, hi, B):
+    B = int(os.environ.get("CTRB_HEADLINE_PARITY_B", B))  # a larger one-off run for profiles/ (the oracle needs ~0.3 ms per configuration)
     bench, orc, ms, cc, s, oenv = _objects()
     idx, theta = bench.make_inputs(B, 1003, lo, hi)        # bench.py's exact inputs (rank 0)
     N = np.asarray(bench.NPTS)
