@@ -77,6 +77,8 @@ class RRT(Solver):
     def _round(self, k):
         cands = self.calc_new_random_configs(k)
         result = self._integrate_and_check(cands)
+        cands["new_rotation_list"] = np.asarray(cands["new_rotation"]).tolist()  # once per round, not once per candidate
+        cands["neighbor_list"] = np.asarray(cands["neighbor"]).tolist()
         for c in range(k):
             self._consider(c, cands, result)
 
@@ -133,33 +135,30 @@ class RRT(Solver):
                 if need_g_out:
                     out["obs"][c], out["goal"][c] = self.cd.check_collision(g, self.tube_rad)
             return out
-        flats, offs, base = [], [0], 0
-        for c in range(k):
-            flat, counts = self._packed(parents[c])
-            flats.append(flat)
-            for n in counts:
-                base += n
-                offs.append(base)
-        prev_g = np.concatenate(flats, 0) if flats else np.zeros((0, 4, 4))
+        packed = [self._packed(p) for p in parents]          # (flat curve, nodes per tube) of every parent
+        prev_g = np.concatenate([f for f, _ in packed], 0) if packed else np.zeros((0, 4, 4))
+        offs_a = np.zeros(k * T + 1, np.int64)
+        if packed:
+            np.cumsum(np.asarray([n for _, n in packed], np.int64).ravel(), out=offs_a[1:])
         want_arrays = self._want_ftl_arrays()
         res = self.model.solve_integrate_batch(cands["delta_rotation"], cands["delta_insert"], cands["new_rotation"],
-                                               cands["new_insert"], prev_g, np.asarray(offs, np.int64),
+                                               cands["new_insert"], prev_g, offs_a,
                                                need_g_out=need_g_out, want_ftl=want_arrays)
+        # whole-array conversions once per round (indexing numpy scalars one by one is what this loop used to spend its time on)
+        out["insert_indices"] = res["insert_indices"].tolist()
+        out["true_insertion"] = res["true_insertions"].tolist()
+        out["ftl_mag"] = list(res["ftl_mag"])
         if need_g_out:
             obs, goal = self.cd.check_collision_batch(res["g"], res["offsets"], self.tube_rad, tube_num=T)
-        for c in range(k):
-            if need_g_out:
-                o = res["offsets"]
-                out["g"][c] = [res["g"][int(o[c * T + n]):int(o[c * T + n + 1])] for n in range(T)]
-                out["obs"][c], out["goal"][c] = float(obs[c]), float(goal[c])
-            out["insert_indices"][c] = res["insert_indices"][c].tolist()
-            out["true_insertion"][c] = res["true_insertions"][c].tolist()
-            out["ftl_mag"][c] = res["ftl_mag"][c]
-            if want_arrays:
-                # kin_eta_ftl_kernel writes npts - prev_idx rows per tube (kinematic.py:181-193); the parent's curve holds
-                # exactly that many nodes unless the index rounding moved (then the library reports an error)
-                need = [self.model.num_discrete_points[n] - int(res["prev_indices"][c][n]) for n in range(T)]
-                out["ftl"][c] = [res["ftl"][offs[c * T + n]:offs[c * T + n] + need[n]] for n in range(T)]
+            out["obs"], out["goal"] = obs.tolist(), goal.tolist()
+            o, g_all = res["offsets"].tolist(), res["g"]
+            out["g"] = [[g_all[o[b + n]:o[b + n + 1]] for n in range(T)] for b in range(0, k * T, T)]
+        if want_arrays:
+            # kin_eta_ftl_kernel writes npts - prev_idx rows per tube (kinematic.py:181-193); the parent's curve holds
+            # exactly that many nodes unless the index rounding moved (then the library reports an error)
+            offs, prev, npts = offs_a.tolist(), res["prev_indices"].tolist(), self.model.num_discrete_points
+            for c in range(k):
+                out["ftl"][c] = [res["ftl"][offs[c * T + n]:offs[c * T + n] + npts[n] - prev[c][n]] for n in range(T)]
         return out
 
     def _packed(self, node_index):
@@ -192,8 +191,9 @@ class RRT(Solver):
             goal_dist = 0
         true_insertion = result["true_insertion"][c]
         heuristic = self._make_heuristic(result, c, obs_min, goal_dist, self._insert_fraction(true_insertion))
-        self.tree.insert(true_insertion, cands["new_rotation"][c].tolist(), int(cands["neighbor"][c]), heuristic,
-                         result["g"][c], result["insert_indices"][c])
+        rotation = cands["new_rotation_list"][c] if "new_rotation_list" in cands else cands["new_rotation"][c].tolist()
+        parent = cands["neighbor_list"][c] if "neighbor_list" in cands else int(cands["neighbor"][c])
+        self.tree.insert(true_insertion, rotation, parent, heuristic, result["g"][c], result["insert_indices"][c])
 
     # ------------------------------------------------------------------ results (rrt.py:167-200)
     def get_path(self, index):
